@@ -1,0 +1,143 @@
+/*
+ * tgcn_b200.h -- C-ABI of the B200-native time-vertex Chebyshev graph-convolution path.
+ *
+ * Drop-in boundary for the hot path of cassianobecker/tgcn (`tgcn/nn/gcn.py`).  The
+ * reference has no FFI (it is pure Python over ATen); each entry point below names the
+ * reference code whose device work it replaces (file:line into the reference tree).
+ * Callers are the `torch.autograd.Function`s in `tgcn_b200/nn/functional.py` (ctypes), or any
+ * C/C++ host.  See INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all tensors are fp32, dense, contiguous; index arrays are int32;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (PyTorch: torch.cuda.current_stream().cuda_stream);
+ *   - every call is asynchronous on `stream`, never synchronises the device, never allocates or
+ *     frees device memory and is legal inside CUDA-graph stream capture;
+ *   - return value: 0 on success, <0 on error (TGCN_ERR_*); `tgcn_last_error()` returns the
+ *     message of the calling thread's last failure.  There is no CPU fallback.
+ *
+ * Shapes: Q batch, N vertices (padded), D = H*F features per vertex of
+ * the input signal (H = horizon, F = in_channels; H = 1 for the spatial-only layers), G =
+ * out_channels, K = filter order.  API tensors keep the reference layout x[Q,N,D], out[Q,N,G].
+ * Internally the signal is a vertex-major "slab" [N, C] with C = Q*D columns (column = q*D + d),
+ * so a neighbour row is one contiguous, coalesced C*4-byte read; the stacked basis is
+ * `stack[K][N][C]`.
+ */
+#ifndef TGCN_B200_H
+#define TGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGCN_OK 0
+#define TGCN_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, misaligned buffer) */
+#define TGCN_ERR_UNSUPPORTED (-2) /* shape outside what the kernels cover */
+#define TGCN_ERR_CUDA (-3)        /* a CUDA runtime call / kernel launch failed */
+
+/* bias_mode */
+#define TGCN_BIAS_NONE 0
+#define TGCN_BIAS_PER_VERTEX 1 /* bias[1,N,G]: TGCNCheb_H / TGCNCheb  (gcn.py:96, :22)  */
+#define TGCN_BIAS_PER_FILTER 2 /* bias[1,1,G]: GCNCheb                (gcn.py:172)      */
+
+/* recursion */
+#define TGCN_RECURSION_REFERENCE 0 /* Xt_k = 2 L^k X - Xt_{k-2}: what gcn.py:146-153 computes   */
+#define TGCN_RECURSION_CHEBYSHEV 1 /* T_k  = 2 L T_{k-1} - T_{k-2}: textbook recursion           */
+
+/* contraction engine */
+#define TGCN_ENGINE_AUTO 0
+#define TGCN_ENGINE_FFMA 1    /* fp32 CUDA-core path (exact fp32 accumulation)                  */
+#define TGCN_ENGINE_TCGEN05 2 /* tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulate in TMEM   */
+
+int tgcn_version(void);
+const char* tgcn_last_error(void);
+/* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
+int tgcn_device_supported(void);
+
+/* ---- layout ------------------------------------------------------------------------------ */
+/* x[Q,N,D] -> slab[N,Q,D]   (replaces X.permute(1,3,2,0).reshape(N,-1), gcn_matmul.py:152-153) */
+int tgcn_to_slab(const float* x, float* slab, int Q, int N, int D, void* stream);
+/* slab[N,Q,D] -> x[Q,N,D]   (replaces res.reshape(..).permute(3,0,2,1), gcn_matmul.py:155-156) */
+int tgcn_from_slab(const float* slab, float* x, int Q, int N, int D, void* stream);
+
+/* ---- K1: CSR SpMM recursion step ---------------------------------------------------------- */
+/* out[r,:] = alpha * sum_e val[e] * in[col[e],:] + beta * prev[r,:]   for r in [0,N), C columns.
+ * Replaces einsum("nm,qmhf->qnhf", L, X) + `2*X - Xt[k-2]` + the slab copy (gcn.py:147-153;
+ * torch.mm at gcn_matmul.py:154).  `prev` may be NULL (beta ignored) and may alias `out`;
+ * `in` must not alias `out`.  `in` may have more rows than N (halo rows of a row partition). */
+int tgcn_spmm_step(const int32_t* rowptr, const int32_t* col, const float* val, int N,
+                   const float* in, const float* prev, float* out, int64_t C,
+                   float alpha, float beta, void* stream);
+
+/* Whole basis: stack[0] = slab(x); stack[j] per `recursion` (REFERENCE: powers L^j x;
+ * CHEBYSHEV: T_j x).  Replaces `_time_chebyshev` / `_chebyshev` (gcn.py:126-154, :208-237, :52-79). */
+int tgcn_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int N,
+                    const float* x, float* stack, int Q, int D, int K, int recursion, void* stream);
+
+/* Stacked basis in the reference's own layout Xt[K,Q,N,D] from the internal stack
+ * (for callers of `layer._time_chebyshev(x)`): Xt_k = sum_j M[k,j] stack[j]. */
+int tgcn_basis_to_reference(const float* stack, float* Xt, int Q, int N, int D, int K,
+                            int recursion, void* stream);
+
+/* ---- weights ------------------------------------------------------------------------------ */
+/* REFERENCE recursion only: Wmix[j] = sum_k M[k,j] W[k]   (transpose=0, forward weights) or
+ * dW[k] = sum_j M[k,j] dWmix[j] (transpose=1, gradient), M from Xt_k = sum_j M[k,j] L^j X.
+ * `inner` = D*G elements per order.  CHEBYSHEV recursion: plain copy. */
+int tgcn_mix_weights(const float* src, float* dst, int K, int64_t inner, int recursion,
+                     int transpose, void* stream);
+
+/* ---- K2: weight contraction ---------------------------------------------------------------- */
+/* out[q,n,g] = sum_{j,d} stack[j][n][q*D+d] * Wmix[j][d][g] (+ bias)
+ * Replaces einsum("kqnhf,khfg->qng") + bias add (gcn.py:113-116, :39-42, :194-198). */
+int tgcn_contract_fwd(const float* stack, const float* Wmix, const float* bias, int bias_mode,
+                      float* out, int Q, int N, int D, int G, int K, int engine, void* stream);
+
+/* ---- K4: backward ------------------------------------------------------------------------ */
+/* Bytes of scratch the backward entry points need (deterministic two-pass reductions of dW / db). */
+int64_t tgcn_contract_bwd_w_workspace(int Q, int N, int D, int G, int K);
+/* dWmix[j][d][g] = sum_{n,q} stack[j][n][q*D+d] * dout[q,n,g]   (autograd of gcn.py:113). */
+int tgcn_contract_bwd_w(const float* stack, const float* dout, float* dWmix, void* workspace,
+                        int Q, int N, int D, int G, int K, int engine, void* stream);
+/* gstack[j][n][q*D+d] = sum_g dout[q,n,g] * Wmix[j][d][g]     (autograd of gcn.py:113 w.r.t. Xt) */
+int tgcn_contract_bwd_x(const float* dout, const float* Wmix, float* gstack,
+                        int Q, int N, int D, int G, int K, int engine, void* stream);
+/* dx[Q,N,D] from gstack (destroyed) through the adjoint recursion with L^T given as CSR
+ * (autograd of gcn.py:146-153). */
+int tgcn_cheb_adjoint(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N,
+                      float* gstack, float* dx, int Q, int D, int K, int recursion, void* stream);
+/* db: per-vertex db[n,g] = sum_q dout[q,n,g]; per-filter db[g] = sum_{q,n} dout[q,n,g]. */
+int tgcn_bias_grad(const float* dout, float* db, void* workspace, int Q, int N, int G, int bias_mode,
+                   void* stream);
+
+/* ---- K3: permuted max-pool ---------------------------------------------------------------- */
+/* y[q,m,g] = max_{s<p} x[q,m*p+s,g]; idx = first maximal s (NaN wins), torch.max(dim) rule.
+ * Replaces gcn_pool / gcn_pool_4 (gcn.py:246-255).  `relu` != 0 applies max(x,0) first
+ * (F.relu before the pool, pytorch_hcp_tgcn.py:135-137).  idx is uint8 [Q,N/p,G]. */
+int tgcn_pool_max_fwd(const float* x, float* y, uint8_t* idx, int Q, int N, int G, int p, int relu,
+                      void* stream);
+/* dx[q,m*p+s,g] = (s == idx) ? dy[q,m,g] : 0; with relu: additionally 0 where x <= 0
+ * (pass the pool input `x`, or NULL when relu == 0). */
+int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, float* dx, int Q, int N,
+                      int G, int p, int relu, void* stream);
+
+/* ---- fused whole-layer entry points (one host call per layer direction) -------------------- */
+/* forward: basis + mix + contraction.  `stack` [K,N,Q*D] and `Wmix` [K,D,G] are caller-owned
+ * workspaces that the backward re-uses. */
+int tgcn_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N,
+                   const float* x, const float* W, const float* bias, int bias_mode,
+                   float* out, float* stack, float* Wmix,
+                   int Q, int D, int G, int K, int recursion, int engine, void* stream);
+/* backward: dW (always), db (if bias_mode != NONE), dx (if dx != NULL; needs gstack [K,N,Q*D]).
+ * `workspace` holds tgcn_layer_bwd_workspace(...) bytes. */
+int64_t tgcn_layer_bwd_workspace(int Q, int N, int D, int G, int K);
+int tgcn_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N,
+                   const float* dout, const float* stack, const float* Wmix,
+                   float* dW, float* db, int bias_mode, float* dx, float* gstack, void* workspace,
+                   int Q, int D, int G, int K, int recursion, int engine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGCN_B200_H */

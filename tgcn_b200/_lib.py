@@ -1,0 +1,79 @@
+"""ctypes binding of libtgcn_b200.so (the C-ABI declared in include/tgcn_b200.h).
+
+There is deliberately no fallback: if the library is missing and cannot be built, or a call
+fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtgcn_b200.so")
+
+OK = 0
+BIAS_NONE, BIAS_PER_VERTEX, BIAS_PER_FILTER = 0, 1, 2
+RECURSION_REFERENCE, RECURSION_CHEBYSHEV = 0, 1
+ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05 = 0, 1, 2
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_l = ctypes.c_int64
+_f = ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol include/tgcn_b200.h declares
+SIGNATURES = {
+    "tgcn_version": (_i, []),
+    "tgcn_last_error": (ctypes.c_char_p, []),
+    "tgcn_device_supported": (_i, []),
+    "tgcn_to_slab": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tgcn_from_slab": (_i, [_p, _p, _i, _i, _i, _p]),
+    "tgcn_spmm_step": (_i, [_p, _p, _p, _i, _p, _p, _p, _l, _f, _f, _p]),
+    "tgcn_cheb_basis": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_basis_to_reference": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_mix_weights": (_i, [_p, _p, _i, _l, _i, _i, _p]),
+    "tgcn_contract_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_contract_bwd_w_workspace": (_l, [_i, _i, _i, _i, _i]),
+    "tgcn_contract_bwd_w": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_contract_bwd_x": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_cheb_adjoint": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_bias_grad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_pool_max_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_pool_max_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_layer_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
+    "tgcn_layer_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load (building first if the sources changed and nvcc is present) and return the CDLL."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libtgcn_b200.so is missing and could not be built; there is no fallback path")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().tgcn_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != OK:
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, last_error()))

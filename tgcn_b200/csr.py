@@ -1,0 +1,107 @@
+"""Rescaled-Laplacian operand: whatever the reference layers accept -> int32 CSR on the device.
+
+The reference keeps `L` as a plain attribute and re-uploads the dense N x N tensor on every
+forward (`L = self.L.to(X.device)`, tgcn/nn/gcn.py:141,223).  Here `L` is converted ONCE per
+device into two CSR triplets (L for the forward recursion, L^T for the adjoint recursion).
+"""
+import threading
+
+import numpy as np
+import torch
+
+
+class LaplacianCSR:
+    """int32 CSR of L and of L^T resident on one CUDA device."""
+
+    __slots__ = ("n", "nnz", "rowptr", "col", "val", "rowptr_t", "col_t", "val_t", "symmetric", "device")
+
+    def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, symmetric, device):
+        self.n, self.nnz = n, int(col.numel())
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.rowptr_t, self.col_t, self.val_t = rowptr_t, col_t, val_t
+        self.symmetric = symmetric
+        self.device = device
+
+
+def _to_scipy_like(L):
+    """Return (crow int64, col int64, val float32, n) as CPU torch tensors, rows sorted by column."""
+    if isinstance(L, torch.Tensor):
+        if L.layout == torch.strided:
+            if L.dim() != 2 or L.shape[0] != L.shape[1]:
+                raise ValueError("L must be a square matrix, got shape %s" % (tuple(L.shape),))
+            csr = L.detach().to(torch.float32).to_sparse_csr()
+        elif L.layout == torch.sparse_coo:
+            csr = L.detach().to(torch.float32).coalesce().to_sparse_csr()
+        elif L.layout == torch.sparse_csr:
+            csr = L.detach().to(torch.float32)
+        else:
+            raise TypeError("unsupported tensor layout for L: %s" % L.layout)
+        n = csr.shape[0]
+        if csr.shape[0] != csr.shape[1]:
+            raise ValueError("L must be square")
+        return csr.crow_indices().cpu().to(torch.int64), csr.col_indices().cpu().to(torch.int64), csr.values().cpu(), n
+    # scipy sparse / numpy
+    try:
+        import scipy.sparse as sp
+    except ImportError:  # pragma: no cover
+        sp = None
+    if sp is not None and sp.issparse(L):
+        m = L.tocsr().astype(np.float32)
+        m.sort_indices()
+        m.sum_duplicates()
+        return (torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int64)),
+                torch.from_numpy(m.data.copy()), m.shape[0])
+    arr = np.asarray(L, dtype=np.float32)
+    return _to_scipy_like(torch.from_numpy(arr))
+
+
+def _transpose_csr(crow, col, val, n):
+    nnz = col.numel()
+    rows = torch.repeat_interleave(torch.arange(n, dtype=torch.int64), crow[1:] - crow[:-1])
+    # sort by (col, row): stable sort on col keeps rows ascending inside each transposed row
+    order = torch.argsort(col, stable=True)
+    col_t = rows[order]
+    val_t = val[order]
+    counts = torch.bincount(col, minlength=n) if nnz else torch.zeros(n, dtype=torch.int64)
+    crow_t = torch.zeros(n + 1, dtype=torch.int64)
+    crow_t[1:] = torch.cumsum(counts, 0)
+    return crow_t, col_t, val_t
+
+
+def build_csr(L, device):
+    crow, col, val, n = _to_scipy_like(L)
+    if col.numel() >= 2 ** 31 - 1:
+        raise ValueError("nnz(L) does not fit int32")
+    crow_t, col_t, val_t = _transpose_csr(crow, col, val, n)
+    symmetric = bool(torch.equal(crow, crow_t) and torch.equal(col, col_t) and torch.equal(val, val_t))
+    dev = torch.device(device)
+    i32 = lambda t: t.to(torch.int32).to(dev)
+    rowptr, c, v = i32(crow), i32(col), val.to(dev)
+    if symmetric:
+        rowptr_t, c_t, v_t = rowptr, c, v
+    else:
+        rowptr_t, c_t, v_t = i32(crow_t), i32(col_t), val_t.to(dev)
+    return LaplacianCSR(n, rowptr, c, v, rowptr_t, c_t, v_t, symmetric, dev)
+
+
+class CSRCache:
+    """Per-device cache of the CSR operand; shared by DataParallel replicas (thread-safe)."""
+
+    def __init__(self):
+        self._plans = {}
+        self._lock = threading.Lock()
+
+    def get(self, L, device):
+        key = (device.type, device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            with self._lock:
+                plan = self._plans.get(key)
+                if plan is None:
+                    plan = build_csr(L, device)
+                    self._plans[key] = plan
+        return plan
+
+    def clear(self):
+        with self._lock:
+            self._plans.clear()

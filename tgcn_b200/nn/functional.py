@@ -1,0 +1,164 @@
+"""autograd Functions over the C-ABI (include/tgcn_b200.h).  Host side of the drop-in boundary.
+
+Every function requires CUDA fp32 tensors and raises otherwise -- there is no CPU path.
+"""
+import torch
+
+from .. import _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: tgcn_b200 has no CPU path (CUDA sm_100a only)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s has dtype %s: tgcn_b200 kernels are fp32" % (name, t.dtype))
+
+
+class _DeviceGuard:
+    """Make the tensor's device current for the raw launches (ctypes calls bypass torch's guard)."""
+
+    def __init__(self, device):
+        self.dev = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+class ChebLayerFunction(torch.autograd.Function):
+    """out[q,n,g] = sum_k Xt_k[q,n,:] . W[k,:,g] + bias   (tgcn/nn/gcn.py:108-118 and friends)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan, bias_mode, recursion, engine):
+        lib = _lib.load()
+        Q, N, D = x.shape
+        K, Dw, G = weight.shape
+        if Dw != D:
+            raise RuntimeError("weight expects %d features per vertex, input has %d" % (Dw, D))
+        if N != plan.n:
+            raise RuntimeError("input has %d vertices, Laplacian has %d" % (N, plan.n))
+        dev = x.device
+        x = x.contiguous()
+        w = weight.contiguous()
+        b = None if bias is None else bias.contiguous()
+        out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
+        stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
+        wmix = torch.empty((K, D, G), dtype=torch.float32, device=dev)
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_layer_fwd(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(w), _ptr(b),
+                                    bias_mode if b is not None else _lib.BIAS_NONE, _ptr(out), _ptr(stack), _ptr(wmix),
+                                    Q, D, G, K, recursion, engine, _stream(dev))
+        _lib.check(rc, "tgcn_layer_fwd")
+        ctx.plan = plan
+        ctx.dims = (Q, N, D, G, K)
+        ctx.cfg = (bias_mode if b is not None else _lib.BIAS_NONE, recursion, engine)
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.w_shape = tuple(weight.shape)
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(stack, wmix)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        stack, wmix = ctx.saved_tensors
+        Q, N, D, G, K = ctx.dims
+        bias_mode, recursion, engine = ctx.cfg
+        plan = ctx.plan
+        dev = dout.device
+        dout = dout.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        dW = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+        db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=dev) if bias_mode != _lib.BIAS_NONE else None
+        dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev) if need_dx else None
+        gstack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev) if need_dx else None
+        ws_bytes = lib.tgcn_layer_bwd_workspace(Q, N, D, G, K)
+        ws = torch.empty((max(int(ws_bytes), 4) + 3) // 4, dtype=torch.float32, device=dev)
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_layer_bwd(_ptr(plan.rowptr_t), _ptr(plan.col_t), _ptr(plan.val_t), N, _ptr(dout), _ptr(stack),
+                                    _ptr(wmix), _ptr(dW), _ptr(db), bias_mode, _ptr(dx), _ptr(gstack), _ptr(ws),
+                                    Q, D, G, K, recursion, engine, _stream(dev))
+        _lib.check(rc, "tgcn_layer_bwd")
+        return dx, dW, db, None, None, None, None
+
+
+class PoolFunction(torch.autograd.Function):
+    """Permuted max-pool with first-argmax gradient routing (tgcn/nn/gcn.py:246-255), optional fused ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, p, relu):
+        lib = _lib.load()
+        _require_cuda_f32(x, "x")
+        if x.dim() != 3:
+            raise RuntimeError("pool expects [Q, N, G], got %s" % (tuple(x.shape),))
+        Q, N, G = x.shape
+        if N % p:
+            raise RuntimeError("shape '[%d, %d, %d, %d]' is invalid for input of size %d"
+                               % (Q, N // p, p, G, x.numel()))  # same failure mode as the reference's reshape
+        x = x.contiguous()
+        dev = x.device
+        y = torch.empty((Q, N // p, G), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, N // p, G), dtype=torch.uint8, device=dev)
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_pool_max_fwd(_ptr(x), _ptr(y), _ptr(idx), Q, N, G, p, int(relu), _stream(dev))
+        _lib.check(rc, "tgcn_pool_max_fwd")
+        ctx.p, ctx.relu, ctx.dims = p, relu, (Q, N, G)
+        if relu:
+            ctx.save_for_backward(idx, x)
+        else:
+            ctx.save_for_backward(idx)
+        ctx.mark_non_differentiable(idx)
+        return y, idx
+
+    @staticmethod
+    def backward(ctx, dy, _didx):
+        lib = _lib.load()
+        saved = ctx.saved_tensors
+        idx = saved[0]
+        x = saved[1] if ctx.relu else None
+        Q, N, G = ctx.dims
+        dy = dy.contiguous()
+        dev = dy.device
+        dx = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_pool_max_bwd(_ptr(dy), _ptr(idx), _ptr(x), _ptr(dx), Q, N, G, ctx.p, int(ctx.relu), _stream(dev))
+        _lib.check(rc, "tgcn_pool_max_bwd")
+        return dx, None, None
+
+
+def cheb_basis(x, plan, K, recursion=_lib.RECURSION_REFERENCE, reference_layout=True):
+    """Stacked basis of x[Q,N,D].  reference_layout: Xt[K,Q,N,D] as `_time_chebyshev` returns it
+    (gcn.py:126-154); otherwise the internal stack[K,N,Q*D]."""
+    lib = _lib.load()
+    _require_cuda_f32(x, "x")
+    Q, N, D = x.shape
+    dev = x.device
+    x = x.contiguous()
+    stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
+    with _DeviceGuard(dev):
+        rc = lib.tgcn_cheb_basis(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(stack), Q, D, K,
+                                 recursion, _stream(dev))
+        _lib.check(rc, "tgcn_cheb_basis")
+        if not reference_layout:
+            return stack
+        Xt = torch.empty((K, Q, N, D), dtype=torch.float32, device=dev)
+        rc = lib.tgcn_basis_to_reference(_ptr(stack), _ptr(Xt), Q, N, D, K, recursion, _stream(dev))
+        _lib.check(rc, "tgcn_basis_to_reference")
+    return Xt
