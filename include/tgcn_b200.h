@@ -137,6 +137,18 @@ int tgcn_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* val
                    float* dW, float* db, int bias_mode, float* dx, float* gstack, void* workspace,
                    int Q, int D, int G, int K, int recursion, int engine, void* stream);
 
+/* ---- host-side graph preprocessing (CPU, no device work) ----------------------------------- */
+/* One level of greedy heavy-edge (Graclus-normalised) matching: replaces the pure-Python loop
+ * `metis_one_level` (gcn/coarsening.py:119-165) bit-exactly.  rr/cc/vv: COO triplets sorted by
+ * row; visit: visiting order; weights: vertex degrees; cluster[n] receives the parent ids.
+ * _f32/_f64 select the dtype the reference's numpy arithmetic would run in. */
+int tgcn_pair_one_level_f32(const int64_t* rr_host, const int64_t* cc_host, const float* vv_host,
+                            int64_t nnz, const int64_t* visit_host, const float* weights_host,
+                            int64_t n, int32_t* cluster_host);
+int tgcn_pair_one_level_f64(const int64_t* rr_host, const int64_t* cc_host, const double* vv_host,
+                            int64_t nnz, const int64_t* visit_host, const double* weights_host,
+                            int64_t n, int32_t* cluster_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtgcn_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _sources():
@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libtgcn_b200.so (and no prebuilt library is present)")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags = list(FLAGS)
     objs = []
     procs = []
     for src in _sources():
