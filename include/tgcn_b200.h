@@ -55,6 +55,9 @@ int tgcn_version(void);
 const char* tgcn_last_error(void);
 /* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
 int tgcn_device_supported(void);
+/* kernel launches issued by this library so far (host counter; a launch recorded during CUDA-graph
+ * capture counts once) */
+long long tgcn_launch_count(void);
 
 /* ---- layout ------------------------------------------------------------------------------ */
 /* x[Q,N,D] -> slab[N,Q,D]   (replaces X.permute(1,3,2,0).reshape(N,-1), gcn_matmul.py:152-153) */
@@ -91,8 +94,12 @@ int tgcn_mix_weights(const float* src, float* dst, int K, int64_t inner, int rec
 /* ---- K2: weight contraction ---------------------------------------------------------------- */
 /* out[q,n,g] = sum_{j,d} stack[j][n][q*D+d] * Wmix[j][d][g] (+ bias)
  * Replaces einsum("kqnhf,khfg->qng") + bias add (gcn.py:113-116, :39-42, :194-198). */
+/* `scratch`: tgcn_contract_fwd_scratch(...) bytes (weight image of the tcgen05 engine; may be NULL
+ * when that returns 0 or engine == TGCN_ENGINE_FFMA). */
+int64_t tgcn_contract_fwd_scratch(int Q, int N, int D, int G, int K);
 int tgcn_contract_fwd(const float* stack, const float* Wmix, const float* bias, int bias_mode,
-                      float* out, int Q, int N, int D, int G, int K, int engine, void* stream);
+                      float* out, void* scratch, int Q, int N, int D, int G, int K, int engine,
+                      void* stream);
 
 /* ---- K4: backward ------------------------------------------------------------------------ */
 /* Bytes of scratch the backward entry points need (deterministic two-pass reductions of dW / db). */
@@ -101,7 +108,7 @@ int64_t tgcn_contract_bwd_w_workspace(int Q, int N, int D, int G, int K);
 int tgcn_contract_bwd_w(const float* stack, const float* dout, float* dWmix, void* workspace,
                         int Q, int N, int D, int G, int K, int engine, void* stream);
 /* gstack[j][n][q*D+d] = sum_g dout[q,n,g] * Wmix[j][d][g]     (autograd of gcn.py:113 w.r.t. Xt) */
-int tgcn_contract_bwd_x(const float* dout, const float* Wmix, float* gstack,
+int tgcn_contract_bwd_x(const float* dout, const float* Wmix, float* gstack, void* workspace,
                         int Q, int N, int D, int G, int K, int engine, void* stream);
 /* dx[Q,N,D] from gstack (destroyed) through the adjoint recursion with L^T given as CSR
  * (autograd of gcn.py:146-153). */
@@ -123,11 +130,13 @@ int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, float
                       int G, int p, int relu, void* stream);
 
 /* ---- fused whole-layer entry points (one host call per layer direction) -------------------- */
-/* forward: basis + mix + contraction.  `stack` [K,N,Q*D] and `Wmix` [K,D,G] are caller-owned
- * workspaces that the backward re-uses. */
+/* forward: basis + mix + contraction.  `stack` [K,N,Q*D] and `workspace`
+ * (tgcn_layer_fwd_workspace bytes; its head is Wmix[K,D,G]) are caller-owned and re-used by the
+ * backward. */
+int64_t tgcn_layer_fwd_workspace(int Q, int N, int D, int G, int K);
 int tgcn_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N,
                    const float* x, const float* W, const float* bias, int bias_mode,
-                   float* out, float* stack, float* Wmix,
+                   float* out, float* stack, void* workspace,
                    int Q, int D, int G, int K, int recursion, int engine, void* stream);
 /* backward: dW (always), db (if bias_mode != NONE), dx (if dx != NULL; needs gstack [K,N,Q*D]).
  * `workspace` holds tgcn_layer_bwd_workspace(...) bytes. */

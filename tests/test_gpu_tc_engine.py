@@ -1,0 +1,142 @@
+"""tcgen05 (3xTF32) contraction engine against the exact-fp32 FFMA engine and the float64 oracle,
+called through the raw C-ABI; then whole layers with engine="tcgen05" against the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import LAYER_CASES, csr_from, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+FFMA, TC = 1, 2
+
+SHAPES = [  # Q, N, D, G, K
+    (8, 96, 30, 32, 10),      # mesh32k layer-1 shape family (D not a multiple of 4)
+    (8, 50, 32, 64, 10),      # layer-2: D = 32, G = 64 (two g blocks in bwd_x, 3 output tiles in bwd_w)
+    (64, 24, 15, 32, 10),     # hcp360 layer 1 (odd D)
+    (100, 31, 12, 15, 10),    # mnist: G = 15 (padded N), ragged tail tile
+    (3, 7, 1, 1, 1),          # degenerate
+    (2, 130, 40, 24, 3),      # D > 32: two k-blocks per order
+    (1, 300, 192, 64, 2),     # config-4 family: D = 192
+    (5, 33, 8, 136, 4),       # G > 128
+]
+
+
+def _buffers(Q, N, D, G, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    stack = torch.randn(K, N, Q * D, device="cuda", generator=g)
+    W = torch.randn(K, D, G, device="cuda", generator=g) * 0.2
+    bias = torch.randn(N, G, device="cuda", generator=g)
+    dout = torch.randn(Q, N, G, device="cuda", generator=g)
+    return stack, W, bias, dout
+
+
+def _tc_covers(lib, shape):
+    return lib.tgcn_contract_fwd_scratch(*shape) > 0
+
+
+def _scratch(nbytes):
+    return torch.empty(max(int(nbytes), 16) // 4 + 64, dtype=torch.float32, device="cuda")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_contract_fwd_tc_vs_ffma_and_fp64(shape):
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    Q, N, D, G, K = shape
+    stack, W, bias, _ = _buffers(*shape)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for eng in (FFMA, TC):
+        out = torch.full((Q, N, G), float("nan"), device="cuda")
+        scr = _scratch(lib.tgcn_contract_fwd_scratch(Q, N, D, G, K))
+        rc = lib.tgcn_contract_fwd(stack.data_ptr(), W.data_ptr(), bias.data_ptr(), 1, out.data_ptr(), scr.data_ptr(),
+                                   Q, N, D, G, K, eng, st)
+        if eng == TC and not _tc_covers(lib, shape):
+            assert rc == -2 and "tcgen05" in _lib.last_error()      # loud, not a silent fallback
+            continue
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        outs[eng] = out.cpu().numpy()
+    ref = torch.einsum("jnqd,jdg->qng", stack.double().reshape(K, N, Q, D), W.double()).cpu().numpy() + bias.cpu().numpy()[None]
+    assert rel_err(outs[FFMA], ref) < 2e-6
+    if TC in outs:
+        assert rel_err(outs[TC], ref) < 5e-6          # 3xTF32 keeps ~21 mantissa bits
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_contract_bwd_x_tc(shape):
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    Q, N, D, G, K = shape
+    _, W, _, dout = _buffers(*shape, seed=1)
+    st = torch.cuda.current_stream().cuda_stream
+    ref = torch.einsum("qng,jdg->jnqd", dout.double(), W.double()).reshape(K, N, Q * D).cpu().numpy()
+    for eng in (FFMA, TC):
+        gs = torch.full((K, N, Q * D), float("nan"), device="cuda")
+        ws = _scratch(lib.tgcn_layer_bwd_workspace(Q, N, D, G, K))
+        rc = lib.tgcn_contract_bwd_x(dout.data_ptr(), W.data_ptr(), gs.data_ptr(), ws.data_ptr(), Q, N, D, G, K, eng, st)
+        if eng == TC and not _tc_covers(lib, shape):
+            assert rc == -2 and "tcgen05" in _lib.last_error()      # loud, not a silent fallback
+            continue
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        assert rel_err(gs.cpu().numpy(), ref) < 5e-6, eng
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_contract_bwd_w_tc(shape):
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    Q, N, D, G, K = shape
+    stack, _, _, dout = _buffers(*shape, seed=2)
+    st = torch.cuda.current_stream().cuda_stream
+    ref = torch.einsum("jnqd,qng->jdg", stack.double().reshape(K, N, Q, D), dout.double()).cpu().numpy()
+    for eng in (FFMA, TC):
+        dW = torch.full((K, D, G), float("nan"), device="cuda")
+        ws = _scratch(lib.tgcn_layer_bwd_workspace(Q, N, D, G, K))
+        rc = lib.tgcn_contract_bwd_w(stack.data_ptr(), dout.data_ptr(), dW.data_ptr(), ws.data_ptr(), Q, N, D, G, K, eng, st)
+        if eng == TC and not _tc_covers(lib, shape):
+            assert rc == -2 and "tcgen05" in _lib.last_error()      # loud, not a silent fallback
+            continue
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        assert rel_err(dW.cpu().numpy(), ref) < 5e-6, eng
+
+
+def test_large_tile_counts_tc():
+    """mesh32k layer-1 size: 2616 tiles, exercises multi-wave scheduling and TMEM re-allocation."""
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    Q, N, D, G, K = 8, 41856, 30, 32, 10
+    stack, W, bias, dout = _buffers(Q, N, D, G, K, seed=3)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for eng in (FFMA, TC):
+        out = torch.empty(Q, N, G, device="cuda")
+        scr = _scratch(lib.tgcn_contract_fwd_scratch(Q, N, D, G, K))
+        assert lib.tgcn_contract_fwd(stack.data_ptr(), W.data_ptr(), bias.data_ptr(), 1, out.data_ptr(), scr.data_ptr(),
+                                     Q, N, D, G, K, eng, st) == 0, _lib.last_error()
+        dW = torch.empty(K, D, G, device="cuda")
+        ws = _scratch(lib.tgcn_layer_bwd_workspace(Q, N, D, G, K))
+        assert lib.tgcn_contract_bwd_w(stack.data_ptr(), dout.data_ptr(), dW.data_ptr(), ws.data_ptr(), Q, N, D, G, K,
+                                       eng, st) == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        res[eng] = (out, dW)
+    assert float((res[TC][0] - res[FFMA][0]).abs().max() / res[FFMA][0].abs().max()) < 1e-5
+    assert float((res[TC][1] - res[FFMA][1]).abs().max() / res[FFMA][1].abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("case", LAYER_CASES)
+def test_layers_with_tcgen05_engine_vs_reference_golden(case):
+    from test_gpu_parity import make_layer
+    r = load_golden(case)
+    L = torch.tensor(np.asarray(csr_from(r, "L").todense()), dtype=torch.float)
+    lay = make_layer(r, L, engine="tcgen05")
+    x = torch.tensor(r["x"], device="cuda", requires_grad=True)
+    out = lay(x)
+    assert rel_err(out.detach().cpu().numpy(), r["out"]) < 1e-4
+    out.backward(torch.tensor(r["dout"], device="cuda"))
+    assert rel_err(lay.weight.grad.cpu().numpy(), r["dW"]) < 1e-4
+    assert rel_err(x.grad.cpu().numpy(), r["dx"]) < 1e-4
+    if "b" in r:
+        assert rel_err(lay.bias.grad.cpu().numpy(), r["db"]) < 1e-4

@@ -25,20 +25,23 @@ SIGNATURES = {
     "tgcn_version": (_i, []),
     "tgcn_last_error": (ctypes.c_char_p, []),
     "tgcn_device_supported": (_i, []),
+    "tgcn_launch_count": (ctypes.c_longlong, []),
     "tgcn_to_slab": (_i, [_p, _p, _i, _i, _i, _p]),
     "tgcn_from_slab": (_i, [_p, _p, _i, _i, _i, _p]),
     "tgcn_spmm_step": (_i, [_p, _p, _p, _i, _p, _p, _p, _l, _f, _f, _p]),
     "tgcn_cheb_basis": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_basis_to_reference": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "tgcn_mix_weights": (_i, [_p, _p, _i, _l, _i, _i, _p]),
-    "tgcn_contract_fwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_contract_fwd_scratch": (_l, [_i, _i, _i, _i, _i]),
+    "tgcn_contract_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_contract_bwd_w_workspace": (_l, [_i, _i, _i, _i, _i]),
     "tgcn_contract_bwd_w": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "tgcn_contract_bwd_x": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_contract_bwd_x": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_cheb_adjoint": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_bias_grad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_pool_max_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tgcn_pool_max_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_layer_fwd_workspace": (_l, [_i, _i, _i, _i, _i]),
     "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_layer_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
     "tgcn_layer_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

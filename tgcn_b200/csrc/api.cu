@@ -1,6 +1,7 @@
 // Library-level entry points: version, error reporting, device check.
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include "common.cuh"
 
 namespace tgcn {
@@ -13,7 +14,11 @@ int set_error(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace tgcn
+
+extern "C" long long tgcn_launch_count(void) { return tgcn::g_launches.load(); }
 
 extern "C" int tgcn_version(void) { return 100; }  // 0.1.0
 

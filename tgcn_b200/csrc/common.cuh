@@ -16,6 +16,10 @@ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Number of kernel launches this library has issued (host-side counter, for bench.py's
+// `gpu_launches`; launches recorded during graph capture count once per capture).
+void count_launch();
+
 }  // namespace tgcn
 
 #define TGCN_REQUIRE(cond, ...)                                            \
@@ -30,6 +34,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 #define TGCN_LAUNCH_CHECK(name)                                                                  \
     do {                                                                                         \
+        tgcn::count_launch();                                                                    \
         cudaError_t e__ = cudaGetLastError();                                                    \
         if (e__ != cudaSuccess)                                                                  \
             return tgcn::set_error(TGCN_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__));      \

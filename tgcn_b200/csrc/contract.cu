@@ -323,21 +323,54 @@ extern "C" int tgcn_mix_weights(const float* src, float* dst, int K, int64_t inn
     return TGCN_OK;
 }
 
+namespace tgcn {
+int tc_supported(int Q, int N, int D, int G, int K);
+int64_t tc_fwd_scratch_bytes(int Q, int N, int D, int G, int K);
+int64_t tc_bwd_scratch_bytes(int Q, int N, int D, int G, int K);
+int contract_fwd_tc(const float* stack, const float* Wmix, const float* bias, int bias_mode, float* out, void* scratch,
+                    int Q, int N, int D, int G, int K, cudaStream_t st);
+int contract_bwd_x_tc(const float* dout, const float* Wmix, float* gstack, void* scratch,
+                      int Q, int N, int D, int G, int K, cudaStream_t st);
+int contract_bwd_w_tc(const float* stack, const float* dout, float* partial, int* P_out,
+                      int Q, int N, int D, int G, int K, cudaStream_t st);
+uint8_t* tc_bwd_partial_ptr(void* scratch, int Q, int N, int D, int G, int K);
+}  // namespace tgcn
+
+// engine resolution: AUTO picks the tensor-core engine whenever its tiles cover the shape
+static int resolve_engine(const char* who, int engine, int Q, int N, int D, int G, int K, int* use_tc) {
+    TGCN_REQUIRE(engine == TGCN_ENGINE_AUTO || engine == TGCN_ENGINE_FFMA || engine == TGCN_ENGINE_TCGEN05,
+                 "%s: unknown engine %d", who, engine);
+    const int ok = tc_supported(Q, N, D, G, K);
+    if (engine == TGCN_ENGINE_TCGEN05)
+        TGCN_SUPPORTED(ok, "%s: tcgen05 engine does not cover D=%d G=%d", who, D, G);
+    *use_tc = (engine != TGCN_ENGINE_FFMA) && ok;
+    return TGCN_OK;
+}
+
 static int check_dims(const char* who, int Q, int N, int D, int G, int K) {
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && G >= 1 && K >= 1, "%s: bad sizes Q=%d N=%d D=%d G=%d K=%d", who, Q, N, D, G, K);
     TGCN_SUPPORTED((int64_t)Q * N < (int64_t)INT32_MAX, "%s: Q*N = %lld exceeds 2^31-1", who, (long long)Q * N);
     return TGCN_OK;
 }
 
+extern "C" int64_t tgcn_contract_fwd_scratch(int Q, int N, int D, int G, int K) {
+    if (Q < 0 || N < 0 || D < 1 || G < 1 || K < 1) return 0;
+    return tc_supported(Q, N, D, G, K) ? tc_fwd_scratch_bytes(Q, N, D, G, K) : 0;
+}
+
 extern "C" int tgcn_contract_fwd(const float* stack, const float* Wmix, const float* bias, int bias_mode,
-                                 float* out, int Q, int N, int D, int G, int K, int engine, void* stream) {
+                                 float* out, void* scratch, int Q, int N, int D, int G, int K, int engine,
+                                 void* stream) {
     TGCN_PROPAGATE(check_dims("tgcn_contract_fwd", Q, N, D, G, K));
     if ((int64_t)Q * N == 0) return TGCN_OK;
     TGCN_REQUIRE(stack && Wmix && out, "tgcn_contract_fwd: null pointer");
     TGCN_REQUIRE(bias_mode == TGCN_BIAS_NONE || bias, "tgcn_contract_fwd: bias_mode %d without bias", bias_mode);
-    TGCN_REQUIRE(engine == TGCN_ENGINE_AUTO || engine == TGCN_ENGINE_FFMA || engine == TGCN_ENGINE_TCGEN05,
-                 "tgcn_contract_fwd: unknown engine %d", engine);
-    TGCN_SUPPORTED(engine != TGCN_ENGINE_TCGEN05, "tgcn_contract_fwd: tcgen05 engine not built in this version");
+    int use_tc = 0;
+    TGCN_PROPAGATE(resolve_engine("tgcn_contract_fwd", engine, Q, N, D, G, K, &use_tc));
+    if (use_tc) {
+        TGCN_REQUIRE(scratch, "tgcn_contract_fwd: the tcgen05 engine needs tgcn_contract_fwd_scratch() bytes of scratch");
+        return contract_fwd_tc(stack, Wmix, bias, bias_mode, out, scratch, Q, N, D, G, K, as_stream(stream));
+    }
     GemmParams p{};
     p.A = stack; p.a_api_rows = 0; p.lda = D; p.a_split = D; p.a_split_stride = (int64_t)N * Q * D; p.a_batch_stride = 0;
     p.B = Wmix; p.ldb_k = G; p.ldb_c = 1; p.b_batch_stride = 0;
@@ -347,12 +380,17 @@ extern "C" int tgcn_contract_fwd(const float* stack, const float* Wmix, const fl
     return launch_small_gemm(p, 1, as_stream(stream));
 }
 
-extern "C" int tgcn_contract_bwd_x(const float* dout, const float* Wmix, float* gstack,
+extern "C" int tgcn_contract_bwd_x(const float* dout, const float* Wmix, float* gstack, void* scratch,
                                    int Q, int N, int D, int G, int K, int engine, void* stream) {
     TGCN_PROPAGATE(check_dims("tgcn_contract_bwd_x", Q, N, D, G, K));
     if ((int64_t)Q * N == 0) return TGCN_OK;
     TGCN_REQUIRE(dout && Wmix && gstack, "tgcn_contract_bwd_x: null pointer");
-    TGCN_SUPPORTED(engine != TGCN_ENGINE_TCGEN05, "tgcn_contract_bwd_x: tcgen05 engine not built in this version");
+    int use_tc = 0;
+    TGCN_PROPAGATE(resolve_engine("tgcn_contract_bwd_x", engine, Q, N, D, G, K, &use_tc));
+    if (use_tc) {
+        TGCN_REQUIRE(scratch, "tgcn_contract_bwd_x: the tcgen05 engine needs tgcn_contract_bwd_w_workspace() bytes of scratch");
+        return contract_bwd_x_tc(dout, Wmix, gstack, scratch, Q, N, D, G, K, as_stream(stream));
+    }
     GemmParams p{};
     p.A = dout; p.a_api_rows = 1; p.lda = G; p.a_split = G; p.a_split_stride = 0; p.a_batch_stride = 0;
     p.B = Wmix; p.ldb_k = 1; p.ldb_c = G; p.b_batch_stride = (int64_t)D * G;
@@ -366,7 +404,12 @@ extern "C" int64_t tgcn_contract_bwd_w_workspace(int Q, int N, int D, int G, int
     if (Q < 0 || N < 0 || D < 1 || G < 1 || K < 1) return 0;
     const int64_t a = (int64_t)bwd_w_partitions((int64_t)Q * N, K * D, G) * K * D * G;
     const int64_t b = (int64_t)bias_filter_blocks((int64_t)Q * N) * G;
-    return (int64_t)sizeof(float) * (a > b ? a : b);
+    int64_t bytes = (int64_t)sizeof(float) * (a > b ? a : b);
+    if (tc_supported(Q, N, D, G, K)) {
+        const int64_t t = tc_bwd_scratch_bytes(Q, N, D, G, K);
+        if (t > bytes) bytes = t;
+    }
+    return (bytes + 255) & ~(int64_t)255;
 }
 
 extern "C" int tgcn_contract_bwd_w(const float* stack, const float* dout, float* dWmix, void* workspace,
@@ -382,7 +425,18 @@ extern "C" int tgcn_contract_bwd_w(const float* stack, const float* dout, float*
         return TGCN_OK;
     }
     TGCN_REQUIRE(stack && dout && workspace, "tgcn_contract_bwd_w: null pointer");
-    TGCN_SUPPORTED(engine != TGCN_ENGINE_TCGEN05, "tgcn_contract_bwd_w: tcgen05 engine not built in this version");
+    int use_tc = 0;
+    TGCN_PROPAGATE(resolve_engine("tgcn_contract_bwd_w", engine, Q, N, D, G, K, &use_tc));
+    if (use_tc) {
+        // partials live behind the bwd_x weight image inside the same workspace
+        float* partial = reinterpret_cast<float*>(tc_bwd_partial_ptr(workspace, Q, N, D, G, K));
+        int P = 0;
+        TGCN_PROPAGATE(contract_bwd_w_tc(stack, dout, partial, &P, Q, N, D, G, K, st));
+        const int64_t n = (int64_t)JD * G;
+        reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, dWmix, P, n);
+        TGCN_LAUNCH_CHECK("reduce_partials");
+        return TGCN_OK;
+    }
     const int P = bwd_w_partitions(M, JD, G);
     dim3 grid((unsigned)P, (unsigned)ceil_div(JD, kBwJD), (unsigned)ceil_div(G, kBwG));
     contract_bwd_w_kernel<<<grid, kBwThreads, 0, st>>>(stack, dout, (float*)workspace, (int)M, Q, N, D, G, JD,

@@ -60,7 +60,8 @@ class ChebLayerFunction(torch.autograd.Function):
         b = None if bias is None else bias.contiguous()
         out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
         stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
-        wmix = torch.empty((K, D, G), dtype=torch.float32, device=dev)
+        fw_bytes = int(lib.tgcn_layer_fwd_workspace(Q, N, D, G, K))
+        wmix = torch.empty((max(fw_bytes, 4) + 3) // 4, dtype=torch.float32, device=dev)   # [Wmix | engine scratch]
         with _DeviceGuard(dev):
             rc = lib.tgcn_layer_fwd(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(w), _ptr(b),
                                     bias_mode if b is not None else _lib.BIAS_NONE, _ptr(out), _ptr(stack), _ptr(wmix),

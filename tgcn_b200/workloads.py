@@ -1,0 +1,158 @@
+"""Synthetic graphs and the reference's model compositions for the BASELINE.json configs.
+
+Graph builders run on the host with `tgcn_b200.graph` / `tgcn_b200.coarsening` (the drop-in
+producers); everything is seeded.  The models mirror the reference's experiment scripts:
+
+  * `NetTGCN_HCP`   examples/pytorch_based/pytorch_hcp_tgcn.py:93-155
+  * `NetTGCN_MNIST` examples/pytorch_based/pytorch_mnist_tgcn.py:67-92 (+ tgcn_mnist.py hyper-parameters)
+
+The conv layers and pooling are tgcn_b200's CUDA path; the dense classifier head
+(Linear/BatchNorm/log_softmax) is plain torch -- SURVEY.md section 8f ranks it "next", outside
+the hot path.
+"""
+import math
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import coarsening, graph
+from .nn.gcn import GCNCheb, TGCNCheb_H, gcn_pool, gcn_pool_4, relu_pool
+
+
+# ------------------------------------------------------------------------------------------------
+# graphs
+# ------------------------------------------------------------------------------------------------
+def _coarsened_laplacians(A, levels, seed):
+    np.random.seed(seed)                       # coarsening.metis draws its visiting order here
+    graphs, perm = coarsening.coarsen(A, levels=levels, self_connections=False)
+    Ls = [graph.rescaled_laplacian_csr(g) for g in graphs]
+    return graphs, perm, Ls
+
+
+def mnist_grid(k=8, levels=4, seed=0):
+    """Config 1: 28x28 k-NN grid graph (seed 0 -> N = [992, 496, 248, 124, 62])."""
+    z = graph.grid(28)
+    dist, idx = graph.distance_sklearn_metrics(z, k=k, metric='euclidean')
+    A = graph.adjacency(dist, idx)
+    return _coarsened_laplacians(A, levels, seed) + (784,)
+
+
+def hcp_parcellation(n_real=360, knn=16, levels=4, seed=0, dense=False):
+    """Config 2: HCP-shaped parcellation connectome, lognormal symmetric weights; sparse variant
+    keeps the top-`knn` entries per row and symmetrises by max."""
+    rng = np.random.default_rng(seed)
+    M = rng.lognormal(0.0, 1.0, size=(n_real, n_real)).astype(np.float32)
+    M = np.maximum(M, M.T)
+    np.fill_diagonal(M, 0.0)
+    if not dense:
+        thresh = np.sort(M, axis=1)[:, -knn][:, None]
+        M = np.where(M >= thresh, M, 0.0).astype(np.float32)
+        M = np.maximum(M, M.T)
+    A = sp.csr_matrix(M)
+    return _coarsened_laplacians(A, levels, seed) + (n_real,)
+
+
+def fibonacci_sphere(n):
+    i = np.arange(n, dtype=np.float64) + 0.5
+    phi = np.arccos(1.0 - 2.0 * i / n)
+    theta = math.pi * (1.0 + 5.0 ** 0.5) * i
+    return np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+
+
+def cortical_mesh(n_real=32492, levels=4, seed=0):
+    """Config 3: closed genus-0 triangulated surface with the fsLR-32k vertex count
+    (load/data_hcp.py:86), unit edge weights from the faces (load/create_hcp.py:330-361,459-460)."""
+    from scipy.spatial import ConvexHull
+    pts = fibonacci_sphere(n_real)
+    faces = ConvexHull(pts).simplices
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], axis=0)
+    e = np.concatenate([e, e[:, ::-1]], axis=0)
+    A = sp.coo_matrix((np.ones(e.shape[0], np.float32), (e[:, 0], e[:, 1])), shape=(n_real, n_real)).tocsr()
+    A.data[:] = 1.0                                            # duplicate edges collapse to weight 1
+    return _coarsened_laplacians(A, levels, seed) + (n_real,)
+
+
+def random_geometric(n=1_000_000, mean_degree=12.0, seed=0):
+    """Config 4: points uniform in the unit square sorted by x (strip partition friendly), edges
+    within r = sqrt(mean_degree / (pi n)), Gaussian weights; no coarsening.  Returns L~ (CSR)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 2))
+    pts = pts[np.argsort(pts[:, 0])]
+    r = math.sqrt(mean_degree / (math.pi * n))
+    pairs = cKDTree(pts).query_pairs(r, output_type='ndarray')
+    d = np.linalg.norm(pts[pairs[:, 0]] - pts[pairs[:, 1]], axis=1)
+    w = np.exp(-(d / (0.5 * r)) ** 2).astype(np.float32)
+    rows = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    cols = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    A = sp.coo_matrix((np.concatenate([w, w]), (rows, cols)), shape=(n, n)).tocsr()
+    return graph.rescaled_laplacian_csr(A), pts
+
+
+def synthetic_signals(Q, N0, H, n_real, perm, seed, F_in=None):
+    """x[Q, N0, H(,F)] ~ N(0,1) on real vertices, exact zeros on the fake vertices the coarsening
+    added (what perm_data_time produces)."""
+    g = torch.Generator().manual_seed(seed)
+    shape = (Q, N0, H) if F_in is None else (Q, N0, H, F_in)
+    x = torch.randn(shape, generator=g)
+    if perm is not None:
+        fake = torch.tensor(np.asarray(perm) >= n_real)
+        x[:, fake] = 0.0
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# models
+# ------------------------------------------------------------------------------------------------
+class NetTGCN_HCP(nn.Module):
+    """TGCNCheb_H(L0,1,32,K,H) -> ReLU -> pool4 -> GCNCheb(L2,32,64,K) -> ReLU -> pool4 -> fc(200) -> BN -> ReLU
+    -> fc(n_classes) -> log_softmax   (pytorch_hcp_tgcn.py:93-155; dropout layers omitted: rate-0
+    equivalent, they are elementwise and outside the measured path)."""
+
+    def __init__(self, L, horizon=15, K=10, g1=32, g2=64, hidden=200, n_classes=6, fused_relu_pool=True, **layer_kw):
+        super().__init__()
+        self.tgcn1 = TGCNCheb_H(L[0], 1, g1, K, horizon, **layer_kw)
+        self.gcn2 = GCNCheb(L[2], g1, g2, K, **layer_kw)
+        n2 = L[2].shape[0]
+        self.fc1 = nn.Linear(int(n2 * g2 / 4), hidden)
+        self.dense1_bn = nn.BatchNorm1d(hidden)
+        self.fc2 = nn.Linear(hidden, n_classes)
+        self.fused = fused_relu_pool
+
+    def forward(self, x):
+        x = self.tgcn1(x)
+        x = relu_pool(x, 4) if self.fused else gcn_pool_4(F.relu(x))
+        x = self.gcn2(x)
+        x = relu_pool(x, 4) if self.fused else gcn_pool_4(F.relu(x))
+        x = x.reshape(x.shape[0], -1)
+        x = F.relu(self.dense1_bn(self.fc1(x)))
+        return F.log_softmax(self.fc2(x), dim=1)
+
+
+class NetTGCN_MNIST(nn.Module):
+    """TGCNCheb_H(L0,1,15,K=10,H=12) -> ReLU -> fc(10) -> log_softmax (pytorch_mnist_tgcn.py:67-92)."""
+
+    def __init__(self, L, horizon=12, K=10, g1=15, n_classes=10, **layer_kw):
+        super().__init__()
+        self.tgcn1 = TGCNCheb_H(L[0], 1, g1, K, horizon, **layer_kw)
+        self.fc1 = nn.Linear(L[0].shape[0] * g1, n_classes)
+
+    def forward(self, x):
+        x = F.relu(self.tgcn1(x))
+        return F.log_softmax(self.fc1(x.reshape(x.shape[0], -1)), dim=1)
+
+
+def as_torch_operands(Ls, device=None, dense=False):
+    """Laplacians in a form with `.shape` and `L[0].shape[0]` (what the reference constructors
+    index): torch sparse COO by default, dense like the example scripts on request."""
+    out = []
+    for L in Ls:
+        coo = L.tocoo()
+        t = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), coo.shape).coalesce()
+        if dense:
+            t = t.to_dense()
+        out.append(t if device is None else t.to(device))
+    return out
