@@ -1,0 +1,93 @@
+"""Worker for the multi-GPU checks; launched by tests/test_gpu_multi.py under torchrun (NCCL).
+
+A. data parallel: sharded batch + one flat allreduce == single-GPU full-batch gradients (rtol 1e-4)
+B. row-partitioned Chebyshev recursion with NVLink halo exchange == unpartitioned, bit for bit
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tgcn_b200 import _lib, workloads as wl  # noqa: E402
+from tgcn_b200.csr import build_csr  # noqa: E402
+from tgcn_b200.parallel import (FlatGradients, RowPartition, broadcast_parameters, halo_exchange,  # noqa: E402
+                                init_distributed, shard_range)
+
+
+def check_dp(rank, world, dev):
+    graphs, perm, Ls, n_real = wl.hcp_parcellation()
+    Lt = wl.as_torch_operands(Ls, device=dev)
+    torch.manual_seed(10 + rank)
+    model = wl.NetTGCN_HCP(Lt, horizon=15).to(dev)
+    broadcast_parameters(model)
+    model.eval()
+    Q = 16 * world
+    x = wl.synthetic_signals(Q, Ls[0].shape[0], 15, n_real, perm, seed=3).to(dev)
+    y = torch.randint(0, 6, (Q,), generator=torch.Generator().manual_seed(4)).to(dev)
+    ref = wl.NetTGCN_HCP(Lt, horizon=15).to(dev)
+    ref.load_state_dict(model.state_dict()); ref.eval()
+    F.nll_loss(ref(x), y).backward()
+    ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    grads = FlatGradients(model.parameters())
+    lo, hi = shard_range(Q, rank, world)
+    grads.zero_()
+    F.nll_loss(model(x[lo:hi]), y[lo:hi]).backward()
+    flat = grads.allreduce_mean()
+    err = float((flat - ref_flat).abs().max() / ref_flat.abs().max())
+    assert err < 1e-4, err
+    return err
+
+
+def check_halo(rank, world, dev):
+    lib = _lib.load()
+    L, _ = wl.random_geometric(n=40000, mean_degree=12.0, seed=1)
+    n = L.shape[0]
+    C, K = 48, 6
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device=dev)
+    # unpartitioned reference on this GPU
+    full = build_csr(L, dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ref = [x]
+    for k in range(1, K):
+        out = torch.empty_like(x)
+        rc = lib.tgcn_spmm_step(full.rowptr.data_ptr(), full.col.data_ptr(), full.val.data_ptr(), n, ref[-1].data_ptr(),
+                                None, out.data_ptr(), C, 1.0, 0.0, st)
+        assert rc == 0, _lib.last_error()
+        ref.append(out)
+    plan = RowPartition(L, rank, world).build_send_lists()
+    rowptr = torch.tensor(plan.rowptr, device=dev); col = torch.tensor(plan.col, device=dev)
+    val = torch.tensor(plan.val, device=dev)
+    ext = torch.empty(plan.n_own + plan.n_halo, C, device=dev)
+    ext[:plan.n_own] = x[plan.lo:plan.hi]
+    for k in range(1, K):
+        halo_exchange(ext[:plan.n_own], plan, halo_out=ext[plan.n_own:])
+        nxt = torch.empty_like(ext)
+        rc = lib.tgcn_spmm_step(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), plan.n_own, ext.data_ptr(), None,
+                                nxt.data_ptr(), C, 1.0, 0.0, st)
+        assert rc == 0, _lib.last_error()
+        assert torch.equal(nxt[:plan.n_own], ref[k][plan.lo:plan.hi]), "step %d differs" % k
+        ext = nxt
+    return plan.n_halo
+
+
+def main():
+    rank, world, local = init_distributed("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    e = check_dp(rank, world, dev)
+    h = check_halo(rank, world, dev)
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d" % (world, e, h))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

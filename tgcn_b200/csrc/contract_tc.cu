@@ -56,6 +56,41 @@ prep_wimg_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int K, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// vector helpers: VEC in {1,2,4} fp32 per lane; a row of 32 columns is covered by 32/VEC lanes and
+// one warp instruction covers VEC rows.
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void ldg_vec(const float* p, float* v) {
+    if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+// hi/lo split of VEC consecutive fp32 into the two operand tiles (same byte offset in both)
+template <int VEC>
+__device__ __forceinline__ void store_split_vec(uint8_t* hi, uint8_t* lo, uint32_t off, const float* x) {
+    float h[VEC], l[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = x[i] - h[i]; }
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(hi + off) = make_float2(h[0], h[1]);
+        *reinterpret_cast<float2*>(lo + off) = make_float2(l[0], l[1]);
+    } else {
+        *reinterpret_cast<float*>(hi + off) = h[0];
+        *reinterpret_cast<float*>(lo + off) = l[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward contraction
 // ------------------------------------------------------------------------------------------------
 struct FwdTcParams {
@@ -66,8 +101,11 @@ struct FwdTcParams {
     int M, Q, N, D, G, GP, K, KB;
 };
 
+template <int VEC>
 __global__ void __launch_bounds__(kTcThreads)
 contract_fwd_tc_kernel(const FwdTcParams p) {
+    constexpr int LPR = 32 / VEC;   // lanes per 32-column row
+    constexpr int NI = 32 / VEC;    // instructions per warp per unit (32 rows, VEC rows each)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     const uint32_t wtile = (uint32_t)p.GP * kRowBytes;
@@ -78,6 +116,7 @@ contract_fwd_tc_kernel(const FwdTcParams p) {
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / LPR, c0 = (lane % LPR) * VEC;
     const int m0 = blockIdx.x * kTileM;
     const uint32_t ncols = tmem_cols_pow2((uint32_t)p.GP);
 
@@ -94,28 +133,34 @@ contract_fwd_tc_kernel(const FwdTcParams p) {
     const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)p.GP, 0, 0);
 
     const int units = p.K * p.KB;
-    float cur[32], nxt[32];
+    float buf[32];
 
-    auto load_unit = [&](int u, float* v) {
+    auto load_unit = [&](int u) {
         const int j = u / p.KB, kb = u - j * p.KB;
-        const int c = kb * 32 + lane;
+        const int c = kb * 32 + c0;
         const float* base = p.stack + (int64_t)j * p.S + (int64_t)m0 * p.D + c;
-        const bool cok = c < p.D;
+        const bool cok = c < p.D;                       // D % VEC == 0: vectors are all-or-nothing
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int r = warp + 4 * e;
-            v[e] = (cok && m0 + r < p.M) ? __ldg(base + (int64_t)r * p.D) : 0.f;
+        for (int e = 0; e < NI; ++e) {
+            const int r = warp * 32 + e * VEC + sub;
+            if (cok && m0 + r < p.M) {
+                ldg_vec<VEC>(base + (int64_t)r * p.D, &buf[e * VEC]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) buf[e * VEC + i] = 0.f;
+            }
         }
     };
 
-    load_unit(0, cur);
+    load_unit(0);
     for (int u = 0; u < units; ++u) {
         const int s = u & 1;
-        if (u + 1 < units) load_unit(u + 1, nxt);
         if (u >= 2) mbar_wait(&bar_free[s], (uint32_t)(((u >> 1) - 1) & 1));   // MMAs of unit u-2 have drained stage s
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-            store_split(a_hi[s], a_lo[s], sw128_offset((uint32_t)(warp + 4 * e), (uint32_t)lane), cur[e]);
+        for (int e = 0; e < NI; ++e)
+            store_split_vec<VEC>(a_hi[s], a_lo[s], sw128_offset((uint32_t)(warp * 32 + e * VEC + sub), (uint32_t)c0),
+                                 &buf[e * VEC]);
+        if (u + 1 < units) load_unit(u + 1);            // in flight across the barrier and the MMA issue
         {   // weight image of this unit: 2 * GP * 128 bytes, 16-byte moves
             const float4* src = reinterpret_cast<const float4*>(p.wimg + (int64_t)u * 2 * wtile);
             float4* dst = reinterpret_cast<float4*>(w_st[s]);
@@ -138,8 +183,6 @@ contract_fwd_tc_kernel(const FwdTcParams p) {
             }
             umma_commit(&bar_free[s]);
         }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) cur[e] = nxt[e];
     }
     {   // all MMAs done: the last commit covers every earlier one
         const int ul = units - 1;
@@ -191,21 +234,27 @@ struct BwdXTcParams {
     int NT;                  // d columns handled per CTA (multiple of 16, <= 64); blockIdx.y selects the chunk
 };
 
+template <int VEC>
 __global__ void __launch_bounds__(kTcThreads)
 contract_bwd_x_tc_kernel(const BwdXTcParams p) {
+    constexpr int LPR = 32 / VEC;
+    constexpr int NI = 32 / VEC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
-    // A: GB blocks x (hi, lo); B: 2 stages x GB blocks x (hi, lo) of [NT rows x 128 B]
+    // A: GB blocks x (hi, lo); B: 2 stages x GB blocks x (hi, lo) of [NT rows x 128 B]; then the
+    // epilogue staging area [4 warps][32 rows x NT fp32]
     uint8_t* a_hi = smem;
     uint8_t* a_lo = smem + (size_t)p.GB * kTileBytes;
     const uint32_t btile = (uint32_t)p.NT * kRowBytes;
     uint8_t* b_st[2];
     b_st[0] = smem + 2 * (size_t)p.GB * kTileBytes;
     b_st[1] = b_st[0] + 2 * (size_t)p.GB * btile;
+    float* epi = reinterpret_cast<float*>(b_st[1] + 2 * (size_t)p.GB * btile);
     __shared__ __align__(8) uint64_t bar_done[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / LPR, c0 = (lane % LPR) * VEC;
     const int m0 = blockIdx.x * kTileM;
     const int n0 = blockIdx.y * p.NT;                      // first d column of this CTA
     const uint32_t ncols = tmem_cols_pow2((uint32_t)(2 * p.NT));
@@ -218,8 +267,9 @@ contract_bwd_x_tc_kernel(const BwdXTcParams p) {
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
 
     // stage the dOut tile once: row r <- API row (q*N + n), 32-column blocks over g
-    for (int e = 0; e < 32; ++e) {
-        const int r = warp + 4 * e;
+#pragma unroll 4
+    for (int e = 0; e < NI; ++e) {
+        const int r = warp * 32 + e * VEC + sub;
         const int m = m0 + r;
         const float* src = nullptr;
         if (m < p.M) {
@@ -227,10 +277,16 @@ contract_bwd_x_tc_kernel(const BwdXTcParams p) {
             src = p.dout + ((int64_t)q * p.N + n) * p.G;
         }
         for (int gb = 0; gb < p.GB; ++gb) {
-            const int g = gb * 32 + lane;
-            const float v = (src && g < p.G) ? __ldg(src + g) : 0.f;
-            store_split(a_hi + (size_t)gb * kTileBytes, a_lo + (size_t)gb * kTileBytes,
-                        sw128_offset((uint32_t)r, (uint32_t)lane), v);
+            const int g = gb * 32 + c0;
+            float v[VEC];
+            if (src && g < p.G) {
+                ldg_vec<VEC>(src + g, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+            }
+            store_split_vec<VEC>(a_hi + (size_t)gb * kTileBytes, a_lo + (size_t)gb * kTileBytes,
+                                 sw128_offset((uint32_t)r, (uint32_t)c0), v);
         }
     }
     tcgen05_fence_before();
@@ -240,6 +296,12 @@ contract_bwd_x_tc_kernel(const BwdXTcParams p) {
     const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)p.NT, 0, 0);
     const int m = m0 + tid;
     const bool live = m < p.M;
+    // When this CTA owns every column of a row (one d-chunk) and D is not a multiple of 4, rows are
+    // staged in shared memory so that each warp writes its 32 x D block of the slab as one contiguous,
+    // coalesced run; otherwise each thread writes its own row with 16-byte stores.
+    const bool linear = (gridDim.y == 1) && (p.D % 4 != 0);
+    const int rows_live = min(32, p.M - (m0 + warp * 32));   // may be <= 0
+    float* my_epi = epi + (size_t)warp * 32 * p.NT;
 
     auto epilogue = [&](int j) {
         const int s = j & 1;
@@ -249,10 +311,30 @@ contract_bwd_x_tc_kernel(const BwdXTcParams p) {
         for (int cb = 0; cb < p.NT; cb += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * p.NT + cb), v);
-            if (!live) continue;
+            if (linear) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (n0 + cb + i < p.D) dst[cb + i] = v[i];
+                for (int i = 0; i < 16; ++i)
+                    if (cb + i < p.D) my_epi[lane * p.D + cb + i] = v[i];
+            } else if (live) {
+                if (p.D % 4 == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        if (n0 + cb + i < p.D) *reinterpret_cast<float4*>(dst + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + cb + i < p.D) dst[cb + i] = v[i];
+                }
+            }
+        }
+        if (linear) {
+            __syncwarp();
+            if (rows_live > 0) {
+                float* wdst = p.gstack + (int64_t)j * p.S + (int64_t)(m0 + warp * 32) * p.D;
+                const int cnt = rows_live * p.D;
+                for (int t = lane; t < cnt; t += 32) wdst[t] = my_epi[t];
+            }
+            __syncwarp();
         }
         tcgen05_fence_before();
     };
@@ -300,20 +382,26 @@ contract_bwd_x_tc_kernel(const BwdXTcParams p) {
 // ------------------------------------------------------------------------------------------------
 // backward w.r.t. the (mixed) weights: dW[(j,d), g] = sum_m P_j[m, d] dOut[m, g]
 // A^T and dOut are consumed in their natural layouts as MN-major operands (reduction index m = rows).
+// A CTA owns the orders [j0, j0 + JC); its packed output index is mn = (j - j0) * DPAD + d.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwKT = 16;   // m rows per staged unit (two k-groups of 8)
+constexpr int kBwKT = 16;      // m rows per staged unit (two MMA k-steps of 8)
+constexpr int kBwMaxFloats = 48;   // staged A floats per thread per unit (JC * CB * 4)
 
 struct BwdWTcParams {
     const float* stack; int64_t S;
     const float* dout;
-    float* partial;          // [P][JD][G]
-    int M, Q, N, D, G, GP, K, JD;
-    int MT;                  // 128-row output tiles per CTA; blockIdx.y selects the group
+    float* partial;          // [P][K*D][G]
+    int M, Q, N, D, G, GP, K;
+    int DPAD, CB, JC, MT;    // padded D (multiple of 8), 32-column blocks per order, orders per CTA, output tiles
     int units_per_cta;       // units (of kBwKT rows) each blockIdx.x walks, contiguous
 };
 
+template <int VEC, int VECG>
 __global__ void __launch_bounds__(kTcThreads)
 contract_bwd_w_tc_kernel(const BwdWTcParams p) {
+    constexpr int LPR = 32 / VEC;
+    constexpr int RG = kBwKT / VEC;                          // row groups per (order, column block)
+    constexpr int NSLOT = kBwMaxFloats / VEC;                // staged vectors per thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     const uint32_t blk = kBwKT * kRowBytes;                 // one 32-wide MN block: KT rows x 128 B = 2 KB
@@ -325,10 +413,15 @@ contract_bwd_w_tc_kernel(const BwdWTcParams p) {
     __shared__ __align__(8) uint64_t bar_free[2];
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / LPR, c0 = (lane % LPR) * VEC;
     const uint32_t ncols = tmem_cols_pow2((uint32_t)(p.MT * p.GP));
-    const int mn0 = blockIdx.y * p.MT * 128;                 // first packed (j,d) index of this CTA
-    const int mn_cnt = min(p.MT * 128, p.JD - mn0);          // live packed indices
+    const int j0 = blockIdx.y * p.JC;
+    const int jc = min(p.JC, p.K - j0);
+    const int mn_cnt = jc * p.DPAD;                          // packed indices this CTA produces
+    const int n_items = jc * p.CB * RG;                      // (order, column block, row group) triples
+    const int GV = p.G / VECG;
+    const int n_bitems = kBwKT * GV;
 
     if (tid == 0) {
         mbar_init(&bar_free[0], 1);
@@ -347,37 +440,86 @@ contract_bwd_w_tc_kernel(const BwdWTcParams p) {
     const int total_units = (p.M + kBwKT - 1) / kBwKT;
     const int u_begin = blockIdx.x * p.units_per_cta;
     const int u_end = min(total_units, u_begin + p.units_per_cta);
+
+    float abuf[kBwMaxFloats];
+    float bbuf[8 * VECG];                                    // up to 8 dOut vectors per thread (G <= 256)
+
+    auto load_unit = [&](int u) {
+        const int mbase = u * kBwKT;
+#pragma unroll
+        for (int e = 0; e < NSLOT; ++e) {
+            const int item = warp + 4 * e;
+            bool ok = item < n_items;
+            int jl = 0, cbk = 0, rg = 0;
+            if (ok) {
+                rg = item % RG;
+                const int t = item / RG;
+                cbk = t % p.CB;
+                jl = t / p.CB;
+            }
+            const int k = rg * VEC + sub;
+            const int d = cbk * 32 + c0;
+            ok = ok && d < p.D && mbase + k < p.M;
+            if (ok) {
+                ldg_vec<VEC>(p.stack + (int64_t)(j0 + jl) * p.S + (int64_t)(mbase + k) * p.D + d, &abuf[e * VEC]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) abuf[e * VEC + i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int item = tid + kTcThreads * e;
+            if (item < n_bitems) {
+                const int k = item / GV, gv = item - k * GV;
+                const int m = mbase + k;
+                if (m < p.M) {
+                    const int n = m / p.Q, q = m - n * p.Q;
+                    ldg_vec<VECG>(p.dout + ((int64_t)q * p.N + n) * p.G + gv * VECG, &bbuf[e * VECG]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VECG; ++i) bbuf[e * VECG + i] = 0.f;
+                }
+            }
+        }
+    };
+
     int it = 0;
+    if (u_begin < u_end) load_unit(u_begin);
     for (int u = u_begin; u < u_end; ++u, ++it) {
         const int s = it & 1;
-        const int mbase = u * kBwKT;
         if (it >= 2) mbar_wait(&bar_free[s], (uint32_t)(((it >> 1) - 1) & 1));
         uint8_t* ah = st[s];
         uint8_t* al = st[s] + a_part;
         uint8_t* bh = st[s] + 2 * a_part;
         uint8_t* bl = bh + b_part;
-        // A: element (k = m - mbase, mn) = stack[j][m][d], mn - mn0 = packed index inside this CTA
-        for (int i = tid; i < kBwKT * mn_cnt; i += kTcThreads) {
-            const int k = i / mn_cnt, mnl = i - k * mn_cnt;
-            const int mn = mn0 + mnl;
-            const int j = mn / p.D, d = mn - j * p.D;
-            const int m = mbase + k;
-            const float v = (m < p.M) ? __ldg(p.stack + (int64_t)j * p.S + (int64_t)m * p.D + d) : 0.f;
-            const uint32_t off = (uint32_t)(mnl >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(mnl & 31));
-            store_split(ah, al, off, v);
-        }
-        // B: element (k, g) = dout[api(m)][g]
-        for (int i = tid; i < kBwKT * p.G; i += kTcThreads) {
-            const int k = i / p.G, g = i - k * p.G;
-            const int m = mbase + k;
-            float v = 0.f;
-            if (m < p.M) {
-                const int n = m / p.Q, q = m - n * p.Q;
-                v = __ldg(p.dout + ((int64_t)q * p.N + n) * p.G + g);
+#pragma unroll
+        for (int e = 0; e < NSLOT; ++e) {
+            const int item = warp + 4 * e;
+            if (item < n_items) {
+                const int rg = item % RG;
+                const int t = item / RG;
+                const int cbk = t % p.CB, jl = t / p.CB;
+                const int d = cbk * 32 + c0;
+                if (d < p.D) {
+                    const int k = rg * VEC + sub;
+                    const int mn = jl * p.DPAD + d;
+                    const uint32_t off = (uint32_t)(mn >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(mn & 31));
+                    store_split_vec<VEC>(ah, al, off, &abuf[e * VEC]);
+                }
             }
-            const uint32_t off = (uint32_t)(g >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(g & 31));
-            store_split(bh, bl, off, v);
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int item = tid + kTcThreads * e;
+            if (item < n_bitems) {
+                const int k = item / GV, gv = item - k * GV;
+                const int g = gv * VECG;
+                const uint32_t off = (uint32_t)(g >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(g & 31));
+                store_split_vec<VECG>(bh, bl, off, &bbuf[e * VECG]);
+            }
+        }
+        if (u + 1 < u_end) load_unit(u + 1);
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -400,26 +542,30 @@ contract_bwd_w_tc_kernel(const BwdWTcParams p) {
             umma_commit(&bar_free[s]);
         }
     }
-    float* dst_base = p.partial + (int64_t)blockIdx.x * p.JD * p.G;
+    // partial[blockIdx.x][(j, d)][g]
+    float* dst_base = p.partial + (int64_t)blockIdx.x * p.K * p.D * p.G;
     if (it > 0) {
         const int il = it - 1;
         mbar_wait(&bar_free[il & 1], (uint32_t)((il >> 1) & 1));
         tcgen05_fence_after();
         for (int t = 0; t < p.MT; ++t) {
             if (t * 128 >= mn_cnt) break;
-            const int mn = mn0 + t * 128 + tid;
+            const int mn = t * 128 + tid;
+            const int jl = mn / p.DPAD, d = mn - jl * p.DPAD;
+            const bool ok = mn < mn_cnt && d < p.D;
+            float* dst = dst_base + ((int64_t)(j0 + jl) * p.D + d) * p.G;
             for (int cb = 0; cb < p.GP; cb += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * p.GP + cb), v);
-                if (mn < p.JD) {
+                if (ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (cb + i < p.G) dst_base[(int64_t)mn * p.G + cb + i] = v[i];
+                        if (cb + i < p.G) dst[cb + i] = v[i];
                 }
             }
         }
     } else {
-        for (int i = tid; i < mn_cnt * p.G; i += kTcThreads) dst_base[(int64_t)mn0 * p.G + i] = 0.f;
+        for (int i = tid; i < jc * p.D * p.G; i += kTcThreads) dst_base[(int64_t)j0 * p.D * p.G + i] = 0.f;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -433,8 +579,8 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct TcPlan {
     bool ok;
-    int GP, KB, DP, GB, NT, NY;          // fwd / bwd_x
-    int GPw, MT, NYw, P, units_per_cta;  // bwd_w
+    int GP, KB, DP, GB, NT, NY;                          // fwd / bwd_x
+    int GPw, DPAD, CB, JC, MT, NYw, P, units_per_cta;    // bwd_w
     size_t smem_fwd, smem_bwdx, smem_bwdw;
     int64_t img_fwd_bytes, img_bwdx_bytes;
 };
@@ -449,17 +595,20 @@ static TcPlan make_plan(int Q, int N, int D, int G, int K) {
     t.NT = t.DP <= 64 ? t.DP : 64;
     t.DP = round_up(t.DP, t.NT);
     t.NY = t.DP / t.NT;
+    // bwd_w
     t.GPw = round_up(G, 32);
-    const int JD = K * D;
-    const int tiles = (JD + 127) / 128;
-    int mt = 256 / t.GPw;                 // <= 256 TMEM columns per CTA so that two CTAs share an SM
-    if (mt > 3) mt = 3;                   // keeps the two-stage ring at <= ~100 KB
-    if (mt < 1) mt = 1;
-    if (mt > tiles) mt = tiles;
-    t.MT = mt;
-    t.NYw = (tiles + mt - 1) / mt;
+    t.DPAD = round_up(D, 8);
+    t.CB = (D + 31) / 32;
+    int mt = t.GPw <= 256 ? 256 / t.GPw : 0;             // <= 256 TMEM columns per CTA: two CTAs share an SM
+    if (mt > 3) mt = 3;                                  // keeps the two-stage ring near 100 KB
+    int jc = mt > 0 ? (mt * 128) / t.DPAD : 0;           // orders whose packed outputs fit the CTA's tiles
+    if (jc > kBwMaxFloats / 4 / t.CB) jc = kBwMaxFloats / 4 / t.CB;   // staged floats per thread: JC * CB * 4
+    if (jc > K) jc = K;
+    t.JC = jc;
+    t.MT = jc > 0 ? (jc * t.DPAD + 127) / 128 : 0;
+    t.NYw = jc > 0 ? (K + jc - 1) / jc : 0;
     const int64_t total_units = (M + kBwKT - 1) / kBwKT;
-    int64_t want = (2 * (int64_t)kNumSMs) / t.NYw;
+    int64_t want = t.NYw > 0 ? (2 * (int64_t)kNumSMs) / t.NYw : 1;
     if (want < 1) want = 1;
     if (want > total_units) want = total_units > 0 ? total_units : 1;
     t.units_per_cta = (int)((total_units + want - 1) / want);
@@ -467,14 +616,14 @@ static TcPlan make_plan(int Q, int N, int D, int G, int K) {
     t.P = (int)((total_units + t.units_per_cta - 1) / t.units_per_cta);
     if (t.P < 1) t.P = 1;
     t.smem_fwd = 1024 + 4 * (size_t)kTileBytes + 4 * (size_t)t.GP * kRowBytes;
-    t.smem_bwdx = 1024 + 2 * (size_t)t.GB * kTileBytes + 2 * 2 * (size_t)t.GB * t.NT * kRowBytes;
+    t.smem_bwdx = 1024 + 2 * (size_t)t.GB * kTileBytes + 2 * 2 * (size_t)t.GB * t.NT * kRowBytes + 128 * (size_t)t.NT * 4;
     const size_t blk = kBwKT * kRowBytes;
     t.smem_bwdw = 1024 + 2 * (2 * (size_t)t.MT * 4 * blk + 2 * (size_t)(t.GPw / 32) * blk);
     t.img_fwd_bytes = (int64_t)K * t.KB * 2 * t.GP * kRowBytes;
     t.img_bwdx_bytes = (int64_t)K * t.GB * 2 * t.DP * kRowBytes;
     const size_t lim = 200 * 1024;
-    t.ok = G <= 256 && t.GP <= 256 && t.GB <= 4 && t.smem_fwd <= lim && t.smem_bwdx <= lim && t.smem_bwdw <= lim &&
-           M < (int64_t)INT32_MAX - 256;
+    t.ok = G <= 256 && t.GP <= 256 && t.GB <= 4 && jc >= 1 && t.smem_fwd <= lim && t.smem_bwdx <= lim &&
+           t.smem_bwdw <= lim && M < (int64_t)INT32_MAX - 256;
     return t;
 }
 
@@ -502,6 +651,14 @@ static uint8_t* align_up(void* p, size_t a) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + a - 1) & ~(uintptr_t)(a - 1));
 }
 
+// widest vector (in fp32) with which rows of `ld` floats starting at `base` can be read
+static int vec_width(const void* base, int64_t ld, int64_t slab) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+    if (ld % 4 == 0 && slab % 4 == 0 && a % 16 == 0) return 4;
+    if (ld % 2 == 0 && slab % 2 == 0 && a % 8 == 0) return 2;
+    return 1;
+}
+
 int contract_fwd_tc(const float* stack, const float* Wmix, const float* bias, int bias_mode, float* out, void* scratch,
                     int Q, int N, int D, int G, int K, cudaStream_t st) {
     const TcPlan t = make_plan(Q, N, D, G, K);
@@ -516,8 +673,18 @@ int contract_fwd_tc(const float* stack, const float* Wmix, const float* bias, in
     FwdTcParams p{};
     p.stack = stack; p.S = (int64_t)N * Q * D; p.wimg = img; p.bias = bias; p.bias_mode = bias_mode; p.out = out;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GP; p.K = K; p.KB = t.KB;
-    TGCN_PROPAGATE(set_smem(contract_fwd_tc_kernel, t.smem_fwd, "contract_fwd_tc"));
-    contract_fwd_tc_kernel<<<(unsigned)ceil_div(p.M, kTileM), kTcThreads, t.smem_fwd, st>>>(p);
+    const unsigned grid = (unsigned)ceil_div(p.M, kTileM);
+    const int vec = vec_width(stack, D, p.S);
+    if (vec == 4) {
+        TGCN_PROPAGATE(set_smem(contract_fwd_tc_kernel<4>, t.smem_fwd, "contract_fwd_tc"));
+        contract_fwd_tc_kernel<4><<<grid, kTcThreads, t.smem_fwd, st>>>(p);
+    } else if (vec == 2) {
+        TGCN_PROPAGATE(set_smem(contract_fwd_tc_kernel<2>, t.smem_fwd, "contract_fwd_tc"));
+        contract_fwd_tc_kernel<2><<<grid, kTcThreads, t.smem_fwd, st>>>(p);
+    } else {
+        TGCN_PROPAGATE(set_smem(contract_fwd_tc_kernel<1>, t.smem_fwd, "contract_fwd_tc"));
+        contract_fwd_tc_kernel<1><<<grid, kTcThreads, t.smem_fwd, st>>>(p);
+    }
     TGCN_LAUNCH_CHECK("contract_fwd_tc");
     return TGCN_OK;
 }
@@ -536,10 +703,35 @@ int contract_bwd_x_tc(const float* dout, const float* Wmix, float* gstack, void*
     BwdXTcParams p{};
     p.dout = dout; p.wimg = img; p.gstack = gstack; p.S = (int64_t)N * Q * D;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.DP = t.DP; p.K = K; p.GB = t.GB; p.NT = t.NT;
-    TGCN_PROPAGATE(set_smem(contract_bwd_x_tc_kernel, t.smem_bwdx, "contract_bwd_x_tc"));
     dim3 grid((unsigned)ceil_div(p.M, kTileM), (unsigned)t.NY);
-    contract_bwd_x_tc_kernel<<<grid, kTcThreads, t.smem_bwdx, st>>>(p);
+    const int vec = vec_width(dout, G, 4);
+    // the 16-byte row stores of the epilogue need 16-byte aligned slab rows
+    TGCN_SUPPORTED(D % 4 != 0 || (reinterpret_cast<uintptr_t>(gstack) % 16 == 0 && p.S % 4 == 0),
+                   "contract_bwd_x_tc: gstack must be 16-byte aligned");
+    if (vec == 4) {
+        TGCN_PROPAGATE(set_smem(contract_bwd_x_tc_kernel<4>, t.smem_bwdx, "contract_bwd_x_tc"));
+        contract_bwd_x_tc_kernel<4><<<grid, kTcThreads, t.smem_bwdx, st>>>(p);
+    } else if (vec == 2) {
+        TGCN_PROPAGATE(set_smem(contract_bwd_x_tc_kernel<2>, t.smem_bwdx, "contract_bwd_x_tc"));
+        contract_bwd_x_tc_kernel<2><<<grid, kTcThreads, t.smem_bwdx, st>>>(p);
+    } else {
+        TGCN_PROPAGATE(set_smem(contract_bwd_x_tc_kernel<1>, t.smem_bwdx, "contract_bwd_x_tc"));
+        contract_bwd_x_tc_kernel<1><<<grid, kTcThreads, t.smem_bwdx, st>>>(p);
+    }
     TGCN_LAUNCH_CHECK("contract_bwd_x_tc");
+    return TGCN_OK;
+}
+
+template <int VEC>
+static int launch_bwd_w(const BwdWTcParams& p, const TcPlan& t, int vecg, cudaStream_t st) {
+    dim3 grid((unsigned)t.P, (unsigned)t.NYw);
+    if (vecg == 4) {
+        TGCN_PROPAGATE(set_smem(contract_bwd_w_tc_kernel<VEC, 4>, t.smem_bwdw, "contract_bwd_w_tc"));
+        contract_bwd_w_tc_kernel<VEC, 4><<<grid, kTcThreads, t.smem_bwdw, st>>>(p);
+    } else {
+        TGCN_PROPAGATE(set_smem(contract_bwd_w_tc_kernel<VEC, 1>, t.smem_bwdw, "contract_bwd_w_tc"));
+        contract_bwd_w_tc_kernel<VEC, 1><<<grid, kTcThreads, t.smem_bwdw, st>>>(p);
+    }
     return TGCN_OK;
 }
 
@@ -550,11 +742,16 @@ int contract_bwd_w_tc(const float* stack, const float* dout, float* partial, int
     TGCN_SUPPORTED(t.ok, "contract_bwd_w_tc: shape D=%d G=%d outside the tcgen05 tiles", D, G);
     BwdWTcParams p{};
     p.stack = stack; p.S = (int64_t)N * Q * D; p.dout = dout; p.partial = partial;
-    p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GPw; p.K = K; p.JD = K * D; p.MT = t.MT;
+    p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GPw; p.K = K;
+    p.DPAD = t.DPAD; p.CB = t.CB; p.JC = t.JC; p.MT = t.MT;
     p.units_per_cta = t.units_per_cta;
-    TGCN_PROPAGATE(set_smem(contract_bwd_w_tc_kernel, t.smem_bwdw, "contract_bwd_w_tc"));
-    dim3 grid((unsigned)t.P, (unsigned)t.NYw);
-    contract_bwd_w_tc_kernel<<<grid, kTcThreads, t.smem_bwdw, st>>>(p);
+    const int vec = vec_width(stack, D, p.S);
+    int vecg = vec_width(dout, G, 4) == 4 ? 4 : 1;
+    if (vecg == 4 && (int64_t)kBwKT * (G / 4) > 8 * kTcThreads) vecg = 1;
+    TGCN_SUPPORTED((int64_t)kBwKT * (G / vecg) <= 8 * kTcThreads, "contract_bwd_w_tc: G=%d too wide for the dOut staging registers", G);
+    if (vec == 4) TGCN_PROPAGATE(launch_bwd_w<4>(p, t, vecg, st));
+    else if (vec == 2) TGCN_PROPAGATE(launch_bwd_w<2>(p, t, vecg, st));
+    else TGCN_PROPAGATE(launch_bwd_w<1>(p, t, vecg, st));
     TGCN_LAUNCH_CHECK("contract_bwd_w_tc");
     *P_out = t.P;
     return TGCN_OK;

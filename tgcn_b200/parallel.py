@@ -72,3 +72,94 @@ def broadcast_parameters(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-partitioned SpMM with halo exchange (graphs too large for
+# one GPU's bandwidth budget).  Rank p owns a contiguous block of rows of L~ and of every slab;
+# before each recursion step it needs the previous slab's rows for the columns it references
+# outside its block (the halo).  The plan is computed once on the host.
+# ------------------------------------------------------------------------------------------------
+class RowPartition:
+    """Host-side plan for one rank.
+
+    local CSR: rows [lo, hi) of L~, columns renumbered to [0, n_own) for owned rows followed by
+    [n_own, n_own + n_halo) for halo rows (sorted by global id, grouped by owner).
+    send_idx[q]: local row ids (0..n_own) this rank sends to rank q each step.
+    recv_cnt[q]: number of halo rows received from rank q (they land contiguously, in owner order).
+    """
+
+    def __init__(self, L_csr, rank, world, bounds=None):
+        import numpy as np
+        L = L_csr.tocsr()
+        n = L.shape[0]
+        self.rank, self.world, self.n_global = rank, world, n
+        if bounds is None:
+            bounds = [shard_range(n, r, world) for r in range(world)]
+        self.bounds = bounds
+        lo, hi = bounds[rank]
+        self.lo, self.hi, self.n_own = lo, hi, hi - lo
+        starts = np.array([b[0] for b in bounds] + [n])
+        sub = L[lo:hi].tocsr()
+        sub.sort_indices()
+        cols = sub.indices.astype(np.int64)
+        outside = (cols < lo) | (cols >= hi)
+        halo_ids = np.unique(cols[outside])                       # sorted => grouped by owner
+        owner = np.searchsorted(starts, halo_ids, side="right") - 1
+        self.halo_ids = halo_ids
+        self.n_halo = int(halo_ids.size)
+        self.recv_cnt = [int((owner == q).sum()) for q in range(world)]
+        remap = np.empty(cols.shape, dtype=np.int64)
+        remap[~outside] = cols[~outside] - lo
+        remap[outside] = self.n_own + np.searchsorted(halo_ids, cols[outside])
+        self.rowptr = sub.indptr.astype(np.int32)
+        self.col = remap.astype(np.int32)
+        self.val = sub.data.astype(np.float32)
+        self.recv_ids = [halo_ids[owner == q] for q in range(world)]   # global ids wanted from q
+        self.send_idx = None                                           # filled by exchange_plans
+
+    @staticmethod
+    def exchange_plans(plans):
+        """Single-process helper (tests / one host building every rank's plan): derive send lists."""
+        import numpy as np
+        for p in plans:
+            p.send_idx = [None] * p.world
+        for p in plans:
+            for q in range(p.world):
+                plans[q].send_idx[p.rank] = (p.recv_ids[q] - plans[q].lo).astype(np.int64)
+        return plans
+
+    def build_send_lists(self, group=None):
+        """Multi-process: tell every owner which of its rows this rank needs (one all-gather of the
+        wanted-id lists; run once per graph)."""
+        import numpy as np
+        wanted = [None] * self.world
+        dist.all_gather_object(wanted, [ids.tolist() for ids in self.recv_ids], group=group)
+        self.send_idx = [np.asarray(wanted[q][self.rank], dtype=np.int64) - self.lo for q in range(self.world)]
+        return self
+
+
+def halo_exchange(slab_own, plan, halo_out=None, group=None):
+    """Gather the rows other ranks need from `slab_own` [n_own, C] and receive this rank's halo rows
+    into `halo_out` [n_halo, C] (point-to-point sends grouped per step: NCCL send/recv over NVLink on
+    GPUs, gloo on CPU)."""
+    C = slab_own.shape[1]
+    if halo_out is None:
+        halo_out = slab_own.new_empty((plan.n_halo, C))
+    ops, keep = [], []
+    off = 0
+    for q in range(plan.world):
+        cnt = plan.recv_cnt[q]
+        if q != plan.rank and cnt:
+            ops.append(dist.P2POp(dist.irecv, halo_out[off:off + cnt], q, group=group))
+        off += cnt
+    for q in range(plan.world):
+        idx = plan.send_idx[q]
+        if q != plan.rank and idx is not None and len(idx):
+            buf = slab_own.index_select(0, torch.as_tensor(idx, device=slab_own.device))
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, q, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return halo_out
