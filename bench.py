@@ -275,7 +275,7 @@ def run_b200(args):
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "final_loss": float(loss_host),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -394,7 +394,7 @@ def run_reference(args):
             "config": {"workload": args.workload, "description": cfg["desc"], "per_gpu_batch": cfg["batch"]},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
