@@ -122,8 +122,17 @@ def test_large_tile_counts_tc():
                                        eng, st) == 0, _lib.last_error()
         torch.cuda.synchronize()
         res[eng] = (out, dW)
-    assert float((res[TC][0] - res[FFMA][0]).abs().max() / res[FFMA][0].abs().max()) < 1e-5
-    assert float((res[TC][1] - res[FFMA][1]).abs().max() / res[FFMA][1].abs().max()) < 1e-5
+    # checker: fp64 on the device (both fp32 engines carry ~sqrt(n) eps of accumulation error over 3.3e5 terms)
+    ref_out = torch.zeros(Q, N, G, device="cuda", dtype=torch.float64)
+    ref_dW = torch.zeros(K, D, G, device="cuda", dtype=torch.float64)
+    for j in range(K):
+        Pj = stack[j].double().reshape(N, Q, D)
+        ref_out += torch.einsum("nqd,dg->qng", Pj, W[j].double())
+        ref_dW[j] = torch.einsum("nqd,qng->dg", Pj, dout.double())
+    ref_out += bias.double()[None]
+    for eng in (FFMA, TC):
+        assert float((res[eng][0].double() - ref_out).abs().max() / ref_out.abs().max()) < 1e-5, eng
+        assert float((res[eng][1].double() - ref_dW).abs().max() / ref_dW.abs().max()) < 5e-5, eng
 
 
 @pytest.mark.parametrize("case", LAYER_CASES)

@@ -10,6 +10,7 @@
 // threads stage fp32 tiles global -> registers -> (hi, lo) swizzled shared-memory tiles, one
 // thread issues the MMAs asynchronously, and several CTAs per SM overlap each other's phases.
 #include "common.cuh"
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace tgcn {
@@ -19,8 +20,11 @@ constexpr int kTcThreads = 128;
 constexpr int kTileM = 128;                 // rows (pairs) per CTA tile = UMMA M
 constexpr uint32_t kTileBytes = 128 * 128;  // one [128 x 32 fp32] operand tile
 
+// Align the dynamic shared-memory window to 1024 B with pointer arithmetic on the __shared__ array itself,
+// so that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST).
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
-    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+    const uint32_t a = tc::smem_u32(p);
+    return p + (((a + 1023u) & ~1023u) - a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -577,6 +581,18 @@ contract_bwd_w_tc_kernel(const BwdWTcParams p) {
 // ------------------------------------------------------------------------------------------------
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// second-generation (persistent, TMA-fed) kernels, contract_tc2.cu
+int contract_fwd_tc2(const float* stack, const uint8_t* wimg, const float* bias, int bias_mode, float* out,
+                     int Q, int N, int D, int G, int GP, int K, cudaStream_t st, int* launched);
+int contract_bwd_w_tc2(const float* stack, const float* dout, float* partial, int* P_out,
+                       int Q, int N, int D, int G, int K, cudaStream_t st, int* launched);
+int bwd_w2_partials(int Q, int N, int D, int G, int K);
+
+static bool use_v2() {
+    static const bool on = [] { const char* e = getenv("TGCN_TC_V1"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 struct TcPlan {
     bool ok;
     int GP, KB, DP, GB, NT, NY;                          // fwd / bwd_x
@@ -636,7 +652,8 @@ int64_t tc_fwd_scratch_bytes(int Q, int N, int D, int G, int K) {
 }
 int64_t tc_bwd_scratch_bytes(int Q, int N, int D, int G, int K) {
     const TcPlan t = make_plan(Q, N, D, G, K);
-    const int64_t partial = (int64_t)t.P * K * D * G * (int64_t)sizeof(float);
+    const int p2 = bwd_w2_partials(Q, N, D, G, K);
+    const int64_t partial = (int64_t)(t.P > p2 ? t.P : p2) * K * D * G * (int64_t)sizeof(float);
     return t.img_bwdx_bytes + partial + 2048;
 }
 
@@ -673,6 +690,11 @@ int contract_fwd_tc(const float* stack, const float* Wmix, const float* bias, in
     FwdTcParams p{};
     p.stack = stack; p.S = (int64_t)N * Q * D; p.wimg = img; p.bias = bias; p.bias_mode = bias_mode; p.out = out;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GP; p.K = K; p.KB = t.KB;
+    if (use_v2()) {
+        int launched = 0;
+        TGCN_PROPAGATE(contract_fwd_tc2(stack, img, bias, bias_mode, out, Q, N, D, G, t.GP, K, st, &launched));
+        if (launched) return TGCN_OK;
+    }
     const unsigned grid = (unsigned)ceil_div(p.M, kTileM);
     const int vec = vec_width(stack, D, p.S);
     if (vec == 4) {
@@ -740,6 +762,11 @@ int contract_bwd_w_tc(const float* stack, const float* dout, float* partial, int
                       int Q, int N, int D, int G, int K, cudaStream_t st) {
     const TcPlan t = make_plan(Q, N, D, G, K);
     TGCN_SUPPORTED(t.ok, "contract_bwd_w_tc: shape D=%d G=%d outside the tcgen05 tiles", D, G);
+    if (use_v2()) {
+        int launched = 0;
+        TGCN_PROPAGATE(contract_bwd_w_tc2(stack, dout, partial, P_out, Q, N, D, G, K, st, &launched));
+        if (launched) return TGCN_OK;
+    }
     BwdWTcParams p{};
     p.stack = stack; p.S = (int64_t)N * Q * D; p.dout = dout; p.partial = partial;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GPw; p.K = K;
