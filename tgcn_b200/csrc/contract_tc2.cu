@@ -20,7 +20,7 @@ using namespace tc;
 
 constexpr int kT2Threads = 320;       // 8 transform warps + producer warp + MMA warp
 constexpr int kT2Transform = 8;       // transform / epilogue warps
-constexpr int kT2Raw = 3;             // raw ring depth
+constexpr int kT2RawMax = 6;          // raw ring depth (run-time value R <= kT2RawMax, sized to fill shared memory)
 constexpr int kT2Op = 2;              // operand stage depth
 constexpr uint32_t kT2TileBytes = 128 * 128;
 
@@ -85,6 +85,8 @@ struct Fwd2Params {
     int M, Q, N, D, G, GP, K;
     int ntiles;
     uint32_t rawA_bytes;           // slot size reserved for the A chunk (128*D*4 rounded up to 1024)
+    int R;                         // raw ring depth
+    int dbg;
 };
 
 template <int VEC>
@@ -99,13 +101,14 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
     const uint32_t raw_bytes = p.rawA_bytes + wbytes;             // [A raw | W image]
     uint8_t* op_base = smem;
     uint8_t* raw_base = smem + kT2Op * op_bytes;
-    __shared__ __align__(8) uint64_t raw_full[kT2Raw], raw_free[kT2Raw], op_full[kT2Op], op_free[kT2Op], acc_full, acc_free;
+    __shared__ __align__(8) uint64_t raw_full[kT2RawMax], raw_free[kT2RawMax], op_full[kT2Op], op_free[kT2Op], acc_full, acc_free;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t R = (uint32_t)p.R;
     const uint32_t ncols = tmem_cols_pow2((uint32_t)p.GP);
     if (tid == 0) {
-        for (int i = 0; i < kT2Raw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kT2Transform); }
+        for (int i = 0; i < kT2RawMax; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kT2Transform); }
         for (int i = 0; i < kT2Op; ++i) { mbar_init(&op_full[i], kT2Transform); mbar_init(&op_free[i], 1); }
         mbar_init(&acc_full, 1);
         mbar_init(&acc_free, kT2Transform);
@@ -119,21 +122,34 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
 
     if (warp == kT2Transform) {
         // ===================== producer =====================
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int m0 = tile * 128;
-                const int rows = min(128, p.M - m0);
-                const uint32_t bytesA = (uint32_t)rows * (uint32_t)p.D * 4u;
-                const bool direct = (bytesA & 15u) != 0;          // ragged tail: transform warps read global themselves
-                for (int j = 0; j < p.K; ++j, ++g) {
-                    const uint32_t r = g % kT2Raw;
-                    if (g >= kT2Raw) mbar_wait(&raw_free[r], ((g / kT2Raw) - 1) & 1);
-                    uint8_t* slot = raw_base + r * raw_bytes;
-                    mbar_arrive_expect_tx(&raw_full[r], wbytes + (direct ? 0u : bytesA));
-                    if (!direct) bulk_g2s(slot, p.stack + (int64_t)j * p.S + (int64_t)m0 * p.D, bytesA, &raw_full[r]);
+        // lane 0 waits for the slot and posts the expected byte count; lanes 0..3 each copy a quarter of the
+        // A chunk and lane 4 the weight image, so five bulk copies per unit are in flight at once
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int m0 = tile * 128;
+            const int rows = min(128, p.M - m0);
+            const uint32_t bytesA = (uint32_t)rows * (uint32_t)p.D * 4u;
+            const bool direct = (bytesA & 15u) != 0;          // ragged tail: transform warps read global themselves
+            const uint32_t piece = ((bytesA / 4u) + 15u) & ~15u;      // quarter, rounded up to 16 B
+            for (int j = 0; j < p.K; ++j, ++g) {
+                const uint32_t r = g % R;
+                uint8_t* slot = raw_base + r * raw_bytes;
+                if (lane == 0) {
+                    if (g >= R) mbar_wait(&raw_free[r], ((g / R) - 1) & 1);
+                    mbar_arrive_expect_tx(&raw_full[r], ((p.dbg & 16) ? 0u : wbytes) + (direct ? 0u : bytesA));
+                }
+                __syncwarp();
+                if (lane < 4 && !direct) {
+                    const uint32_t off = (uint32_t)lane * piece;
+                    if (off < bytesA) {
+                        const uint32_t len = min(piece, bytesA - off);
+                        bulk_g2s(slot + off, reinterpret_cast<const uint8_t*>(p.stack + (int64_t)j * p.S + (int64_t)m0 * p.D) + off,
+                                 len, &raw_full[r]);
+                    }
+                } else if (lane == 4 && !(p.dbg & 16)) {
                     bulk_g2s(slot + p.rawA_bytes, p.wimg + (int64_t)j * wbytes, wbytes, &raw_full[r]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == kT2Transform + 1) {
@@ -154,6 +170,7 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
                     const uint64_t dbh = make_desc_kmajor(smem_u32(op + 2 * kT2TileBytes));
                     const uint64_t dbl = make_desc_kmajor(smem_u32(op + 2 * kT2TileBytes + wbytes / 2));
                     for (int ks = 0; ks < nks; ++ks) {
+                        if (p.dbg & 1) break;
                         const uint64_t adv = (uint64_t)(ks * 2);
                         umma_tf32(tmem_acc, dal + adv, dbh + adv, idesc, (j | ks) ? 1u : 0u);
                         umma_tf32(tmem_acc, dah + adv, dbl + adv, idesc, 1u);
@@ -175,10 +192,10 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
             const int rows = min(128, p.M - m0);
             const bool direct = (((uint32_t)rows * (uint32_t)p.D * 4u) & 15u) != 0;
             for (int j = 0; j < p.K; ++j, ++g) {
-                const uint32_t r = g % kT2Raw, s = g % kT2Op;
+                const uint32_t r = g % R, s = g % kT2Op;
                 const uint8_t* slot = raw_base + r * raw_bytes;
                 float buf[16];
-                mbar_wait(&raw_full[r], (g / kT2Raw) & 1);
+                mbar_wait(&raw_full[r], (g / R) & 1);
 #pragma unroll
                 for (int e = 0; e < NI; ++e) {
                     const int row = warp * 16 + e * VEC + sub;
@@ -186,6 +203,7 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) buf[e * VEC + i] = 0.f;
                     } else if (!direct) {
+                        if (p.dbg & 4) { for (int i = 0; i < VEC; ++i) buf[e * VEC + i] = 1.f; } else
                         lds_vec<VEC>(slot + ((uint32_t)row * (uint32_t)p.D + (uint32_t)c0) * 4u, &buf[e * VEC]);
                     } else {
 #pragma unroll
@@ -200,19 +218,21 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int idx = tid + i * 256;
-                    if (idx < wpieces) wv[i] = wsrc[idx];
+                    if (idx < wpieces && !(p.dbg & 16)) wv[i] = wsrc[idx];
                 }
                 if (g >= kT2Op) mbar_wait(&op_free[s], ((g / kT2Op) - 1) & 1);
                 uint8_t* op = op_base + s * op_bytes;
+                if (!(p.dbg & 2)) {
 #pragma unroll
                 for (int e = 0; e < NI; ++e)
                     split_store<VEC>(op, op + kT2TileBytes, sw128_offset((uint32_t)(warp * 16 + e * VEC + sub), (uint32_t)c0),
                                      &buf[e * VEC]);
+                }
                 float4* wdst = reinterpret_cast<float4*>(op + 2 * kT2TileBytes);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int idx = tid + i * 256;
-                    if (idx < wpieces) wdst[idx] = wv[i];
+                    if (idx < wpieces && !(p.dbg & 16)) wdst[idx] = wv[i];
                 }
                 // The raw slot is released only here: the stores above consumed every register loaded from it,
                 // so no load from the slot can still be in flight when the producer's next bulk copy lands
@@ -236,7 +256,7 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
             for (int cb = ch * 16; cb < p.GP; cb += 32) {
                 float v[16];
                 tmem_ld16(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)cb, v);
-                if (!live) continue;
+                if (!live || (p.dbg & 32)) continue;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int gc = cb + i;
@@ -279,6 +299,7 @@ struct BwdW2Params {
     int DPAD, JC, MT;
     int units_per_cta;
     uint32_t rawA_bytes;           // JC * 16 * D * 4 rounded up to 128
+    int R;                         // raw ring depth
 };
 
 template <int VEC>
@@ -297,10 +318,11 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
     const uint32_t raw_bytes = p.rawA_bytes + kBw2KT * rowG;
     uint8_t* op_base = smem;
     uint8_t* raw_base = smem + kT2Op * op_bytes;
-    __shared__ __align__(8) uint64_t raw_full[kT2Raw], raw_free[kT2Raw], op_full[kT2Op], op_free[kT2Op], acc_full;
+    __shared__ __align__(8) uint64_t raw_full[kT2RawMax], raw_free[kT2RawMax], op_full[kT2Op], op_free[kT2Op], acc_full;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t R = (uint32_t)p.R;
     const uint32_t ncols = tmem_cols_pow2((uint32_t)(p.MT * p.GP));
     const int j0 = blockIdx.y * p.JC;
     const int jc = min(p.JC, p.K - j0);
@@ -311,7 +333,7 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
     const uint32_t chunkA = (uint32_t)kBw2KT * (uint32_t)p.D * 4u;      // one order's 16 rows
 
     if (tid == 0) {
-        for (int i = 0; i < kT2Raw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kT2Transform); }
+        for (int i = 0; i < kT2RawMax; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kT2Transform); }
         for (int i = 0; i < kT2Op; ++i) { mbar_init(&op_full[i], kT2Transform); mbar_init(&op_free[i], 1); }
         mbar_init(&acc_full, 1);
         fence_mbar_init();
@@ -329,13 +351,13 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
         // ===================== producer (all lanes issue copies) =====================
         uint32_t g = 0;
         for (int u = u_begin; u < u_end; ++u, ++g) {
-            const uint32_t r = g % kT2Raw;
+            const uint32_t r = g % R;
             const int mbase = u * kBw2KT;
             const int rows = min(kBw2KT, p.M - mbase);
             const bool direct = rows < kBw2KT;                    // ragged last unit: transform warps read global
             uint8_t* slot = raw_base + r * raw_bytes;
             if (lane == 0) {
-                if (g >= kT2Raw) mbar_wait(&raw_free[r], ((g / kT2Raw) - 1) & 1);
+                if (g >= R) mbar_wait(&raw_free[r], ((g / R) - 1) & 1);
                 mbar_arrive_expect_tx(&raw_full[r], direct ? 0u : (uint32_t)jc * chunkA + (uint32_t)rows * rowG);
             }
             __syncwarp();
@@ -392,14 +414,14 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
         const int n_bitems = kBw2KT * GV;
         uint32_t g = 0;
         for (int u = u_begin; u < u_end; ++u, ++g) {
-            const uint32_t r = g % kT2Raw, s = g % kT2Op;
+            const uint32_t r = g % R, s = g % kT2Op;
             const uint8_t* slot = raw_base + r * raw_bytes;
             const int mbase = u * kBw2KT;
             const int rows = min(kBw2KT, p.M - mbase);
             const bool direct = rows < kBw2KT;
             float abuf[24];
             float4 bbuf[2];
-            mbar_wait(&raw_full[r], (g / kT2Raw) & 1);
+            mbar_wait(&raw_full[r], (g / R) & 1);
 #pragma unroll
             for (int e = 0; e < NSLOT; ++e) {
                 const int item = warp + kT2Transform * e;
@@ -530,8 +552,15 @@ int contract_fwd_tc2(const float* stack, const uint8_t* wimg, const float* bias,
     p.rawA_bytes = (uint32_t)round_up2(128 * D * 4, 1024);
     if (const char* e = getenv("TGCN_T2_PAD")) p.rawA_bytes += (uint32_t)atoi(e);
     const size_t wbytes = 2 * (size_t)GP * kRowBytes;
-    const size_t smem = 1024 + kT2Op * (2 * (size_t)kT2TileBytes + wbytes) + kT2Raw * ((size_t)p.rawA_bytes + wbytes);
-    if (smem > kT2SmemLimit) return TGCN_OK;
+    const size_t op_total = 1024 + kT2Op * (2 * (size_t)kT2TileBytes + wbytes);
+    const size_t raw_slot = (size_t)p.rawA_bytes + wbytes;
+    if (op_total + 2 * raw_slot > kT2SmemLimit) return TGCN_OK;
+    int R = (int)((kT2SmemLimit - op_total) / raw_slot);
+    if (R > kT2RawMax) R = kT2RawMax;
+    if (const char* e = getenv("TGCN_T2_R")) { const int v = atoi(e); if (v >= 2 && v <= R) R = v; }
+    p.R = R;
+    if (const char* e = getenv("TGCN_T2_DBG")) p.dbg = atoi(e);
+    const size_t smem = op_total + (size_t)R * raw_slot;
     const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
     if (D % 4 == 0) {
         TGCN_PROPAGATE(set_smem2(contract_fwd_tc2_kernel<4>, smem, "contract_fwd_tc2"));
@@ -549,7 +578,7 @@ int contract_fwd_tc2(const float* stack, const uint8_t* wimg, const float* bias,
 }
 
 // plan of the v2 bwd_w kernel; P (number of partial slabs) must match the workspace sizing in contract_tc.cu
-struct BwdW2Plan { bool ok; int GP, DPAD, JC, MT, NY, P, units_per_cta; size_t smem; uint32_t rawA; };
+struct BwdW2Plan { bool ok; int GP, DPAD, JC, MT, NY, P, units_per_cta, R; size_t smem; uint32_t rawA; };
 
 static BwdW2Plan make_bwd_w2_plan(int Q, int N, int D, int G, int K) {
     BwdW2Plan t{};
@@ -576,8 +605,12 @@ static BwdW2Plan make_bwd_w2_plan(int Q, int N, int D, int G, int K) {
     const size_t op = 2 * (size_t)t.MT * 4 * blk + 2 * (size_t)(t.GP / 32) * blk;
     t.rawA = (uint32_t)round_up2(jc * kBw2KT * D * 4, 128);
     const size_t raw = (size_t)t.rawA + (size_t)kBw2KT * G * 4;
-    t.smem = 1024 + kT2Op * op + kT2Raw * raw;
-    t.ok = jc >= 1 && D <= 32 && G % 4 == 0 && G <= 128 && (kBw2KT * (G / 4)) <= 512 && t.smem <= kT2SmemLimit && M > 0;
+    int R = (1024 + kT2Op * op + 2 * raw <= kT2SmemLimit) ? (int)((kT2SmemLimit - 1024 - kT2Op * op) / raw) : 0;
+    if (R > kT2RawMax) R = kT2RawMax;
+    if (const char* e = getenv("TGCN_T2_R")) { const int v = atoi(e); if (v >= 2 && v <= R) R = v; }
+    t.R = R;
+    t.smem = 1024 + kT2Op * op + (size_t)(R > 0 ? R : 0) * raw;
+    t.ok = R >= 2 && jc >= 1 && D <= 32 && G % 4 == 0 && G <= 128 && (kBw2KT * (G / 4)) <= 512 && t.smem <= kT2SmemLimit && M > 0;
     return t;
 }
 
@@ -596,7 +629,7 @@ int contract_bwd_w_tc2(const float* stack, const float* dout, float* partial, in
     BwdW2Params p{};
     p.stack = stack; p.S = S; p.dout = dout; p.partial = partial;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GP; p.K = K;
-    p.DPAD = t.DPAD; p.JC = t.JC; p.MT = t.MT; p.units_per_cta = t.units_per_cta; p.rawA_bytes = t.rawA;
+    p.DPAD = t.DPAD; p.JC = t.JC; p.MT = t.MT; p.units_per_cta = t.units_per_cta; p.rawA_bytes = t.rawA; p.R = t.R;
     dim3 grid((unsigned)t.P, (unsigned)t.NY);
     if (D % 4 == 0) {
         TGCN_PROPAGATE(set_smem2(contract_bwd_w_tc2_kernel<4>, t.smem, "contract_bwd_w_tc2"));
