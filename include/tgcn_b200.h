@@ -50,6 +50,7 @@ extern "C" {
 #define TGCN_ENGINE_AUTO 0
 #define TGCN_ENGINE_FFMA 1    /* fp32 CUDA-core path (exact fp32 accumulation)                  */
 #define TGCN_ENGINE_TCGEN05 2 /* tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulate in TMEM   */
+#define TGCN_ENGINE_RESIDENT 3 /* sample-resident fused layer kernels (small graphs), fp32 FFMA    */
 
 int tgcn_version(void);
 const char* tgcn_last_error(void);
@@ -145,6 +146,33 @@ int tgcn_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* val
                    const float* dout, const float* stack, const float* Wmix,
                    float* dW, float* db, int bias_mode, float* dx, float* gstack, void* workspace,
                    int Q, int D, int G, int K, int recursion, int engine, void* stream);
+
+/* ---- sample-resident fused layer (graphs whose per-sample slab [N,D] fits in shared memory) ---- */
+/* One CTA per sample runs the whole layer: recursion in shared memory, contraction accumulated in
+ * registers across all K orders, bias (+ optional ReLU + permuted max-pool) in the epilogue; the
+ * basis is written to HBM once for the backward.  Replaces, per layer, the K-1 `bmm` launches, the
+ * einsum and the following F.relu + gcn_pool(_4) of the reference models (gcn.py:108-154, :189-237,
+ * :246-255; pytorch_hcp_tgcn.py:133-141).  `W` is the RAW layer weight [K,D,G] (the recursion's
+ * basis change is applied on the fly); the CSR triplet is the same as for tgcn_spmm_step.
+ *   out  [Q,N,G] or NULL;  y [Q,N/pool_p,G] + idx (uint8) or NULL (at least one of out / y);
+ *   relu != 0 applies max(.,0) before the pool;  stack: tgcn_resident_stack_bytes(...) bytes or NULL
+ *   (NULL = inference, no backward).  1 = supported for these sizes, 0 = use the streaming path. */
+int tgcn_resident_supported(int N, int D, int G, int K, int64_t nnz);
+int64_t tgcn_resident_stack_bytes(int Q, int N, int D, int K);
+int64_t tgcn_resident_bwd_workspace(int Q, int N, int D, int G, int K);
+int tgcn_resident_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N, int64_t nnz,
+                            const float* x, const float* W, const float* bias, int bias_mode,
+                            float* out, float* y, uint8_t* idx, int pool_p, int relu, float* stack,
+                            int Q, int D, int G, int K, int recursion, void* stream);
+/* Backward of the above.  Pass exactly one of `dout` [Q,N,G] (un-pooled output was returned) or
+ * `dy` [Q,N/pool_p,G] with the forward's `idx` and pooled output `y` (the max-pool / ReLU gradient
+ * routing is applied on the fly).  Produces dW [K,D,G], db (per bias_mode), dx [Q,N,D] (if non-NULL;
+ * needs the CSR of L^T).  `workspace`: tgcn_resident_bwd_workspace(...) bytes.  Deterministic. */
+int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N, int64_t nnz,
+                            const float* dout, const float* dy, const uint8_t* idx, const float* y,
+                            int pool_p, int relu, const float* stack, const float* W,
+                            float* dW, float* db, int bias_mode, float* dx, void* workspace,
+                            int Q, int D, int G, int K, int recursion, void* stream);
 
 /* ---- host-side graph preprocessing (CPU, no device work) ----------------------------------- */
 /* One level of greedy heavy-edge (Graclus-normalised) matching: replaces the pure-Python loop

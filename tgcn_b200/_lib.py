@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libtgcn_b200.so")
 OK = 0
 BIAS_NONE, BIAS_PER_VERTEX, BIAS_PER_FILTER = 0, 1, 2
 RECURSION_REFERENCE, RECURSION_CHEBYSHEV = 0, 1
-ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05, ENGINE_RESIDENT = 0, 1, 2, 3
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -45,6 +45,12 @@ SIGNATURES = {
     "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_layer_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
     "tgcn_layer_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_resident_supported": (_i, [_i, _i, _i, _i, _l]),
+    "tgcn_resident_stack_bytes": (_l, [_i, _i, _i, _i]),
+    "tgcn_resident_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
+    "tgcn_resident_layer_fwd": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_resident_layer_bwd": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p,
+                                     _i, _i, _i, _i, _i, _p]),
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
 }

@@ -100,6 +100,88 @@ class ChebLayerFunction(torch.autograd.Function):
         return dx, dW, db, None, None, None, None
 
 
+def resident_supported(plan, D, G, K):
+    """True when the sample-resident fused kernels cover this layer (per-sample slab fits in shared memory)."""
+    return bool(_lib.load().tgcn_resident_supported(plan.n, D, G, K, plan.nnz))
+
+
+class ResidentChebFunction(torch.autograd.Function):
+    """Whole layer in one launch per direction (csrc/resident.cu): basis + contraction + bias, optionally
+    followed by ReLU + permuted max-pool (`pool_p` in {2, 4}) without materialising the un-pooled
+    activation.  Same math as ChebLayerFunction (+ PoolFunction); gcn.py:108-154, :246-255."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan, bias_mode, recursion, pool_p, relu):
+        lib = _lib.load()
+        Q, N, D = x.shape
+        K, Dw, G = weight.shape
+        if Dw != D:
+            raise RuntimeError("weight expects %d features per vertex, input has %d" % (Dw, D))
+        if N != plan.n:
+            raise RuntimeError("input has %d vertices, Laplacian has %d" % (N, plan.n))
+        if pool_p and N % pool_p:
+            raise RuntimeError("shape '[%d, %d, %d, %d]' is invalid for input of size %d"
+                               % (Q, N // pool_p, pool_p, G, Q * N * G))
+        dev = x.device
+        x = x.contiguous()
+        w = weight.contiguous()
+        b = None if bias is None else bias.contiguous()
+        bm = bias_mode if b is not None else _lib.BIAS_NONE
+        need_grad = any(ctx.needs_input_grad[:3])   # grad mode is off inside Function.forward
+        stack = torch.empty(int(lib.tgcn_resident_stack_bytes(Q, N, D, K)) // 4, dtype=torch.float32, device=dev) \
+            if need_grad else None
+        if pool_p:
+            out = None
+            y = torch.empty((Q, N // pool_p, G), dtype=torch.float32, device=dev)
+            idx = torch.empty((Q, N // pool_p, G), dtype=torch.uint8, device=dev)
+        else:
+            out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
+            y = idx = None
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_resident_layer_fwd(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, plan.nnz, _ptr(x), _ptr(w),
+                                             _ptr(b), bm, _ptr(out), _ptr(y), _ptr(idx), pool_p, int(relu), _ptr(stack),
+                                             Q, D, G, K, recursion, _stream(dev))
+        _lib.check(rc, "tgcn_resident_layer_fwd")
+        ctx.plan = plan
+        ctx.dims = (Q, N, D, G, K)
+        ctx.cfg = (bm, recursion, pool_p, bool(relu))
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.w_shape = tuple(weight.shape)
+        ctx.x_shape = tuple(x.shape)
+        if pool_p:
+            ctx.save_for_backward(stack, w, y, idx)
+            ctx.mark_non_differentiable(idx)
+            return y, idx
+        ctx.save_for_backward(stack, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad, _didx=None):
+        lib = _lib.load()
+        Q, N, D, G, K = ctx.dims
+        bm, recursion, pool_p, relu = ctx.cfg
+        plan = ctx.plan
+        saved = ctx.saved_tensors
+        stack, w = saved[0], saved[1]
+        y, idx = (saved[2], saved[3]) if pool_p else (None, None)
+        if stack is None:
+            raise RuntimeError("resident layer was run without gradient tracking; nothing saved for backward")
+        dev = grad.device
+        grad = grad.contiguous()
+        need_dx = ctx.needs_input_grad[0]
+        dW = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
+        db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=dev) if bm != _lib.BIAS_NONE else None
+        dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev) if need_dx else None
+        ws = torch.empty(max(int(lib.tgcn_resident_bwd_workspace(Q, N, D, G, K)) // 4, 1), dtype=torch.float32, device=dev)
+        with _DeviceGuard(dev):
+            rc = lib.tgcn_resident_layer_bwd(_ptr(plan.rowptr_t), _ptr(plan.col_t), _ptr(plan.val_t), N, plan.nnz,
+                                             None if pool_p else _ptr(grad), _ptr(grad) if pool_p else None, _ptr(idx), _ptr(y),
+                                             pool_p, int(relu), _ptr(stack), _ptr(w), _ptr(dW), _ptr(db), bm, _ptr(dx), _ptr(ws),
+                                             Q, D, G, K, recursion, _stream(dev))
+        _lib.check(rc, "tgcn_resident_layer_bwd")
+        return dx, dW, db, None, None, None, None, None
+
+
 class PoolFunction(torch.autograd.Function):
     """Permuted max-pool with first-argmax gradient routing (tgcn/nn/gcn.py:246-255), optional fused ReLU."""
 

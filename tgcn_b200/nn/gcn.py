@@ -19,7 +19,8 @@ from ..csr import CSRCache
 from . import functional as F_
 
 _RECURSION = {"reference": _lib.RECURSION_REFERENCE, "chebyshev": _lib.RECURSION_CHEBYSHEV}
-_ENGINE = {"auto": _lib.ENGINE_AUTO, "ffma": _lib.ENGINE_FFMA, "tcgen05": _lib.ENGINE_TCGEN05}
+_ENGINE = {"auto": _lib.ENGINE_AUTO, "ffma": _lib.ENGINE_FFMA, "tcgen05": _lib.ENGINE_TCGEN05,
+           "resident": _lib.ENGINE_RESIDENT}
 
 
 def uniform(size, tensor):
@@ -67,18 +68,44 @@ class _ChebBase(torch.nn.Module):
     def _canon(self, x):
         raise NotImplementedError
 
-    def _run(self, x3):
+    def _use_resident(self, plan, D, G, K):
+        """engine="auto": the sample-resident fused kernels whenever one sample's slab fits in shared
+        memory, else the streaming path; engine="resident" insists (error if it does not fit)."""
+        if self.engine not in ("auto", "resident"):
+            return False
+        ok = F_.resident_supported(plan, D, G, K)
+        if self.engine == "resident" and not ok:
+            raise RuntimeError("engine='resident': N=%d D=%d G=%d K=%d nnz=%d does not fit the resident kernels"
+                               % (plan.n, D, G, K, plan.nnz))
+        return ok
+
+    def _run(self, x3, pool_p=0, relu=False):
         F_._require_cuda_f32(x3, "x")
         w = self.weight
         F_._require_cuda_f32(w, "weight")
         K = w.shape[0]
         w3 = w.reshape(K, -1, w.shape[-1])
-        return F_.ChebLayerFunction.apply(x3, w3, self.bias, self._plan(x3.device), self._bias_mode,
-                                          _RECURSION[self.recursion], _ENGINE[self.engine])
+        plan = self._plan(x3.device)
+        rec = _RECURSION[self.recursion]
+        if self._use_resident(plan, w3.shape[1], w3.shape[2], K):
+            res = F_.ResidentChebFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, pool_p, relu)
+            return res[0] if pool_p else res
+        out = F_.ChebLayerFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, _ENGINE[self.engine])
+        if pool_p:
+            out = F_.PoolFunction.apply(out, pool_p, relu)[0]
+        return out
 
     def forward(self, x):
         x3 = self._canon(x)
         return self._run(x3)
+
+    def forward_relu_pool(self, x, p):
+        """gcn_pool / gcn_pool_4 (p = 2 / 4) of F.relu(self(x)) as one fused operation
+        (pytorch_hcp_tgcn.py:133-141 applies exactly this chain after each conv layer): identical
+        values, pool indices and gradients, without writing the un-pooled activation."""
+        if p not in (2, 4):
+            raise ValueError("pool size must be 2 (gcn_pool) or 4 (gcn_pool_4)")
+        return self._run(self._canon(x), pool_p=p, relu=True)
 
     def _basis(self, x):
         x3 = self._canon(x)

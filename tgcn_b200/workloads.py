@@ -123,10 +123,11 @@ class NetTGCN_HCP(nn.Module):
         self.fused = fused_relu_pool
 
     def forward(self, x):
-        x = self.tgcn1(x)
-        x = relu_pool(x, 4) if self.fused else gcn_pool_4(F.relu(x))
-        x = self.gcn2(x)
-        x = relu_pool(x, 4) if self.fused else gcn_pool_4(F.relu(x))
+        if self.fused:
+            x = self.gcn2.forward_relu_pool(self.tgcn1.forward_relu_pool(x, 4), 4)
+        else:
+            x = gcn_pool_4(F.relu(self.tgcn1(x)))
+            x = gcn_pool_4(F.relu(self.gcn2(x)))
         x = x.reshape(x.shape[0], -1)
         x = F.relu(self.dense1_bn(self.fc1(x)))
         return F.log_softmax(self.fc2(x), dim=1)
