@@ -153,24 +153,37 @@ int tgcn_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* val
  * basis is written to HBM once for the backward.  Replaces, per layer, the K-1 `bmm` launches, the
  * einsum and the following F.relu + gcn_pool(_4) of the reference models (gcn.py:108-154, :189-237,
  * :246-255; pytorch_hcp_tgcn.py:133-141).  `W` is the RAW layer weight [K,D,G] (the recursion's
- * basis change is applied on the fly); the CSR triplet is the same as for tgcn_spmm_step.
+ * basis change is applied on the fly).  Small batches are split over 2 or 4 CTAs per sample (a
+ * thread-block cluster exchanging rows through distributed shared memory in the forward).
  *   out  [Q,N,G] or NULL;  y [Q,N/pool_p,G] + idx (uint8) or NULL (at least one of out / y);
  *   relu != 0 applies max(.,0) before the pool;  stack: tgcn_resident_stack_bytes(...) bytes or NULL
  *   (NULL = inference, no backward).  1 = supported for these sizes, 0 = use the streaming path. */
 int tgcn_resident_supported(int N, int D, int G, int K, int64_t nnz);
 int64_t tgcn_resident_stack_bytes(int Q, int N, int D, int K);
 int64_t tgcn_resident_bwd_workspace(int Q, int N, int D, int G, int K);
-int tgcn_resident_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N, int64_t nnz,
+/* bytes of the weight images ([K][DP][GP] mixed weights and their transpose) the forward writes into
+ * `wimages` and the backward reads back */
+int64_t tgcn_resident_weights_bytes(int D, int G, int K);
+/* The resident kernels read L~ as a PACKED CSR: rowinfo[n] = (start, len) (2*N int32 rounded up to a multiple of 4, start even) and
+ * entries[e] = (col, float bits of val) (2*E int32, 16-byte aligned), with each row's entries ordered
+ * so that rows sharing a quarter-warp gather from different shared-memory bank groups.  Build it once
+ * per graph on the host with tgcn_pack_csr_host (entries_host == NULL: size query; returns E) using
+ * classes = tgcn_resident_pack_classes(Q, N, D, backward) and upload both arrays.  Any `classes`
+ * value gives correct results; the matching one gives the fewest bank conflicts. */
+int64_t tgcn_pack_csr_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
+                           int classes, int32_t* rowinfo_host, int32_t* entries_host);
+int tgcn_resident_pack_classes(int Q, int N, int D, int backward);
+int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* entries, int N, int64_t E,
                             const float* x, const float* W, const float* bias, int bias_mode,
                             float* out, float* y, uint8_t* idx, int pool_p, int relu, float* stack,
-                            int Q, int D, int G, int K, int recursion, void* stream);
+                            float* wimages, int Q, int D, int G, int K, int recursion, void* stream);
 /* Backward of the above.  Pass exactly one of `dout` [Q,N,G] (un-pooled output was returned) or
  * `dy` [Q,N/pool_p,G] with the forward's `idx` and pooled output `y` (the max-pool / ReLU gradient
  * routing is applied on the fly).  Produces dW [K,D,G], db (per bias_mode), dx [Q,N,D] (if non-NULL;
- * needs the CSR of L^T).  `workspace`: tgcn_resident_bwd_workspace(...) bytes.  Deterministic. */
-int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N, int64_t nnz,
+ * needs the packed CSR of L^T).  `workspace`: tgcn_resident_bwd_workspace(...) bytes.  Deterministic. */
+int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, int N, int64_t E,
                             const float* dout, const float* dy, const uint8_t* idx, const float* y,
-                            int pool_p, int relu, const float* stack, const float* W,
+                            int pool_p, int relu, const float* stack, const float* wimages,
                             float* dW, float* db, int bias_mode, float* dx, void* workspace,
                             int Q, int D, int G, int K, int recursion, void* stream);
 

@@ -48,8 +48,11 @@ SIGNATURES = {
     "tgcn_resident_supported": (_i, [_i, _i, _i, _i, _l]),
     "tgcn_resident_stack_bytes": (_l, [_i, _i, _i, _i]),
     "tgcn_resident_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
-    "tgcn_resident_layer_fwd": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
-    "tgcn_resident_layer_bwd": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p,
+    "tgcn_pack_csr_host": (_l, [_p, _p, _p, _i, _i, _p, _p]),
+    "tgcn_resident_pack_classes": (_i, [_i, _i, _i, _i]),
+    "tgcn_resident_weights_bytes": (_l, [_i, _i, _i]),
+    "tgcn_resident_layer_fwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_resident_layer_bwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p,
                                      _i, _i, _i, _i, _i, _p]),
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),

@@ -13,7 +13,8 @@ import torch
 class LaplacianCSR:
     """int32 CSR of L and of L^T resident on one CUDA device."""
 
-    __slots__ = ("n", "nnz", "rowptr", "col", "val", "rowptr_t", "col_t", "val_t", "symmetric", "device")
+    __slots__ = ("n", "nnz", "rowptr", "col", "val", "rowptr_t", "col_t", "val_t", "symmetric", "device",
+                 "_host", "_packed", "_lock")
 
     def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, symmetric, device):
         self.n, self.nnz = n, int(col.numel())
@@ -21,6 +22,40 @@ class LaplacianCSR:
         self.rowptr_t, self.col_t, self.val_t = rowptr_t, col_t, val_t
         self.symmetric = symmetric
         self.device = device
+        self._host = None          # (crow, col, val, crow_t, col_t, val_t) as int32/float32 numpy, for packing
+        self._packed = {}
+        self._lock = threading.Lock()
+
+    def packed(self, classes, transpose=False):
+        """Packed, bank-ordered CSR for the sample-resident kernels (include/tgcn_b200.h,
+        tgcn_pack_csr_host): (rowinfo int32 [N,2], entries int32 [E,2], E) on this device, cached."""
+        if self.symmetric:
+            transpose = False
+        key = (int(classes), bool(transpose))
+        hit = self._packed.get(key)
+        if hit is not None:
+            return hit
+        with self._lock:
+            hit = self._packed.get(key)
+            if hit is not None:
+                return hit
+            from . import _lib
+            lib = _lib.load()
+            if self._host is None:
+                self._host = tuple(np.ascontiguousarray(t.cpu().numpy()) for t in
+                                   (self.rowptr, self.col, self.val, self.rowptr_t, self.col_t, self.val_t))
+            rp, c, v = self._host[3:] if transpose else self._host[:3]
+            rowinfo = np.zeros((max((self.n + 1) & ~1, 2), 2), dtype=np.int32)
+            E = int(lib.tgcn_pack_csr_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, self.n, key[0],
+                                           rowinfo.ctypes.data, None))
+            if E < 0:
+                raise RuntimeError("tgcn_pack_csr_host rejected the CSR operand")
+            entries = np.zeros((max(E, 2), 2), dtype=np.int32)
+            lib.tgcn_pack_csr_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, self.n, key[0], rowinfo.ctypes.data,
+                                   entries.ctypes.data)
+            hit = (torch.from_numpy(rowinfo).to(self.device), torch.from_numpy(entries).to(self.device), E)
+            self._packed[key] = hit
+        return hit
 
 
 def _to_scipy_like(L):

@@ -24,18 +24,6 @@ constexpr int kT2RawMax = 6;          // raw ring depth (run-time value R <= kT2
 constexpr int kT2Op = 2;              // operand stage depth
 constexpr uint32_t kT2TileBytes = 128 * 128;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D bulk copy global -> shared, completion (bytes) signalled on `bar`; 16-byte aligned, size % 16 == 0
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // Align the dynamic shared-memory window to 1024 B with pointer arithmetic on the __shared__ array itself,
 // so that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST).
 __device__ __forceinline__ uint8_t* align1024_2(uint8_t* p) {

@@ -1,15 +1,20 @@
 // Sample-resident fused layer kernels (TGCN_ENGINE_RESIDENT).
 //
 // The columns of the [N, Q*D] slab are independent through the whole recursion, so when one
-// sample's slab [N, D] fits in shared memory the complete layer runs out of one CTA per sample:
+// sample's slab [N, D] fits in shared memory the complete layer runs out of shared memory:
 //
-//   forward : P_0 = x_q;  P_j = L~ P_{j-1}  (CSR gather, shared -> shared, ping-pong);
-//             out += P_j * W'_j  after every step (accumulators live in registers for all K steps);
-//             epilogue adds the bias and optionally applies ReLU + the permuted max-pool, so the
+//   forward : P_0 = x_q;  P_j = L~ P_{j-1}  (packed-CSR gather, shared -> shared, ping-pong);
+//             out += P_j * W'_j after every step (accumulators live in registers for all K steps);
+//             the epilogue adds the bias and optionally applies ReLU + the permuted max-pool, so the
 //             un-pooled activation never reaches HBM.  Every P_j is written to HBM exactly once
-//             (coalesced, fire-and-forget) for the backward.
-//   backward: dW'_j = P_j^T dOut  (P_j streamed back from HBM/L2, dOut resident in shared memory),
-//             dx = sum_j (L~^T)^j (dOut W'_j^T) by Horner's rule on a resident [N, D] accumulator.
+//             (fire-and-forget) for the backward.  Small batches split a sample by rows over the
+//             2 or 4 CTAs of a thread-block cluster: each CTA computes its rows and pushes them into
+//             the peers' copies of the slab with st.async (distributed shared memory, completion
+//             counted on the receiver's mbarrier) -- no cluster-wide barrier inside the loop.
+//   backward: dW'_j = P_j^T dOut with the saved basis streamed HBM -> shared memory by 1-D bulk
+//             copies (cp.async.bulk, mbarrier ring) and dOut resident in shared memory (the max-pool /
+//             ReLU gradient routing is applied while it is staged);
+//             dx = sum_j (L~^T)^j (dOut W'_j^T) by Horner's rule on a resident accumulator.
 //             Per-sample partials are reduced over the batch by a second, deterministic kernel
 //             that also applies the transposed weight mix and produces the bias gradient.
 //
@@ -19,25 +24,20 @@
 // contraction is far below one SM-microsecond of tensor-core work and staging hi/lo TF32 operand
 // images would cost more shared-memory traffic than the FFMAs it replaces; the tcgen05 engine
 // (contract_tc*.cu) serves the large-graph configs where the stack streams from HBM.
+#include <cstdlib>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tgcn {
+using namespace tc;
 
-constexpr int kResThreads = 512;
 constexpr size_t kResSmemLimit = 227 * 1024;
 constexpr int kResMaxK = 32;
+constexpr int kBwdThreads = 512;
+constexpr int kRingStages = 3;
 
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
-
-// W'_j[e] of the reference recursion (see mix_weights_kernel in contract.cu), fp64 accumulate.
-__device__ __forceinline__ float mixed_weight(const float* __restrict__ W, int K, int64_t inner, int j, int64_t e,
-                                              int recursion) {
-    if (recursion == TGCN_RECURSION_CHEBYSHEV) return __ldg(W + (int64_t)j * inner + e);
-    const double c = j < 2 ? 1.0 : 2.0;
-    double s = 0.0, sign = 1.0;
-    for (int k = j; k < K; k += 2, sign = -sign) s += sign * c * (double)__ldg(W + (int64_t)k * inner + e);
-    return (float)s;
-}
+__host__ __device__ inline int round_up2(int v) { return (v + 1) & ~1; }
 
 __device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) {
     acc.x = fmaf(w, x.x, acc.x);
@@ -46,36 +46,84 @@ __device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) {
     acc.w = fmaf(w, x.w, acc.w);
 }
 
-// out[v] += sum_e val[e] * in[col[e]][v] for one row, one float4 column group; CSR pairs packed as
-// int2 (col, float bits) in shared memory (kCsrSmem) or read from global memory.
+// ------------------------------------------------------------------------------------------------
+// weight images: Wm[j][d][g] ([K][DP][GP], zero padded) = W'_j of the reference recursion
+// (W'_j = sum_k M[k,j] W_k, see mix_weights_kernel in contract.cu; plain copy for the textbook
+// recursion) and its transpose Wt[j][g][d] ([K][GP][DP]) for the dx recursion.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resident_prep_kernel(const float* __restrict__ W, float* __restrict__ Wm, float* __restrict__ Wt, int K, int D, int G,
+                     int DP, int GP, int recursion) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= DP * GP) return;
+    const int d = i / GP, g = i - d * GP;
+    const bool valid = d < D && g < G;
+    float w[kResMaxK];
+#pragma unroll
+    for (int k = 0; k < kResMaxK; ++k) w[k] = (valid && k < K) ? __ldg(W + ((int64_t)k * D + d) * G + g) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kResMaxK; ++j) {
+        if (j >= K) break;
+        float m;
+        if (recursion == TGCN_RECURSION_CHEBYSHEV) {
+            m = w[j];
+        } else {
+            const double c = j < 2 ? 1.0 : 2.0;
+            double s = 0.0, sign = 1.0;
+#pragma unroll
+            for (int k = j; k < kResMaxK; k += 2) {
+                if (k < K) s += sign * c * (double)w[k];
+                sign = -sign;
+            }
+            m = (float)s;
+        }
+        Wm[((int64_t)j * DP + d) * GP + g] = m;
+        Wt[((int64_t)j * GP + g) * DP + d] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed CSR: rowinfo[n] = (start, len), start even so a row's (col, val-bits) pairs can be read two
+// at a time as one 16-byte vector; within a row the entries are ordered so that the m rows that
+// share a quarter-warp hit different shared-memory bank groups at the same loop position (the
+// bank group of neighbour row c is c mod m when a CTA keeps 8/m float4 per row).
+// ------------------------------------------------------------------------------------------------
+template <bool kSmem>
+__device__ __forceinline__ int4 ld_pair(const int2* p) {
+    if (kSmem) return *reinterpret_cast<const int4*>(p);
+    return __ldg(reinterpret_cast<const int4*>(p));
+}
+template <bool kSmem>
+__device__ __forceinline__ int2 ld_one(const int2* p) {
+    if (kSmem) return *p;
+    return __ldg(p);
+}
+
+// sum_e val[e] * in[col[e]][v] for one row and one float4 column group (fixed summation order)
 template <bool kCsrSmem>
-__device__ __forceinline__ float4 gather_row(const int2* __restrict__ csr_s, const int* __restrict__ col,
-                                             const float* __restrict__ val, int e, const int e1,
+__device__ __forceinline__ float4 gather_row(const int2* __restrict__ ent, const int2 info,
                                              const float4* __restrict__ in4, const int V, const int v) {
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    for (; e + 4 <= e1; e += 4) {
-        int c0, c1, c2, c3;
-        float w0, w1, w2, w3;
-        if (kCsrSmem) {
-            const int2 p0 = csr_s[e], p1 = csr_s[e + 1], p2 = csr_s[e + 2], p3 = csr_s[e + 3];
-            c0 = p0.x; c1 = p1.x; c2 = p2.x; c3 = p3.x;
-            w0 = __int_as_float(p0.y); w1 = __int_as_float(p1.y); w2 = __int_as_float(p2.y); w3 = __int_as_float(p3.y);
-        } else {
-            c0 = __ldg(col + e); c1 = __ldg(col + e + 1); c2 = __ldg(col + e + 2); c3 = __ldg(col + e + 3);
-            w0 = __ldg(val + e); w1 = __ldg(val + e + 1); w2 = __ldg(val + e + 2); w3 = __ldg(val + e + 3);
-        }
-        const float4 x0 = in4[c0 * V + v], x1 = in4[c1 * V + v], x2 = in4[c2 * V + v], x3 = in4[c3 * V + v];
-        fma4s(a0, w0, x0);
-        fma4s(a1, w1, x1);
-        fma4s(a0, w2, x2);
-        fma4s(a1, w3, x3);
+    const int2* e = ent + info.x;
+    int k = 0;
+    for (; k + 4 <= info.y; k += 4) {
+        const int4 p01 = ld_pair<kCsrSmem>(e + k), p23 = ld_pair<kCsrSmem>(e + k + 2);
+        const float4 x0 = in4[p01.x * V + v], x1 = in4[p01.z * V + v], x2 = in4[p23.x * V + v], x3 = in4[p23.z * V + v];
+        fma4s(a0, __int_as_float(p01.y), x0);
+        fma4s(a1, __int_as_float(p01.w), x1);
+        fma4s(a0, __int_as_float(p23.y), x2);
+        fma4s(a1, __int_as_float(p23.w), x3);
     }
-    for (; e < e1; ++e) {
-        int c0;
-        float w0;
-        if (kCsrSmem) { const int2 p0 = csr_s[e]; c0 = p0.x; w0 = __int_as_float(p0.y); }
-        else { c0 = __ldg(col + e); w0 = __ldg(val + e); }
-        fma4s(a0, w0, in4[c0 * V + v]);
+    if (k + 2 <= info.y) {
+        const int4 p01 = ld_pair<kCsrSmem>(e + k);
+        const float4 x0 = in4[p01.x * V + v], x1 = in4[p01.z * V + v];
+        fma4s(a0, __int_as_float(p01.y), x0);
+        fma4s(a1, __int_as_float(p01.w), x1);
+        k += 2;
+    }
+    if (k < info.y) {
+        const int2 p0 = ld_one<kCsrSmem>(e + k);
+        fma4s(a0, __int_as_float(p0.y), in4[p0.x * V + v]);
     }
     return make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
 }
@@ -86,75 +134,143 @@ __device__ __forceinline__ void take_max_r(float cand, int s, float& best, int& 
     if (better) { best = cand; arg = s; }
 }
 
+// ---- thread-block cluster helpers (a sample may be split by rows over CL CTAs of one cluster)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// 16-byte store into a peer CTA's shared memory; completes 16 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, const float4& v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 struct ResFwdParams {
-    const int* rowptr; const int* col; const float* val;
+    const int2* rowinfo; const int2* entries;   // packed CSR of L~
     const float* x;        // [Q,N,D]
-    const float* W;        // [K,D,G] raw layer weights
+    const float* Wm;       // [K][DP][GP] mixed, padded weights (resident_prep_kernel)
     const float* bias;     // [N,G] / [G] / null
     float* out;            // [Q,N,G] or null
     float* y;              // [Q,N/p,G] or null (fused pool)
     uint8_t* idx;          // [Q,N/p,G]
-    float* stack;          // [Q][K][NP][DP] or null (inference)
-    int N, NP, nnz, D, DP, V, G, GP, GG, K;
+    float* stack;          // [Q][NP][K][DP] or null (inference)
+    int N, NP, E, D, DP, V, G, GP, GG, K;
     int bias_mode, recursion, pool_p, relu;
+    int CL, rg_per;        // CTAs per sample (cluster size) and row groups (of 4 rows) per CTA
 };
 
-struct ResSmemFwd { size_t rowptr, csr, P, W, total; };
+struct ResSmemFwd { size_t bars, P, W, csr, rowinfo, total; };
 
-static ResSmemFwd res_fwd_smem(int N, int nnz, int DP, int GP, bool csr_smem) {
+static ResSmemFwd res_fwd_smem(int N, int64_t E, int DP, int GP, int K, bool csr_smem, bool w_smem) {
     ResSmemFwd s{};
     const int NP = round_up4(N);
     size_t o = 0;
-    s.P = o;      o += sizeof(float) * 2 * (size_t)NP * DP;
-    s.W = o;      o += sizeof(float) * 2 * (size_t)DP * GP;
-    s.csr = o;    o += csr_smem ? sizeof(int2) * (size_t)nnz : 0;
-    s.rowptr = o; o += sizeof(int) * (size_t)(N + 1);
+    s.bars = o;    o += 64;
+    s.P = o;       o += sizeof(float) * 2 * (size_t)NP * DP;
+    s.W = o;       o += w_smem ? sizeof(float) * (size_t)K * DP * GP : 0;
+    s.csr = o;     o += csr_smem ? sizeof(int2) * (size_t)E : 0;
+    s.rowinfo = o; o += sizeof(int2) * (size_t)round_up2(N);
     s.total = (o + 15) & ~(size_t)15;
     return s;
 }
 
-template <int TPT, bool kCsrSmem>
-__global__ void __launch_bounds__(kResThreads, 1)
+template <int THREADS, int TPT, bool kCsrSmem, bool kWSmem>
+__global__ void __launch_bounds__(THREADS, 1)
 resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);     // [0] prologue loads, [1],[2] peer rows
     float* Pbuf = reinterpret_cast<float*>(smem + lay.P);
     float* Wsm = reinterpret_cast<float*>(smem + lay.W);
     int2* csr_s = reinterpret_cast<int2*>(smem + lay.csr);
-    int* rowptr_s = reinterpret_cast<int*>(smem + lay.rowptr);
+    int2* rowinfo_s = reinterpret_cast<int2*>(smem + lay.rowinfo);
 
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int q = blockIdx.x;
-    const int N = p.N, NP = p.NP, D = p.D, DP = p.DP, V = p.V, G = p.G, GP = p.GP, GG = p.GG, K = p.K;
-    const int slab = NP * DP;                               // floats per P buffer / per stack slab
+    const int tid = threadIdx.x;
+    constexpr int T = THREADS;
+    const int CL = p.CL;
+    const int q = blockIdx.x / CL, c = blockIdx.x - q * CL;    // 1-D clusters: c is the rank in the cluster
+    const int N = p.N, NP = p.NP, D = p.D, DP = p.DP, V = p.V, G = p.G, GG = p.GG, K = p.K;
+    const int slab = NP * DP;                                  // floats per P buffer
+    const int rg0 = c * p.rg_per, rg1 = min(NP / 4, rg0 + p.rg_per);
+    const int row0 = rg0 * 4, row1 = min(N, rg1 * 4);          // rows this CTA computes
+    const int wslab = DP * p.GP;
 
-    for (int i = tid; i <= N; i += T) rowptr_s[i] = __ldg(p.rowptr + i);
-    if (kCsrSmem)
-        for (int e = tid; e < p.nnz; e += T) csr_s[e] = make_int2(__ldg(p.col + e), __float_as_int(__ldg(p.val + e)));
-    {   // P_0 = x_q (zero pad columns / rows), also the first slab of the saved stack
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {   // operands that are used as they are: bulk copies straight into shared memory
+        const uint32_t b_ri = (uint32_t)sizeof(int2) * (uint32_t)round_up2(N);
+        const uint32_t b_csr = kCsrSmem ? (uint32_t)sizeof(int2) * (uint32_t)p.E : 0u;
+        const uint32_t b_w = kWSmem ? (uint32_t)sizeof(float) * (uint32_t)(K * wslab) : 0u;
+        mbar_arrive_expect_tx(&bars[0], b_ri + b_csr + b_w);
+        bulk_g2s(rowinfo_s, p.rowinfo, b_ri, &bars[0]);
+        if (b_csr) bulk_g2s(csr_s, p.entries, b_csr, &bars[0]);
+        if (b_w) bulk_g2s(Wsm, p.Wm, b_w, &bars[0]);
+    }
+    const int2* ent = kCsrSmem ? csr_s : p.entries;
+    {   // P_0 = x_q (zero pad columns / rows): every CTA of the cluster keeps the full slab; the owner
+        // of a row also writes it to the saved stack [q][n][j][DP]
         const float* xq = p.x + (int64_t)q * N * D;
-        float* st0 = p.stack ? p.stack + (int64_t)q * K * slab : nullptr;
-        for (int i = tid; i < slab; i += T) {
-            const int n = i / DP, d = i - n * DP;
-            const float v = (n < N && d < D) ? __ldg(xq + (int64_t)n * D + d) : 0.f;
-            Pbuf[i] = v;
-            if (st0) st0[i] = v;
+        float* stq = p.stack ? p.stack + (int64_t)q * NP * K * DP : nullptr;
+        if (DP != D || NP != N) {
+            for (int i = tid; i < slab; i += T) {
+                const int n = i / DP, d = i - n * DP;
+                if (n >= N || d >= D) Pbuf[i] = 0.f;
+            }
+        }
+        const int total = N * D;
+        if ((total & 3) == 0 && aligned16(p.x)) {
+            const float4* x4 = reinterpret_cast<const float4*>(xq);
+            for (int i4 = tid; i4 < total / 4; i4 += T) {
+                const float4 v = __ldg(x4 + i4);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                if (DP == D) {
+                    reinterpret_cast<float4*>(Pbuf)[i4] = v;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = 4 * i4 + u, n = e / D, d = e - n * D;
+                        Pbuf[n * DP + d] = vv[u];
+                    }
+                }
+            }
+        } else {
+            for (int e = tid; e < total; e += T) {
+                const int n = e / D, d = e - n * D;
+                Pbuf[n * DP + d] = __ldg(xq + e);
+            }
+        }
+        __syncthreads();
+        if (stq) {
+            const float4* P4 = reinterpret_cast<const float4*>(Pbuf);
+            float4* st4 = reinterpret_cast<float4*>(stq);
+            for (int i = row0 * V + tid; i < rg1 * 4 * V; i += T) {
+                const int n = i / V, v = i - n * V;
+                st4[(n * K) * V + v] = P4[i];
+            }
         }
     }
-    const int64_t inner = (int64_t)D * G;
-    auto stage_w = [&](int j) {
-        float* dst = Wsm + (j & 1) * DP * GP;
-        for (int i = tid; i < DP * GP; i += T) {
-            const int d = i / GP, g = i - d * GP;
-            dst[i] = (d < D && g < G) ? mixed_weight(p.W, K, inner, j, (int64_t)d * G + g, p.recursion) : 0.f;
-        }
-    };
-    stage_w(0);
-    __syncthreads();
+    uint32_t peer_data[3] = {0u, 0u, 0u}, peer_bar[3] = {0u, 0u, 0u};
+    if (CL > 1) {
+        const uint32_t mine = smem_u32(Pbuf), mybar = smem_u32(&bars[1]);
+        int k = 0;
+        for (int r = 0; r < CL; ++r)
+            if (r != c) { peer_data[k] = map_to_rank(mine, (uint32_t)r); peer_bar[k] = map_to_rank(mybar, (uint32_t)r); ++k; }
+    }
+    mbar_wait(&bars[0], 0);
+    if (CL > 1) cluster_sync_all();   // every CTA of the cluster runs and has initialised its barriers
+    else __syncthreads();
 
-    const int ntiles = (NP / 4) * GG;
+    const uint32_t rx_bytes = (uint32_t)(N - (row1 - row0)) * (uint32_t)DP * 4u;   // rows the peers send per step
+    const int ntiles = (rg1 - rg0) * GG;
     float4 acc[TPT][4];
 #pragma unroll
     for (int s = 0; s < TPT; ++s)
@@ -164,35 +280,53 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     for (int j = 0; j < K; ++j) {
         float* Pcur = Pbuf + (j & 1) * slab;
         if (j > 0) {
+            const int b = j & 1;                                  // peer rows of step j are counted on bars[1 + b]
+            if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&bars[1 + b], rx_bytes);
             const float4* in4 = reinterpret_cast<const float4*>(Pbuf + ((j - 1) & 1) * slab);
             float4* out4 = reinterpret_cast<float4*>(Pcur);
-            float4* st4 = p.stack ? reinterpret_cast<float4*>(p.stack + ((int64_t)q * K + j) * slab) : nullptr;
+            float4* st4 = p.stack ? reinterpret_cast<float4*>(p.stack + (int64_t)q * NP * K * DP) + j * V : nullptr;
             const bool cheb = (p.recursion == TGCN_RECURSION_CHEBYSHEV) && j >= 2;
-            for (int i = tid; i < N * V; i += T) {
+            const uint32_t boff = (uint32_t)(b * slab) * 4u;
+            for (int i = row0 * V + tid; i < row1 * V; i += T) {
                 const int n = i / V, v = i - n * V;
-                float4 r = gather_row<kCsrSmem>(csr_s, p.col, p.val, rowptr_s[n], rowptr_s[n + 1], in4, V, v);
+                float4 r = gather_row<kCsrSmem>(ent, rowinfo_s[n], in4, V, v);
                 if (cheb) {   // T_j = 2 L~ T_{j-1} - T_{j-2}; T_{j-2} is what the output buffer still holds
                     const float4 o = out4[i];
                     r.x = fmaf(-1.f, o.x, 2.f * r.x); r.y = fmaf(-1.f, o.y, 2.f * r.y);
                     r.z = fmaf(-1.f, o.z, 2.f * r.z); r.w = fmaf(-1.f, o.w, 2.f * r.w);
                 }
                 out4[i] = r;
-                if (st4) st4[i] = r;
+                if (CL > 1) {       // replicate the new rows into the peers' copies of the slab
+                    const uint32_t off = boff + (uint32_t)i * 16u;
+                    st_async_f4(peer_data[0] + off, r, peer_bar[0] + 8u * b);
+                    if (CL > 2) {
+                        st_async_f4(peer_data[1] + off, r, peer_bar[1] + 8u * b);
+                        st_async_f4(peer_data[2] + off, r, peer_bar[2] + 8u * b);
+                    }
+                }
+                if (st4) st4[(n * K) * V + v] = r;
             }
-            stage_w(j);
             __syncthreads();
+            if (CL > 1) mbar_wait(&bars[1 + b], (uint32_t)(((j - 1) >> 1) & 1));
         }
         // contraction step: acc[tile] += P_j[4 rows][DP] * W'_j[DP][4 g]
         const float4* P4 = reinterpret_cast<const float4*>(Pcur);
-        const float4* W4 = reinterpret_cast<const float4*>(Wsm + (j & 1) * DP * GP);
+        const float4* W4 = reinterpret_cast<const float4*>(kWSmem ? Wsm + j * wslab : p.Wm + (int64_t)j * wslab);
 #pragma unroll
         for (int s = 0; s < TPT; ++s) {
             const int t = tid + s * T;
             if (t >= ntiles) break;
-            const int rg = t / GG, gg = t - rg * GG;
+            const int rgl = t / GG, gg = t - rgl * GG;
+            const int rg = rg0 + rgl;
             for (int v = 0; v < V; ++v) {
-                const float4 w0 = W4[(4 * v + 0) * GG + gg], w1 = W4[(4 * v + 1) * GG + gg];
-                const float4 w2 = W4[(4 * v + 2) * GG + gg], w3 = W4[(4 * v + 3) * GG + gg];
+                float4 w0, w1, w2, w3;
+                if (kWSmem) {
+                    w0 = W4[(4 * v + 0) * GG + gg]; w1 = W4[(4 * v + 1) * GG + gg];
+                    w2 = W4[(4 * v + 2) * GG + gg]; w3 = W4[(4 * v + 3) * GG + gg];
+                } else {
+                    w0 = __ldg(W4 + (4 * v + 0) * GG + gg); w1 = __ldg(W4 + (4 * v + 1) * GG + gg);
+                    w2 = __ldg(W4 + (4 * v + 2) * GG + gg); w3 = __ldg(W4 + (4 * v + 3) * GG + gg);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const float4 a = P4[(rg * 4 + r) * V + v];
@@ -211,7 +345,8 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     for (int s = 0; s < TPT; ++s) {
         const int t = tid + s * T;
         if (t >= ntiles) break;
-        const int rg = t / GG, gg = t - rg * GG;
+        const int rgl = t / GG, gg = t - rgl * GG;
+        const int rg = rg0 + rgl;
         const int g0 = gg * 4;
         float o[4][4];
 #pragma unroll
@@ -220,10 +355,10 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
             float b[4] = {0.f, 0.f, 0.f, 0.f};
             if (n < N) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (g0 + c < G) {
-                        if (p.bias_mode == TGCN_BIAS_PER_VERTEX) b[c] = __ldg(p.bias + (int64_t)n * G + g0 + c);
-                        else if (p.bias_mode == TGCN_BIAS_PER_FILTER) b[c] = __ldg(p.bias + g0 + c);
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (g0 + cc < G) {
+                        if (p.bias_mode == TGCN_BIAS_PER_VERTEX) b[cc] = __ldg(p.bias + (int64_t)n * G + g0 + cc);
+                        else if (p.bias_mode == TGCN_BIAS_PER_FILTER) b[cc] = __ldg(p.bias + g0 + cc);
                     }
                 }
             }
@@ -239,23 +374,26 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
                 if ((G & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
                 else
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) if (g0 + c < G) dst[c] = o[r][c];
+                    for (int cc = 0; cc < 4; ++cc) if (g0 + cc < G) dst[cc] = o[r][cc];
             }
         }
         if (p.y) {
-            const int groups = 4 / pp;                      // pooled rows produced by this tile (1 or 2)
-            for (int u = 0; u < groups; ++u) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u * pp >= 4) break;                     // pooled rows produced by this tile: 4 / pp
                 const int m = (rg * 4) / pp + u;            // pooled row
                 if (m * pp >= N) continue;
                 float best[4];
                 int arg[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    for (int s2 = 0; s2 < pp; ++s2) {
-                        float vv = o[u * pp + s2][c];
+                for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                    for (int s2 = 0; s2 < 4; ++s2) {
+                        if (s2 >= pp) break;
+                        float vv = (pp == 4) ? o[s2][cc] : o[(u * 2 + s2) & 3][cc];
                         if (p.relu) vv = (vv != vv) ? vv : fmaxf(vv, 0.f);
-                        if (s2 == 0) { best[c] = vv; arg[c] = 0; }
-                        else take_max_r(vv, s2, best[c], arg[c]);
+                        if (s2 == 0) { best[cc] = vv; arg[cc] = 0; }
+                        else take_max_r(vv, s2, best[cc], arg[cc]);
                     }
                 }
                 const int64_t off = ((int64_t)q * (N / pp) + m) * G + g0;
@@ -265,8 +403,8 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
                         make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (g0 + c < G) { p.y[off + c] = best[c]; p.idx[off + c] = (uint8_t)arg[c]; }
+                    for (int cc = 0; cc < 4; ++cc)
+                        if (g0 + cc < G) { p.y[off + cc] = best[cc]; p.idx[off + cc] = (uint8_t)arg[cc]; }
                 }
             }
         }
@@ -277,207 +415,300 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
 // backward
 // ------------------------------------------------------------------------------------------------
 struct ResBwdParams {
-    const int* rowptrT; const int* colT; const float* valT;   // CSR of L~^T (only read when dx != null)
+    const int2* rowinfoT; const int2* entriesT;               // packed CSR of L~^T (only read when dx != null)
     const float* dout;     // [Q,N,G] or null
     const float* dy;       // [Q,N/p,G] (fused pool) or null
     const uint8_t* idx;    // [Q,N/p,G]
     const float* y;        // pooled forward output (ReLU mask) or null
-    const float* stack;    // [Q][K][NP][DP]
-    const float* W;        // [K,D,G] raw layer weights
+    const float* stack;    // [Q][NP][K][DP]
+    const float* Wt;       // [K][GP][DP] transposed mixed weights (resident_prep_kernel)
     float* dWpart;         // [Q][K][DP][GP] per-sample gradient in the power basis
     float* dbpart;         // [Q][GP] per-sample column sums of dOut (per-filter bias) or null
     float* dx;             // [Q,N,D] or null
-    int N, NP, nnz, D, DP, V, G, GP, GG, K;
+    int N, NP, E, D, DP, V, G, GP, GG, K;
     int recursion, pool_p, relu;
+    int S, Vh;             // CTAs per sample (gridDim.y) and float4 column groups of dx per CTA
+    int R;                 // rows of the saved basis per ring stage
 };
 
-struct ResSmemBwd { size_t dOut, red, A, W, csr, rowptr, total; };
+struct ResSmemBwd { size_t bars, dOut, red, ring, A, W, csr, rowinfo, total; };
 
-static ResSmemBwd res_bwd_smem(int N, int nnz, int DP, int GP, bool need_dx, bool csr_smem) {
+static ResSmemBwd res_bwd_smem(int N, int64_t E, int DP, int Vh, int GP, int K, int R, bool need_dx, bool csr_smem,
+                               bool w_smem) {
     ResSmemBwd s{};
     const int NP = round_up4(N);
     size_t o = 0;
-    s.dOut = o;   o += sizeof(float) * (size_t)NP * GP;
-    s.red = o;    o += sizeof(float) * (size_t)kResThreads;
-    s.A = o;      o += need_dx ? sizeof(float) * 2 * (size_t)NP * DP : 0;
-    s.W = o;      o += need_dx ? sizeof(float) * 2 * (size_t)DP * GP : 0;
-    s.csr = o;    o += (need_dx && csr_smem) ? sizeof(int2) * (size_t)nnz : 0;
-    s.rowptr = o; o += need_dx ? sizeof(int) * (size_t)(N + 1) : 0;
+    s.bars = o;    o += 64;
+    s.dOut = o;    o += sizeof(float) * (size_t)NP * (GP + 4);
+    s.red = o;     o += sizeof(float) * (size_t)kBwdThreads;
+    s.ring = o;    o += sizeof(float) * (size_t)kRingStages * R * K * DP;
+    s.A = o;       o += need_dx ? sizeof(float) * 2 * (size_t)NP * 4 * Vh : 0;
+    s.W = o;       o += (need_dx && w_smem) ? sizeof(float) * (size_t)K * 4 * Vh * GP : 0;
+    s.csr = o;     o += (need_dx && csr_smem) ? sizeof(int2) * (size_t)E : 0;
+    s.rowinfo = o; o += need_dx ? sizeof(int2) * (size_t)round_up2(N) : 0;
     s.total = (o + 15) & ~(size_t)15;
     return s;
 }
 
-template <bool kCsrSmem>
-__global__ void __launch_bounds__(kResThreads, 1)
+template <int DWT, bool kCsrSmem, bool kWSmem>
+__global__ void __launch_bounds__(kBwdThreads, 1)
 resident_bwd_kernel(const ResBwdParams p, const ResSmemBwd lay) {
     extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);     // [0..2] ring stages, [3] dx operands
     float* dOut_s = reinterpret_cast<float*>(smem + lay.dOut);
+    float* ring = reinterpret_cast<float*>(smem + lay.ring);
     float* Abuf = reinterpret_cast<float*>(smem + lay.A);
     float* Wsm = reinterpret_cast<float*>(smem + lay.W);
     int2* csr_s = reinterpret_cast<int2*>(smem + lay.csr);
-    int* rowptr_s = reinterpret_cast<int*>(smem + lay.rowptr);
+    int2* rowinfo_s = reinterpret_cast<int2*>(smem + lay.rowinfo);
 
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    constexpr int T = kBwdThreads;
+    const int q = blockIdx.x, h = blockIdx.y, S = p.S;
     const int N = p.N, NP = p.NP, D = p.D, DP = p.DP, V = p.V, G = p.G, GP = p.GP, GG = p.GG, K = p.K;
-    const int slab = NP * DP;
+    const int GS = GG + 1;                                    // dOut row stride in float4 (odd: 8 consecutive rows
+    const int GSf = 4 * GS;                                   // hit 8 different bank groups)
     const bool need_dx = p.dx != nullptr;
+    const int R = p.R;
+    const int rowf = K * DP;                                  // floats of the saved basis per vertex
+    const int nchunks = (N + R - 1) / R;
+    const float* stq = p.stack + (int64_t)q * NP * rowf;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue_chunk = [&](int cidx) {   // one thread: rows [cidx*R, ...) of every order, one contiguous run
+        const int r0 = cidx * R, rows = min(R, N - r0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)rowf * 4u;
+        uint64_t* bar = &bars[cidx % kRingStages];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(ring + (size_t)(cidx % kRingStages) * R * rowf, stq + (size_t)r0 * rowf, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int cidx = 0; cidx < kRingStages - 1 && cidx < nchunks; ++cidx) issue_chunk(cidx);
+        if (need_dx) {
+            const uint32_t b_ri = (uint32_t)sizeof(int2) * (uint32_t)round_up2(N);
+            const uint32_t b_csr = kCsrSmem ? (uint32_t)sizeof(int2) * (uint32_t)p.E : 0u;
+            mbar_arrive_expect_tx(&bars[3], b_ri + b_csr);
+            bulk_g2s(rowinfo_s, p.rowinfoT, b_ri, &bars[3]);
+            if (b_csr) bulk_g2s(csr_s, p.entriesT, b_csr, &bars[3]);
+        }
+    }
 
     // ---- dOut tile of this sample: plain copy, or the max-pool (+ReLU) gradient routed on the fly
     if (p.dout) {
         const float* src = p.dout + (int64_t)q * N * G;
-        for (int i = tid; i < NP * GP; i += T) {
-            const int n = i / GP, g = i - n * GP;
-            dOut_s[i] = (n < N && g < G) ? __ldg(src + (int64_t)n * G + g) : 0.f;
+        if ((G & 3) == 0 && aligned16(p.dout)) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int i = tid; i < NP * GG; i += T) {
+                const int n = i / GG, gg = i - n * GG;
+                reinterpret_cast<float4*>(dOut_s)[n * GS + gg] = n < N ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int i = tid; i < NP * GP; i += T) {
+                const int n = i / GP, g = i - n * GP;
+                dOut_s[n * GSf + g] = (n < N && g < G) ? __ldg(src + (int64_t)n * G + g) : 0.f;
+            }
         }
     } else {
         const int pp = p.pool_p;
-        const int64_t base = (int64_t)q * (N / pp) * G;
-        for (int i = tid; i < NP * GP; i += T) {
-            const int n = i / GP, g = i - n * GP;
-            float v = 0.f;
-            if (n < N && g < G) {
-                const int m = n / pp, s = n - m * pp;
-                const int64_t off = base + (int64_t)m * G + g;
-                if ((int)p.idx[off] == s) {
-                    v = __ldg(p.dy + off);
-                    if (p.relu) {
-                        const float yy = __ldg(p.y + off);      // relu(x_argmax): > 0 <=> x_argmax > 0, NaN <=> NaN
-                        v = (yy > 0.f || yy != yy) ? v : 0.f;
-                    }
+        const int M = N / pp;
+        const int64_t base = (int64_t)q * M * G;
+        if ((G & 3) == 0 && aligned16(p.dy) && (!p.relu || aligned16(p.y)) && (reinterpret_cast<uintptr_t>(p.idx) & 3u) == 0) {
+            for (int i = tid; i < M * GG; i += T) {           // one pooled float4: three independent vector loads
+                const int m = i / GG, gg = i - m * GG;
+                const int64_t off = base + (int64_t)m * G + 4 * gg;
+                const uchar4 a = *reinterpret_cast<const uchar4*>(p.idx + off);
+                float4 v = __ldg(reinterpret_cast<const float4*>(p.dy + off));
+                if (p.relu) {   // relu(x_argmax) = y: > 0 <=> x_argmax > 0, NaN <=> NaN (gradient passes)
+                    const float4 yy = __ldg(reinterpret_cast<const float4*>(p.y + off));
+                    v.x = (yy.x > 0.f || yy.x != yy.x) ? v.x : 0.f; v.y = (yy.y > 0.f || yy.y != yy.y) ? v.y : 0.f;
+                    v.z = (yy.z > 0.f || yy.z != yy.z) ? v.z : 0.f; v.w = (yy.w > 0.f || yy.w != yy.w) ? v.w : 0.f;
+                }
+                for (int s = 0; s < pp; ++s) {
+                    const float4 o = make_float4(a.x == s ? v.x : 0.f, a.y == s ? v.y : 0.f, a.z == s ? v.z : 0.f,
+                                                 a.w == s ? v.w : 0.f);
+                    reinterpret_cast<float4*>(dOut_s)[(m * pp + s) * GS + gg] = o;
                 }
             }
-            dOut_s[i] = v;
+            for (int i = N * GG + tid; i < NP * GG; i += T)
+                reinterpret_cast<float4*>(dOut_s)[(i / GG) * GS + (i % GG)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = tid; i < NP * GP; i += T) {
+                const int n = i / GP, g = i - n * GP;
+                float v = 0.f;
+                if (n < N && g < G) {
+                    const int m = n / pp, s = n - m * pp;
+                    const int64_t off = base + (int64_t)m * G + g;
+                    if ((int)p.idx[off] == s) {
+                        v = __ldg(p.dy + off);
+                        if (p.relu) {
+                            const float yy = __ldg(p.y + off);
+                            v = (yy > 0.f || yy != yy) ? v : 0.f;
+                        }
+                    }
+                }
+                dOut_s[n * GSf + g] = v;
+            }
         }
     }
-    if (need_dx) {
-        for (int i = tid; i <= N; i += T) rowptr_s[i] = __ldg(p.rowptrT + i);
-        if (kCsrSmem)
-            for (int e = tid; e < p.nnz; e += T) csr_s[e] = make_int2(__ldg(p.colT + e), __float_as_int(__ldg(p.valT + e)));
+    const int Vh = p.Vh, DPh = 4 * Vh;
+    const int wslab = DPh * GP;      // this CTA's slice of one order of Wt: [GP][DPh]
+    if (need_dx && kWSmem) {
+        // Wt[j][g][h*DPh .. +DPh) -> shared [j][g][DPh]
+        const float4* src = reinterpret_cast<const float4*>(p.Wt);
+        float4* dst = reinterpret_cast<float4*>(Wsm);
+        for (int i = tid; i < K * GP * Vh; i += T) {
+            const int jg = i / Vh, vl = i - jg * Vh;
+            dst[i] = __ldg(src + (int64_t)jg * V + h * Vh + vl);
+        }
     }
     __syncthreads();
 
     // ---- per-filter bias gradient of this sample: column sums of dOut in a fixed order
     float* red_s = reinterpret_cast<float*>(smem + lay.red);
     const int RL = T / GP;                                   // row lanes per column
-    if (p.dbpart) {
+    const bool do_db = p.dbpart != nullptr && h == 0;
+    if (do_db) {
         const int g = tid % GP, lr = tid / GP;
         float s = 0.f;
         if (lr < RL)
-            for (int n = lr; n < N; n += RL) s += dOut_s[n * GP + g];
+            for (int n = lr; n < N; n += RL) s += dOut_s[n * GSf + g];
         red_s[tid] = s;
     }
 
-    // ---- dW'_j[d][g] = sum_n P_j[n][d] dOut[n][g]: one (j, 4 d, 4 g) tile per thread at a time
+    // ---- dW'_j[d][g] = sum_n P_j[n][d] dOut[n][g]: DWT (j, 4 d, 4 g) tiles per thread, accumulated over
+    // the row chunks as they arrive in the ring; the S CTAs of a sample take alternate warp-sized tile groups
     {
         const float4* dO4 = reinterpret_cast<const float4*>(dOut_s);
         const int per_j = V * GG;
         const int ntiles = K * per_j;
-        for (int t = tid; t < ntiles; t += T) {
-            const int j = t / per_j, rem = t - j * per_j;
-            const int v = rem / GG, gg = rem - v * GG;
-            const float4* st4 = reinterpret_cast<const float4*>(p.stack + ((int64_t)q * K + j) * slab) + v;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-            int n = 0;
-            for (; n + 4 <= N; n += 4) {
-                float4 pv[4], dv[4];
+        int tj[DWT], tv[DWT], tg[DWT];
+        bool live[DWT];
+        float4 acc[DWT][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pv[u] = __ldg(st4 + (int64_t)(n + u) * V);
+        for (int u = 0; u < DWT; ++u) {
+            const int te = tid + u * T;
+            const int t = (((te >> 5) * S + h) << 5) + (te & 31);
+            live[u] = t < ntiles;
+            const int tt = live[u] ? t : 0;
+            tj[u] = tt / per_j;
+            const int rem = tt - tj[u] * per_j;
+            tv[u] = rem / GG; tg[u] = rem - tv[u] * GG;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) dv[u] = dO4[(n + u) * GG + gg];
+            for (int r = 0; r < 4; ++r) acc[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int cidx = 0; cidx < nchunks; ++cidx) {
+            if (tid == 0 && cidx + kRingStages - 1 < nchunks) issue_chunk(cidx + kRingStages - 1);
+            mbar_wait(&bars[cidx % kRingStages], (uint32_t)((cidx / kRingStages) & 1));
+            const float4* st4 = reinterpret_cast<const float4*>(ring + (size_t)(cidx % kRingStages) * R * rowf);
+            const int r0 = cidx * R, rows = min(R, N - r0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    fma4s(a0, pv[u].x, dv[u]);
-                    fma4s(a1, pv[u].y, dv[u]);
-                    fma4s(a2, pv[u].z, dv[u]);
-                    fma4s(a3, pv[u].w, dv[u]);
+            for (int u = 0; u < DWT; ++u) {
+                if (!live[u]) continue;
+                const float4* pcol = st4 + tj[u] * V + tv[u];
+                const float4* dcol = dO4 + (size_t)r0 * GS + tg[u];
+                int r = 0;
+                for (; r + 4 <= rows; r += 4) {
+                    float4 pv[4], dv[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { pv[w] = pcol[(r + w) * K * V]; dv[w] = dcol[(r + w) * GS]; }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        fma4s(acc[u][0], pv[w].x, dv[w]);
+                        fma4s(acc[u][1], pv[w].y, dv[w]);
+                        fma4s(acc[u][2], pv[w].z, dv[w]);
+                        fma4s(acc[u][3], pv[w].w, dv[w]);
+                    }
+                }
+                for (; r < rows; ++r) {
+                    const float4 pv = pcol[r * K * V], dv = dcol[r * GS];
+                    fma4s(acc[u][0], pv.x, dv); fma4s(acc[u][1], pv.y, dv);
+                    fma4s(acc[u][2], pv.z, dv); fma4s(acc[u][3], pv.w, dv);
                 }
             }
-            for (; n < N; ++n) {
-                const float4 pv = __ldg(st4 + (int64_t)n * V);
-                const float4 dv = dO4[n * GG + gg];
-                fma4s(a0, pv.x, dv); fma4s(a1, pv.y, dv); fma4s(a2, pv.z, dv); fma4s(a3, pv.w, dv);
-            }
-            float4* dst = reinterpret_cast<float4*>(p.dWpart + (((int64_t)q * K + j) * DP + 4 * v) * GP) + gg;
-            dst[0] = a0; dst[GG] = a1; dst[2 * GG] = a2; dst[3 * GG] = a3;
+            __syncthreads();          // the stage may be refilled by the next iteration's bulk copy
+        }
+#pragma unroll
+        for (int u = 0; u < DWT; ++u) {
+            if (!live[u]) continue;
+            float4* dst = reinterpret_cast<float4*>(p.dWpart + (((int64_t)q * K + tj[u]) * DP + 4 * tv[u]) * GP) + tg[u];
+            dst[0] = acc[u][0]; dst[GG] = acc[u][1]; dst[2 * GG] = acc[u][2]; dst[3 * GG] = acc[u][3];
         }
     }
-    if (p.dbpart) {
-        __syncthreads();
+    if (do_db) {   // red_s was written before the chunk loop's barriers
+        if (nchunks == 0) __syncthreads();
         if (tid < GP) {
             float s = 0.f;
             for (int u = 0; u < RL; ++u) s += red_s[u * GP + tid];
             p.dbpart[(int64_t)q * GP + tid] = s;
         }
     }
-    if (!need_dx) return;
+    if (!need_dx || h * Vh >= V) return;
 
     // ---- dx = sum_j (L~^T)^j (dOut W'_j^T): Horner, A_j = dOut W'_j^T + L~^T A_{j+1}; textbook
     // recursion: Clenshaw, B_j = dOut W_j^T + 2 L~^T B_{j+1} - B_{j+2}, dx = dOut W_0^T + L~^T B_1 - B_2.
-    const int64_t inner = (int64_t)D * G;
-    auto stage_wt = [&](int j, int buf) {     // transposed image Wt[g][d] so the 4 d of a tile are one float4
-        float* dst = Wsm + buf * DP * GP;
-        for (int i = tid; i < DP * GP; i += T) {
-            const int g = i / DP, d = i - g * DP;
-            dst[i] = (d < D && g < G) ? mixed_weight(p.W, K, inner, j, (int64_t)d * G + g, p.recursion) : 0.f;
-        }
-    };
-    stage_wt(K - 1, (K - 1) & 1);
-    __syncthreads();
+    // This CTA owns the float4 column groups [h*Vh, (h+1)*Vh) of dx: columns never mix.
+    mbar_wait(&bars[3], 0);
+    const int2* ent = kCsrSmem ? csr_s : p.entriesT;
     const bool cheb = p.recursion == TGCN_RECURSION_CHEBYSHEV;
-    const int NR = NP / 4;                                   // tile rows are n, n+NR, n+2NR, n+3NR
-    const int ntiles = NR * V;
+    const int aslab = NP * DPh;
+    const int nitems = N * Vh;
     for (int j = K - 1; j >= 0; --j) {
-        const float4* Wt4 = reinterpret_cast<const float4*>(Wsm + (j & 1) * DP * GP);
         const float4* dO4 = reinterpret_cast<const float4*>(dOut_s);
         // A_{j+1} lives in buffer (j+1)&1; A_j goes to buffer j&1 (which still holds A_{j+2})
-        const float4* Ain4 = reinterpret_cast<const float4*>(Abuf + ((j + 1) & 1) * slab);
-        float4* Aout4 = reinterpret_cast<float4*>(Abuf + (j & 1) * slab);
-        for (int t = tid; t < ntiles; t += T) {
-            const int r0 = t / V, v = t - r0 * V;
-            float4 acc[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int gg = 0; gg < GG; ++gg) {
-                const float4 w0 = Wt4[(4 * gg + 0) * V + v], w1 = Wt4[(4 * gg + 1) * V + v];
-                const float4 w2 = Wt4[(4 * gg + 2) * V + v], w3 = Wt4[(4 * gg + 3) * V + v];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float4 b = dO4[(r0 + r * NR) * GG + gg];
-                    fma4s(acc[r], b.x, w0);
-                    fma4s(acc[r], b.y, w1);
-                    fma4s(acc[r], b.z, w2);
-                    fma4s(acc[r], b.w, w3);
+        const float4* Ain4 = reinterpret_cast<const float4*>(Abuf + ((j + 1) & 1) * aslab);
+        float4* Aout4 = reinterpret_cast<float4*>(Abuf + (j & 1) * aslab);
+        for (int i = tid; i < nitems; i += T) {
+            const int n = i / Vh, vl = i - n * Vh;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* drow = dO4 + n * GS;
+            if (kWSmem) {
+                const float4* wcol = reinterpret_cast<const float4*>(Wsm + j * wslab) + vl;
+#pragma unroll 4
+                for (int gg = 0; gg < GG; ++gg) {
+                    const float4 b = drow[gg];
+                    fma4s(acc, b.x, wcol[(4 * gg + 0) * Vh]);
+                    fma4s(acc, b.y, wcol[(4 * gg + 1) * Vh]);
+                    fma4s(acc, b.z, wcol[(4 * gg + 2) * Vh]);
+                    fma4s(acc, b.w, wcol[(4 * gg + 3) * Vh]);
+                }
+            } else {
+                const float4* wcol = reinterpret_cast<const float4*>(p.Wt + (int64_t)j * GP * DP) + h * Vh + vl;
+#pragma unroll 4
+                for (int gg = 0; gg < GG; ++gg) {
+                    const float4 b = drow[gg];
+                    fma4s(acc, b.x, __ldg(wcol + (4 * gg + 0) * V));
+                    fma4s(acc, b.y, __ldg(wcol + (4 * gg + 1) * V));
+                    fma4s(acc, b.z, __ldg(wcol + (4 * gg + 2) * V));
+                    fma4s(acc, b.w, __ldg(wcol + (4 * gg + 3) * V));
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int n = r0 + r * NR;
-                if (n >= N) continue;
-                if (j < K - 1) {
-                    const float4 s = gather_row<kCsrSmem>(csr_s, p.colT, p.valT, rowptr_s[n], rowptr_s[n + 1], Ain4, V, v);
-                    const float sc = (cheb && j >= 1) ? 2.f : 1.f;
-                    acc[r].x = fmaf(sc, s.x, acc[r].x); acc[r].y = fmaf(sc, s.y, acc[r].y);
-                    acc[r].z = fmaf(sc, s.z, acc[r].z); acc[r].w = fmaf(sc, s.w, acc[r].w);
-                    if (cheb && j < K - 2) {
-                        const float4 o = Aout4[n * V + v];
-                        acc[r].x -= o.x; acc[r].y -= o.y; acc[r].z -= o.z; acc[r].w -= o.w;
-                    }
+            if (j < K - 1) {
+                const float4 s = gather_row<kCsrSmem>(ent, rowinfo_s[n], Ain4, Vh, vl);
+                const float sc = (cheb && j >= 1) ? 2.f : 1.f;
+                acc.x = fmaf(sc, s.x, acc.x); acc.y = fmaf(sc, s.y, acc.y);
+                acc.z = fmaf(sc, s.z, acc.z); acc.w = fmaf(sc, s.w, acc.w);
+                if (cheb && j < K - 2) {
+                    const float4 o = Aout4[i];
+                    acc.x -= o.x; acc.y -= o.y; acc.z -= o.z; acc.w -= o.w;
                 }
-                if (j > 0) {
-                    Aout4[n * V + v] = acc[r];
-                } else {
-                    float* dst = p.dx + ((int64_t)q * N + n) * D + 4 * v;
-                    if ((D & 3) == 0) *reinterpret_cast<float4*>(dst) = acc[r];
-                    else {
-                        const float o[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+            }
+            if (j > 0) {
+                Aout4[i] = acc;
+            } else {
+                const int d0 = 4 * (h * Vh + vl);
+                float* dst = p.dx + ((int64_t)q * N + n) * D + d0;
+                if ((D & 3) == 0) *reinterpret_cast<float4*>(dst) = acc;
+                else {
+                    const float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) if (4 * v + c < D) dst[c] = o[c];
-                    }
+                    for (int cc = 0; cc < 4; ++cc) if (d0 + cc < D) dst[cc] = o[cc];
                 }
             }
         }
-        if (j > 0) stage_wt(j - 1, (j - 1) & 1);
         __syncthreads();
     }
 }
@@ -495,20 +726,6 @@ struct ResReduceParams {
 constexpr int kRedElems = 32;    // (d,g) elements per weight block
 constexpr int kRedMaxK = 32;
 
-__device__ __forceinline__ float routed_dout(const ResReduceParams& p, int q, int n, int g) {
-    if (p.dout) return __ldg(p.dout + ((int64_t)q * p.N + n) * p.G + g);
-    const int pp = p.pool_p;
-    const int m = n / pp, s = n - m * pp;
-    const int64_t off = ((int64_t)q * (p.N / pp) + m) * p.G + g;
-    if ((int)p.idx[off] != s) return 0.f;
-    float v = __ldg(p.dy + off);
-    if (p.relu) {
-        const float yy = __ldg(p.y + off);
-        v = (yy > 0.f || yy != yy) ? v : 0.f;
-    }
-    return v;
-}
-
 __global__ void __launch_bounds__(kRedElems * 16)
 resident_reduce_kernel(const ResReduceParams p) {
     __shared__ double red[kRedMaxK][kRedElems];
@@ -524,14 +741,15 @@ resident_reduce_kernel(const ResReduceParams p) {
             if (e < DG) {
                 const float* src = p.dWpart + ((int64_t)jj * p.DP + d) * p.GP + g;
                 const int64_t qs = (int64_t)p.K * p.DP * p.GP;
-                float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 int q = 0;
-                for (; q + 4 <= p.Q; q += 4) {
-                    f0 += __ldg(src + (q + 0) * qs); f1 += __ldg(src + (q + 1) * qs);
-                    f2 += __ldg(src + (q + 2) * qs); f3 += __ldg(src + (q + 3) * qs);
+                for (; q + 8 <= p.Q; q += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) f[u] += __ldg(src + (q + u) * qs);
                 }
-                for (; q < p.Q; ++q) f0 += __ldg(src + q * qs);
-                s = ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
+                for (; q < p.Q; ++q) f[0] += __ldg(src + q * qs);
+                s = (((double)f[0] + (double)f[1]) + ((double)f[2] + (double)f[3])) +
+                    (((double)f[4] + (double)f[5]) + ((double)f[6] + (double)f[7]));
             }
             red[jj][e_local] = s;
         }
@@ -556,12 +774,38 @@ resident_reduce_kernel(const ResReduceParams p) {
     // ---- bias gradient
     const int64_t i = (int64_t)(blockIdx.x - p.w_blocks) * blockDim.x + tid;
     if (p.bias_mode == TGCN_BIAS_PER_VERTEX) {
-        if (i >= (int64_t)p.N * p.G) return;
-        const int n = (int)(i / p.G), g = (int)(i - (int64_t)n * p.G);
-        float s = 0.f;
+        if (p.dout) {
+            if (i >= (int64_t)p.N * p.G) return;
+            const int64_t NG = (int64_t)p.N * p.G;
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int q = 0;
+            for (; q + 8 <= p.Q; q += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] += __ldg(p.dout + (q + u) * NG + i);
+            }
+            for (; q < p.Q; ++q) f[0] += __ldg(p.dout + q * NG + i);
+            p.db[i] = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+        } else {
+            // one pooled element per thread: its gradient goes to the sibling idx selected in each sample
+            const int pp = p.pool_p, M = p.N / pp;
+            if (i >= (int64_t)M * p.G) return;
+            const int64_t MG = (int64_t)M * p.G;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < p.Q; ++q) s += routed_dout(p, q, n, g);
-        p.db[i] = s;
+            for (int q = 0; q < p.Q; ++q) {
+                const int64_t off = q * MG + i;
+                const int a = p.idx[off];
+                float v = __ldg(p.dy + off);
+                if (p.relu) {
+                    const float yy = __ldg(p.y + off);
+                    v = (yy > 0.f || yy != yy) ? v : 0.f;
+                }
+                s0 += a == 0 ? v : 0.f; s1 += a == 1 ? v : 0.f; s2 += a == 2 ? v : 0.f; s3 += a == 3 ? v : 0.f;
+            }
+            const int m = (int)(i / p.G), g = (int)(i - (int64_t)m * p.G);
+            const float s[4] = {s0, s1, s2, s3};
+            for (int u = 0; u < pp; ++u) p.db[((int64_t)m * pp + u) * p.G + g] = s[u];
+        }
     } else if (p.bias_mode == TGCN_BIAS_PER_FILTER) {
         if (i >= p.G) return;
         float s = 0.f;
@@ -574,41 +818,97 @@ resident_reduce_kernel(const ResReduceParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct ResPlan { bool ok, csr_smem; int NP, DP, V, GP, GG, tpt; size_t smem; };
+struct ResPlan { bool ok, csr_smem, w_smem; int NP, DP, V, GP, GG, threads, tpt, split, rg_per, Vh, R, dwt; size_t smem; };
 
-static ResPlan res_plan_fwd(int N, int D, int G, int K, int64_t nnz) {
+static bool res_dims_ok(int N, int D, int G, int K, int64_t E) {
+    if (N < 1 || D < 1 || G < 1 || K < 1 || K > kResMaxK || E < 0 || E > (int64_t)INT32_MAX / 16) return false;
+    return (int64_t)round_up4(N) * round_up4(D) * K <= (1 << 22) && round_up4(G) <= kBwdThreads;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// forward: CL CTAs (one cluster) per sample, rows split in groups of 4
+static ResPlan res_plan_fwd(int Q, int N, int D, int G, int K, int64_t E) {
     ResPlan pl{};
-    if (N < 1 || D < 1 || G < 1 || K < 1 || K > kResMaxK || nnz < 0 || nnz > (int64_t)INT32_MAX / 2) return pl;
+    if (!res_dims_ok(N, D, G, K, E)) return pl;
     pl.NP = round_up4(N); pl.DP = round_up4(D); pl.V = pl.DP / 4; pl.GP = round_up4(G); pl.GG = pl.GP / 4;
-    if ((int64_t)pl.NP * pl.DP > (1 << 20)) return pl;
-    const int ntiles = (pl.NP / 4) * pl.GG;
-    pl.tpt = (ntiles + kResThreads - 1) / kResThreads;
+    const int RG = pl.NP / 4;
+    int CL = 1;
+    if ((int64_t)Q * 2 <= kNumSMs && RG >= 2) CL = 2;
+    if ((int64_t)Q * 4 <= kNumSMs && RG >= 4) CL = 4;
+    const int forced = env_int("TGCN_RES_CL", 0);
+    if ((forced == 1 || forced == 2 || forced == 4) && RG >= forced) CL = forced;
+    pl.split = CL;
+    pl.rg_per = (RG + CL - 1) / CL;
+    const int ntiles = pl.rg_per * pl.GG;
+    pl.threads = (ntiles <= 1024 && env_int("TGCN_RES_T", 1024) == 1024) ? 1024 : 512;
+    pl.tpt = (ntiles + pl.threads - 1) / pl.threads;
     if (pl.tpt > 4) return pl;
-    ResSmemFwd s = res_fwd_smem(N, (int)nnz, pl.DP, pl.GP, true);
-    pl.csr_smem = s.total <= kResSmemLimit;
-    if (!pl.csr_smem) s = res_fwd_smem(N, (int)nnz, pl.DP, pl.GP, false);
-    pl.smem = s.total;
-    pl.ok = s.total <= kResSmemLimit;
+    for (int opt = 0; opt < 4 && !pl.ok; ++opt) {
+        pl.csr_smem = !(opt & 2); pl.w_smem = !(opt & 1);
+        pl.smem = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, pl.w_smem).total;
+        pl.ok = pl.smem <= kResSmemLimit;
+    }
     return pl;
 }
 
-static ResPlan res_plan_bwd(int N, int D, int G, int K, int64_t nnz, bool need_dx) {
+// backward: S independent CTAs per sample (alternate dW tile groups; disjoint dx column groups)
+static ResPlan res_plan_bwd(int Q, int N, int D, int G, int K, int64_t E, bool need_dx) {
     ResPlan pl{};
-    if (N < 1 || D < 1 || G < 1 || K < 1 || K > kResMaxK || nnz < 0 || nnz > (int64_t)INT32_MAX / 2) return pl;
+    if (!res_dims_ok(N, D, G, K, E)) return pl;
     pl.NP = round_up4(N); pl.DP = round_up4(D); pl.V = pl.DP / 4; pl.GP = round_up4(G); pl.GG = pl.GP / 4;
-    if ((int64_t)pl.NP * pl.DP > (1 << 20)) return pl;
-    ResSmemBwd s = res_bwd_smem(N, (int)nnz, pl.DP, pl.GP, need_dx, true);
-    pl.csr_smem = s.total <= kResSmemLimit;
-    if (!pl.csr_smem) s = res_bwd_smem(N, (int)nnz, pl.DP, pl.GP, need_dx, false);
-    pl.smem = s.total;
-    pl.ok = s.total <= kResSmemLimit;
+    int S = 1;
+    for (int c = 2; c <= 4; c *= 2)
+        if ((int64_t)Q * c <= kNumSMs && (!need_dx || pl.V % c == 0)) S = c;
+    const int forced = env_int("TGCN_RES_S", 0);
+    if ((forced == 1 || forced == 2 || forced == 4) && (!need_dx || pl.V % forced == 0)) S = forced;
+    pl.split = S;
+    pl.Vh = need_dx ? pl.V / S : pl.V;
+    const int ntiles = K * pl.V * pl.GG;
+    const int groups = (ntiles + 31) / 32;                    // warp-sized tile groups, dealt round-robin to the S CTAs
+    const int my_tiles = ((groups + S - 1) / S) * 32;
+    pl.dwt = (my_tiles + kBwdThreads - 1) / kBwdThreads;
+    if (pl.dwt > 4) return pl;
+    const int rowbytes = K * pl.DP * 4;
+    int R = 24 * 1024 / rowbytes;                             // ~24 KB per ring stage
+    if (R > N) R = N;
+    if (R < 1) R = 1;
+    while (!pl.ok && R >= 1) {
+        pl.R = R;
+        for (int opt = 0; opt < 4 && !pl.ok; ++opt) {
+            pl.csr_smem = !(opt & 2); pl.w_smem = !(opt & 1);
+            pl.smem = res_bwd_smem(N, E, pl.DP, pl.Vh, pl.GP, K, R, need_dx, pl.csr_smem, pl.w_smem).total;
+            pl.ok = pl.smem <= kResSmemLimit;
+        }
+        R = R > 8 ? R / 2 : R - 1;
+    }
     return pl;
 }
 
-template <typename Kern>
-static int res_set_smem(Kern kern, size_t bytes, const char* name) {
+static int bank_classes(int v_per_cta) { return v_per_cta == 1 ? 8 : v_per_cta == 2 ? 4 : v_per_cta == 4 ? 2 : 1; }
+
+template <typename Kern, typename... Args>
+static int res_launch(Kern kern, dim3 grid, int threads, int cluster, size_t smem, cudaStream_t st, const char* name,
+                      Args... args) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmemLimit);
-    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu): %s", name, bytes, cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster > 1 ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, args...);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
     return TGCN_OK;
 }
 
@@ -616,8 +916,54 @@ static int res_set_smem(Kern kern, size_t bytes, const char* name) {
 
 using namespace tgcn;
 
+// Host-side packing of a CSR triplet for the resident kernels (see the comment at gather_row).
+// rowinfo_host: 2*ceil2(N) int32 (start, len; the padding row is zero); entries_host: 2*E int32
+// (col, float bits) or NULL for a size query.  `classes` (1, 2, 4 or 8): tgcn_resident_pack_classes(...).
+// Returns E (even), or -1 on bad arguments.
+extern "C" int64_t tgcn_pack_csr_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
+                                      int classes, int32_t* rowinfo_host, int32_t* entries_host) {
+    if (N < 0 || !rowptr_host || (classes != 1 && classes != 2 && classes != 4 && classes != 8)) return -1;
+    int64_t E = 0;
+    for (int n = 0; n < N; ++n) {
+        const int len = rowptr_host[n + 1] - rowptr_host[n];
+        if (len < 0) return -1;
+        if (rowinfo_host) { rowinfo_host[2 * n] = (int32_t)E; rowinfo_host[2 * n + 1] = len; }
+        if (entries_host) {
+            // stable counting sort by ((col - n) mod classes): class n mod m first, then the next one, ...
+            int64_t o = E;
+            for (int cls = 0; cls < classes; ++cls) {
+                for (int e = rowptr_host[n]; e < rowptr_host[n + 1]; ++e) {
+                    const int key = ((col_host[e] - n) % classes + classes) % classes;
+                    if (key != cls) continue;
+                    entries_host[2 * o] = col_host[e];
+                    union { float f; int32_t i; } u; u.f = val_host[e];
+                    entries_host[2 * o + 1] = u.i;
+                    ++o;
+                }
+            }
+            if (len & 1) { entries_host[2 * o] = 0; entries_host[2 * o + 1] = 0; }   // alignment slot, never read as an entry
+        }
+        E += (len + 1) & ~1;
+    }
+    if (rowinfo_host && (N & 1)) { rowinfo_host[2 * N] = 0; rowinfo_host[2 * N + 1] = 0; }
+    return E;
+}
+
+// Bank classes the packing should use for a layer with D features per vertex and batch Q:
+// backward == 0: the forward kernel (all V = ceil(D/4) float4 of a row in one CTA);
+// backward != 0: the dx recursion of the backward kernel (V / S float4 per CTA).
+extern "C" int tgcn_resident_pack_classes(int Q, int N, int D, int backward) {
+    if (D < 1 || N < 1 || Q < 0) return 1;
+    const int V = round_up4(D) / 4;
+    if (!backward) return bank_classes(V);
+    const ResPlan pl = res_plan_bwd(Q, N, D, 4, 1, 0, true);
+    return bank_classes(pl.Vh > 0 ? pl.Vh : V);
+}
+
 extern "C" int tgcn_resident_supported(int N, int D, int G, int K, int64_t nnz) {
-    return (res_plan_fwd(N, D, G, K, nnz).ok && res_plan_bwd(N, D, G, K, nnz, true).ok) ? 1 : 0;
+    const int64_t E = nnz + N;    // upper bound of the packed entry count
+    // worst case over the batch-dependent splits: a single CTA per sample holds the most
+    return (res_plan_fwd(kNumSMs, N, D, G, K, E).ok && res_plan_bwd(kNumSMs, N, D, G, K, E, true).ok) ? 1 : 0;
 }
 
 extern "C" int64_t tgcn_resident_stack_bytes(int Q, int N, int D, int K) {
@@ -625,20 +971,29 @@ extern "C" int64_t tgcn_resident_stack_bytes(int Q, int N, int D, int K) {
     return (int64_t)sizeof(float) * Q * K * round_up4(N) * round_up4(D);
 }
 
+// weight images written by the forward and read by the backward: [Wm | Wt], K*DP*GP floats each
+extern "C" int64_t tgcn_resident_weights_bytes(int D, int G, int K) {
+    if (D < 1 || G < 1 || K < 1) return 0;
+    return (int64_t)sizeof(float) * 2 * K * round_up4(D) * round_up4(G);
+}
+
 extern "C" int64_t tgcn_resident_bwd_workspace(int Q, int N, int D, int G, int K) {
     if (Q < 0 || N < 0 || D < 1 || G < 1 || K < 1) return 0;
     return (int64_t)sizeof(float) * Q * ((int64_t)K * round_up4(D) * round_up4(G) + round_up4(G));
 }
 
-extern "C" int tgcn_resident_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N, int64_t nnz,
+extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* entries, int N, int64_t E,
                                        const float* x, const float* W, const float* bias, int bias_mode,
                                        float* out, float* y, uint8_t* idx, int pool_p, int relu, float* stack,
-                                       int Q, int D, int G, int K, int recursion, void* stream) {
+                                       float* wimages, int Q, int D, int G, int K, int recursion, void* stream) {
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && G >= 1 && K >= 1, "tgcn_resident_layer_fwd: bad sizes");
     TGCN_REQUIRE(recursion == TGCN_RECURSION_REFERENCE || recursion == TGCN_RECURSION_CHEBYSHEV,
                  "tgcn_resident_layer_fwd: unknown recursion %d", recursion);
     if (Q == 0 || N == 0) return TGCN_OK;
-    TGCN_REQUIRE(rowptr && x && W, "tgcn_resident_layer_fwd: null pointer");
+    TGCN_REQUIRE(rowinfo && x && W && wimages && (entries || E == 0), "tgcn_resident_layer_fwd: null pointer");
+    TGCN_REQUIRE((E & 1) == 0 && aligned16(entries) && aligned16(rowinfo) && aligned16(wimages),
+                 "tgcn_resident_layer_fwd: packed CSR / weight images must be 16-byte aligned with an even entry count");
+    TGCN_REQUIRE(!stack || aligned16(stack), "tgcn_resident_layer_fwd: stack must be 16-byte aligned");
     TGCN_REQUIRE(out || y, "tgcn_resident_layer_fwd: neither out nor pooled output requested");
     TGCN_REQUIRE(bias_mode == TGCN_BIAS_NONE || bias, "tgcn_resident_layer_fwd: bias_mode %d without bias", bias_mode);
     if (y) {
@@ -646,34 +1001,43 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowptr, const int32_t* col
         TGCN_REQUIRE(N % pool_p == 0, "tgcn_resident_layer_fwd: vertex count %d not divisible by pool size %d", N, pool_p);
         TGCN_REQUIRE(idx, "tgcn_resident_layer_fwd: pooled output without idx");
     }
-    const ResPlan pl = res_plan_fwd(N, D, G, K, nnz);
-    TGCN_SUPPORTED(pl.ok, "tgcn_resident_layer_fwd: N=%d D=%d G=%d nnz=%lld does not fit shared memory", N, D, G, (long long)nnz);
-    ResFwdParams p{};
-    p.rowptr = rowptr; p.col = col; p.val = val; p.x = x; p.W = W; p.bias = bias; p.out = out; p.y = y; p.idx = idx;
-    p.stack = stack; p.N = N; p.NP = pl.NP; p.nnz = (int)nnz; p.D = D; p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP;
-    p.GG = pl.GG; p.K = K; p.bias_mode = bias_mode; p.recursion = recursion; p.pool_p = y ? pool_p : 4; p.relu = relu;
-    const ResSmemFwd lay = res_fwd_smem(N, (int)nnz, pl.DP, pl.GP, pl.csr_smem);
+    const ResPlan pl = res_plan_fwd(Q, N, D, G, K, E);
+    TGCN_SUPPORTED(pl.ok, "tgcn_resident_layer_fwd: N=%d D=%d G=%d K=%d E=%lld does not fit shared memory", N, D, G, K, (long long)E);
     cudaStream_t st = as_stream(stream);
-#define TGCN_RES_FWD(TPT, CS)                                                                              \
-    do {                                                                                                   \
-        TGCN_PROPAGATE(res_set_smem(resident_fwd_kernel<TPT, CS>, lay.total, "resident_fwd"));             \
-        resident_fwd_kernel<TPT, CS><<<(unsigned)Q, kResThreads, lay.total, st>>>(p, lay);                 \
+    float* Wm = wimages;
+    float* Wt = wimages + (int64_t)K * pl.DP * pl.GP;
+    resident_prep_kernel<<<(unsigned)ceil_div(pl.DP * pl.GP, 256), 256, 0, st>>>(W, Wm, Wt, K, D, G, pl.DP, pl.GP, recursion);
+    TGCN_LAUNCH_CHECK("resident_prep");
+    ResFwdParams p{};
+    p.rowinfo = reinterpret_cast<const int2*>(rowinfo); p.entries = reinterpret_cast<const int2*>(entries);
+    p.x = x; p.Wm = Wm; p.bias = bias; p.out = out; p.y = y; p.idx = idx;
+    p.stack = stack; p.N = N; p.NP = pl.NP; p.E = (int)E; p.D = D; p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP;
+    p.GG = pl.GG; p.K = K; p.bias_mode = bias_mode; p.recursion = recursion; p.pool_p = y ? pool_p : 4; p.relu = relu;
+    p.CL = pl.split; p.rg_per = pl.rg_per;
+    const ResSmemFwd lay = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, pl.w_smem);
+    const dim3 grid((unsigned)(Q * pl.split));
+#define TGCN_RES_FWD2(TH, TPT, CS, WS) \
+    TGCN_PROPAGATE(res_launch(resident_fwd_kernel<TH, TPT, CS, WS>, grid, TH, pl.split, lay.total, st, "resident_layer_fwd", p, lay))
+#define TGCN_RES_FWD1(TH, TPT)                                                                                       \
+    do {                                                                                                             \
+        if (pl.csr_smem) { if (pl.w_smem) TGCN_RES_FWD2(TH, TPT, true, true); else TGCN_RES_FWD2(TH, TPT, true, false); }   \
+        else             { if (pl.w_smem) TGCN_RES_FWD2(TH, TPT, false, true); else TGCN_RES_FWD2(TH, TPT, false, false); } \
     } while (0)
-    if (pl.csr_smem) {
-        switch (pl.tpt) { case 1: TGCN_RES_FWD(1, true); break; case 2: TGCN_RES_FWD(2, true); break;
-                          case 3: TGCN_RES_FWD(3, true); break; default: TGCN_RES_FWD(4, true); break; }
+    if (pl.threads == 1024) {
+        TGCN_RES_FWD1(1024, 1);
     } else {
-        switch (pl.tpt) { case 1: TGCN_RES_FWD(1, false); break; case 2: TGCN_RES_FWD(2, false); break;
-                          case 3: TGCN_RES_FWD(3, false); break; default: TGCN_RES_FWD(4, false); break; }
+        switch (pl.tpt) { case 1: TGCN_RES_FWD1(512, 1); break; case 2: TGCN_RES_FWD1(512, 2); break;
+                          case 3: TGCN_RES_FWD1(512, 3); break; default: TGCN_RES_FWD1(512, 4); break; }
     }
-#undef TGCN_RES_FWD
+#undef TGCN_RES_FWD1
+#undef TGCN_RES_FWD2
     TGCN_LAUNCH_CHECK("resident_layer_fwd");
     return TGCN_OK;
 }
 
-extern "C" int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N, int64_t nnz,
+extern "C" int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, int N, int64_t E,
                                        const float* dout, const float* dy, const uint8_t* idx, const float* y,
-                                       int pool_p, int relu, const float* stack, const float* W,
+                                       int pool_p, int relu, const float* stack, const float* wimages,
                                        float* dW, float* db, int bias_mode, float* dx, void* workspace,
                                        int Q, int D, int G, int K, int recursion, void* stream) {
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && G >= 1 && K >= 1, "tgcn_resident_layer_bwd: bad sizes");
@@ -687,7 +1051,8 @@ extern "C" int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* co
         if (db && bias_mode == TGCN_BIAS_PER_FILTER) cudaMemsetAsync(db, 0, sizeof(float) * G, st);
         return TGCN_OK;
     }
-    TGCN_REQUIRE(stack && W && workspace, "tgcn_resident_layer_bwd: null pointer");
+    TGCN_REQUIRE(stack && wimages && workspace, "tgcn_resident_layer_bwd: null pointer");
+    TGCN_REQUIRE(aligned16(stack) && aligned16(wimages) && aligned16(workspace), "tgcn_resident_layer_bwd: misaligned buffer");
     TGCN_REQUIRE((dout != nullptr) != (dy != nullptr), "tgcn_resident_layer_bwd: pass exactly one of dout / dy");
     if (dy) {
         TGCN_SUPPORTED(pool_p == 2 || pool_p == 4, "tgcn_resident_layer_bwd: pool size %d", pool_p);
@@ -695,23 +1060,34 @@ extern "C" int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* co
         TGCN_REQUIRE(!relu || y, "tgcn_resident_layer_bwd: relu backward needs the pooled forward output");
     }
     TGCN_REQUIRE(bias_mode == TGCN_BIAS_NONE || db, "tgcn_resident_layer_bwd: bias_mode %d without db", bias_mode);
-    TGCN_REQUIRE(!dx || rowptrT, "tgcn_resident_layer_bwd: dx requested without the CSR of L^T");
-    const ResPlan pl = res_plan_bwd(N, D, G, K, nnz, dx != nullptr);
-    TGCN_SUPPORTED(pl.ok, "tgcn_resident_layer_bwd: N=%d D=%d G=%d nnz=%lld does not fit shared memory", N, D, G, (long long)nnz);
-    ResBwdParams p{};
-    p.rowptrT = rowptrT; p.colT = colT; p.valT = valT; p.dout = dout; p.dy = dy; p.idx = idx; p.y = y; p.stack = stack;
-    p.W = W; p.dWpart = reinterpret_cast<float*>(workspace); p.dx = dx;
-    p.dbpart = bias_mode == TGCN_BIAS_PER_FILTER ? p.dWpart + (int64_t)Q * K * pl.DP * pl.GP : nullptr; p.N = N; p.NP = pl.NP; p.nnz = (int)nnz; p.D = D;
-    p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP; p.GG = pl.GG; p.K = K; p.recursion = recursion;
-    p.pool_p = dy ? pool_p : 4; p.relu = relu;
-    const ResSmemBwd lay = res_bwd_smem(N, (int)nnz, pl.DP, pl.GP, dx != nullptr, pl.csr_smem);
-    if (pl.csr_smem) {
-        TGCN_PROPAGATE(res_set_smem(resident_bwd_kernel<true>, lay.total, "resident_bwd"));
-        resident_bwd_kernel<true><<<(unsigned)Q, kResThreads, lay.total, st>>>(p, lay);
-    } else {
-        TGCN_PROPAGATE(res_set_smem(resident_bwd_kernel<false>, lay.total, "resident_bwd"));
-        resident_bwd_kernel<false><<<(unsigned)Q, kResThreads, lay.total, st>>>(p, lay);
+    if (dx) {
+        TGCN_REQUIRE(rowinfoT && (entriesT || E == 0), "tgcn_resident_layer_bwd: dx requested without the packed CSR of L^T");
+        TGCN_REQUIRE((E & 1) == 0 && aligned16(entriesT) && aligned16(rowinfoT),
+                     "tgcn_resident_layer_bwd: packed CSR must be 16-byte aligned with an even entry count");
     }
+    const ResPlan pl = res_plan_bwd(Q, N, D, G, K, E, dx != nullptr);
+    TGCN_SUPPORTED(pl.ok, "tgcn_resident_layer_bwd: N=%d D=%d G=%d K=%d E=%lld does not fit shared memory", N, D, G, K, (long long)E);
+    ResBwdParams p{};
+    p.rowinfoT = reinterpret_cast<const int2*>(rowinfoT); p.entriesT = reinterpret_cast<const int2*>(entriesT);
+    p.dout = dout; p.dy = dy; p.idx = idx; p.y = y; p.stack = stack;
+    p.Wt = wimages + (int64_t)K * pl.DP * pl.GP; p.dWpart = reinterpret_cast<float*>(workspace); p.dx = dx;
+    p.dbpart = bias_mode == TGCN_BIAS_PER_FILTER ? p.dWpart + (int64_t)Q * K * pl.DP * pl.GP : nullptr;
+    p.N = N; p.NP = pl.NP; p.E = (int)E; p.D = D;
+    p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP; p.GG = pl.GG; p.K = K; p.recursion = recursion;
+    p.pool_p = dy ? pool_p : 4; p.relu = relu; p.S = pl.split; p.Vh = pl.Vh; p.R = pl.R;
+    const ResSmemBwd lay = res_bwd_smem(N, E, pl.DP, pl.Vh, pl.GP, K, pl.R, dx != nullptr, pl.csr_smem, pl.w_smem);
+    const dim3 grid((unsigned)Q, (unsigned)pl.split);
+#define TGCN_RES_BWD2(DWT, CS, WS) \
+    TGCN_PROPAGATE(res_launch(resident_bwd_kernel<DWT, CS, WS>, grid, kBwdThreads, 1, lay.total, st, "resident_layer_bwd", p, lay))
+#define TGCN_RES_BWD1(DWT)                                                                                     \
+    do {                                                                                                       \
+        if (pl.csr_smem) { if (pl.w_smem) TGCN_RES_BWD2(DWT, true, true); else TGCN_RES_BWD2(DWT, true, false); }   \
+        else             { if (pl.w_smem) TGCN_RES_BWD2(DWT, false, true); else TGCN_RES_BWD2(DWT, false, false); } \
+    } while (0)
+    switch (pl.dwt) { case 1: TGCN_RES_BWD1(1); break; case 2: TGCN_RES_BWD1(2); break;
+                      case 3: TGCN_RES_BWD1(3); break; default: TGCN_RES_BWD1(4); break; }
+#undef TGCN_RES_BWD1
+#undef TGCN_RES_BWD2
     TGCN_LAUNCH_CHECK("resident_layer_bwd");
 
     ResReduceParams r{};
@@ -720,7 +1096,8 @@ extern "C" int tgcn_resident_layer_bwd(const int32_t* rowptrT, const int32_t* co
     r.bias_mode = bias_mode; r.pool_p = p.pool_p; r.relu = relu;
     r.w_blocks = (int)ceil_div((int64_t)D * G, kRedElems);
     int b_blocks = 0;
-    if (bias_mode == TGCN_BIAS_PER_VERTEX) b_blocks = (int)ceil_div((int64_t)N * G, kRedElems * 16);
+    if (bias_mode == TGCN_BIAS_PER_VERTEX)
+        b_blocks = (int)ceil_div(dout ? (int64_t)N * G : (int64_t)(N / p.pool_p) * G, kRedElems * 16);
     else if (bias_mode == TGCN_BIAS_PER_FILTER) b_blocks = (int)ceil_div(G, kRedElems * 16);
     resident_reduce_kernel<<<(unsigned)(r.w_blocks + b_blocks), kRedElems * 16, 0, st>>>(r);
     TGCN_LAUNCH_CHECK("resident_reduce");

@@ -137,10 +137,12 @@ class ResidentChebFunction(torch.autograd.Function):
         else:
             out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
             y = idx = None
+        wimg = torch.empty(int(lib.tgcn_resident_weights_bytes(D, G, K)) // 4, dtype=torch.float32, device=dev)
+        rowinfo, entries, E = plan.packed(lib.tgcn_resident_pack_classes(Q, N, D, 0))
         with _DeviceGuard(dev):
-            rc = lib.tgcn_resident_layer_fwd(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, plan.nnz, _ptr(x), _ptr(w),
+            rc = lib.tgcn_resident_layer_fwd(_ptr(rowinfo), _ptr(entries), N, E, _ptr(x), _ptr(w),
                                              _ptr(b), bm, _ptr(out), _ptr(y), _ptr(idx), pool_p, int(relu), _ptr(stack),
-                                             Q, D, G, K, recursion, _stream(dev))
+                                             _ptr(wimg), Q, D, G, K, recursion, _stream(dev))
         _lib.check(rc, "tgcn_resident_layer_fwd")
         ctx.plan = plan
         ctx.dims = (Q, N, D, G, K)
@@ -149,10 +151,10 @@ class ResidentChebFunction(torch.autograd.Function):
         ctx.w_shape = tuple(weight.shape)
         ctx.x_shape = tuple(x.shape)
         if pool_p:
-            ctx.save_for_backward(stack, w, y, idx)
+            ctx.save_for_backward(stack, wimg, y, idx)
             ctx.mark_non_differentiable(idx)
             return y, idx
-        ctx.save_for_backward(stack, w)
+        ctx.save_for_backward(stack, wimg)
         return out
 
     @staticmethod
@@ -162,7 +164,7 @@ class ResidentChebFunction(torch.autograd.Function):
         bm, recursion, pool_p, relu = ctx.cfg
         plan = ctx.plan
         saved = ctx.saved_tensors
-        stack, w = saved[0], saved[1]
+        stack, wimg = saved[0], saved[1]
         y, idx = (saved[2], saved[3]) if pool_p else (None, None)
         if stack is None:
             raise RuntimeError("resident layer was run without gradient tracking; nothing saved for backward")
@@ -173,10 +175,11 @@ class ResidentChebFunction(torch.autograd.Function):
         db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=dev) if bm != _lib.BIAS_NONE else None
         dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev) if need_dx else None
         ws = torch.empty(max(int(lib.tgcn_resident_bwd_workspace(Q, N, D, G, K)) // 4, 1), dtype=torch.float32, device=dev)
+        rowinfo, entries, E = plan.packed(lib.tgcn_resident_pack_classes(Q, N, D, 1), transpose=True)
         with _DeviceGuard(dev):
-            rc = lib.tgcn_resident_layer_bwd(_ptr(plan.rowptr_t), _ptr(plan.col_t), _ptr(plan.val_t), N, plan.nnz,
+            rc = lib.tgcn_resident_layer_bwd(_ptr(rowinfo), _ptr(entries), N, E,
                                              None if pool_p else _ptr(grad), _ptr(grad) if pool_p else None, _ptr(idx), _ptr(y),
-                                             pool_p, int(relu), _ptr(stack), _ptr(w), _ptr(dW), _ptr(db), bm, _ptr(dx), _ptr(ws),
+                                             pool_p, int(relu), _ptr(stack), _ptr(wimg), _ptr(dW), _ptr(db), bm, _ptr(dx), _ptr(ws),
                                              Q, D, G, K, recursion, _stream(dev))
         _lib.check(rc, "tgcn_resident_layer_bwd")
         return dx, dW, db, None, None, None, None, None
