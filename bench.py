@@ -116,7 +116,7 @@ def algorithmic_step_bytes(N, C, nnz, has_prev):
 def run_b200(args):
     import torch.distributed as dist
     from tgcn_b200 import _lib, workloads as wl
-    from tgcn_b200.parallel import FlatGradients, broadcast_parameters, init_distributed
+    from tgcn_b200.parallel import GradientBucket, broadcast_parameters, init_distributed
 
     rank, world, local = init_distributed("nccl")
     if world != args.gpus:
@@ -139,61 +139,60 @@ def run_b200(args):
         model = wl.NetTGCN_MNIST(Lt, horizon=H, n_classes=cfg["classes"], engine=args.engine).to(dev)
     broadcast_parameters(model)
     N0 = Ls[0].shape[0]
-    grads = FlatGradients(model.parameters())
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.5)   # pytorch_hcp_tgcn.py defaults
+    grads = GradientBucket(model.parameters())
+    # pytorch_hcp_tgcn.py defaults (lr 0.01, momentum 0.5); torch's fused multi-tensor implementation: one launch
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.5, fused=True)
 
     # synthetic data: a few distinct pinned host batches per rank, cycled
     n_host = 4
     hx = [wl.synthetic_signals(Q, N0, H, n_real, perm, seed=1000 * rank + i).pin_memory() for i in range(n_host)]
     g = torch.Generator().manual_seed(77 + rank)
     hy = [torch.randint(0, cfg["classes"], (Q,), generator=g).pin_memory() for _ in range(n_host)]
-    x = hx[0].to(dev)
-    y = hy[0].to(dev)
+    # two device input buffers: while step i runs, the copy stream uploads batch i+1 into the other one
+    xs = [hx[0].to(dev), hx[1].to(dev)]
+    ys = [hy[0].to(dev), hy[1].to(dev)]
     loss_dev = torch.zeros((), device=dev)
     loss_host = torch.zeros((), pin_memory=True)
 
-    def fwd_bwd():
-        grads.zero_()
-        out = model(x)
-        loss = F.nll_loss(out, y)
+    def fwd_bwd(b):
+        opt.zero_grad(set_to_none=True)      # autograd allocates the gradients: no zero fill, no accumulate kernels
+        out = model(xs[b])
+        loss = F.nll_loss(out, ys[b])
         loss.backward()
         loss_dev.copy_(loss.detach())
 
     def finish_step():
-        grads.allreduce_mean()
+        grads.sync()                         # world > 1: one flat NCCL allreduce (average)
         opt.step()
 
-    # warm-up (eager, side stream) then capture the forward/backward and the update as two graphs
+    # warm-up (eager, side stream) then capture the whole training step (forward, loss, backward, gradient
+    # allreduce, SGD update) as ONE CUDA graph per input buffer
     model.train()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        for _ in range(3):
-            fwd_bwd(); finish_step()
+        for i in range(3):
+            fwd_bwd(i % 2); finish_step()
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     use_graph = not args.no_graph
     launches_per_step = None
     if use_graph:
-        g1 = torch.cuda.CUDAGraph()
-        c0 = lib.tgcn_launch_count()
-        with torch.cuda.graph(g1):
-            fwd_bwd()
-        launches_per_step = lib.tgcn_launch_count() - c0
-        g2 = torch.cuda.CUDAGraph()
-        if world == 1:
-            with torch.cuda.graph(g2):
-                opt.step()
-
-        def step():
-            g1.replay()
-            if world == 1:
-                g2.replay()
-            else:
+        graphs_ = []
+        for b in range(2):
+            g = torch.cuda.CUDAGraph()
+            c0 = lib.tgcn_launch_count()
+            with torch.cuda.graph(g):
+                fwd_bwd(b)
                 finish_step()
+            launches_per_step = lib.tgcn_launch_count() - c0
+            graphs_.append(g)
+
+        def step(b=0):
+            graphs_[b].replay()
     else:
-        def step():
-            fwd_bwd(); finish_step()
+        def step(b=0):
+            fwd_bwd(b); finish_step()
         c0 = lib.tgcn_launch_count(); step(); launches_per_step = lib.tgcn_launch_count() - c0
 
     # L2 hygiene: flush between timed iterations when the step's working set fits in L2
@@ -207,8 +206,21 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream()
+
     def timed(nsteps, e2e):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        copied = [torch.cuda.Event() for _ in range(nsteps + 1)]
+        done = [torch.cuda.Event() for _ in range(nsteps)]
+        main = torch.cuda.current_stream()
+
+        def upload(i):                       # batch i -> device buffer i % 2, on the copy stream
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(done[i - 2])      # the buffer's previous consumer has finished
+                xs[i % 2].copy_(hx[i % n_host], non_blocking=True)
+                ys[i % 2].copy_(hy[i % n_host], non_blocking=True)
+                copied[i].record(copy_stream)
         barrier()
         t0 = time.perf_counter()
         for i in range(nsteps):
@@ -216,10 +228,14 @@ def run_b200(args):
                 flush_buf.fill_(float(i))
             ev[i][0].record()
             if e2e:
-                x.copy_(hx[i % n_host], non_blocking=True)
-                y.copy_(hy[i % n_host], non_blocking=True)
-            step()
+                if i == 0:
+                    upload(0)
+                if i + 1 < nsteps:
+                    upload(i + 1)            # overlaps with this step's compute
+                main.wait_event(copied[i])
+            step(i % 2 if e2e else 0)
             if e2e:
+                done[i].record(main)
                 loss_host.copy_(loss_dev, non_blocking=True)
             ev[i][1].record()
             if e2e:
@@ -265,7 +281,8 @@ def run_b200(args):
                        "N_padded": [int(L.shape[0]) for L in Ls], "nnz_L0": int(Ls[0].nnz), "K": 10, "H": H,
                        "parallelism": "dp%d" % world, "engine": args.engine,
                        "l2": "flushed between timed steps (256 MB write)" if flush else "working set exceeds L2 (K-slab stack > 126 MB)",
-                       "cuda_graph": use_graph},
+                       "cuda_graph": use_graph,
+                       "e2e_pipeline": "batch i+1 is uploaded (pinned host -> device, copy stream) while step i runs; the loss is read back and synchronised every step"},
             "e2e": {"value": world * Q / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 8), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -281,40 +298,26 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
-    """Average launch duration of the dominant kernel (the CSR SpMM recursion step of layer 1) on the
-    workload's own operand and slab shapes, CUDA events on the launching stream."""
+def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    plan = model.tgcn1._plan(dev)
-    N = plan.n
-    C = Q * H
-    K = 10
-    stack = torch.randn(K, N, C, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    reps = 20
+        return json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
-    def steps():
-        st = torch.cuda.current_stream().cuda_stream
-        for k in range(1, K):
-            lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), N,
-                               stack[k - 1].data_ptr(), None, stack[k].data_ptr(), C, 1.0, 0.0, st)
+
+def _time_graph(fn, reps, flush_buf):
+    """Average device time of fn() (CUDA events on the launching stream, CUDA-graph replay so that host
+    launch latency is not what gets timed on the small workloads, L2 flushed between replays)."""
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(3):
-            steps()
+            fn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    # the K-1 launches are replayed from a CUDA graph so that host launch latency (ctypes) is not
-    # what gets timed on the small workloads
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        st = torch.cuda.current_stream().cuda_stream
-        steps()
+        fn()
     total = 0.0
     for r in range(reps):
         if flush_buf is not None:
@@ -322,7 +325,62 @@ def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); graph.replay(); b.record(); b.synchronize()
         total += a.elapsed_time(b)
-    per_launch_ms = total / (reps * (K - 1))
+    return total / reps
+
+
+def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
+    """Roofline of the dominant kernel of layer 1 on the workload's own operand shapes.
+
+    Streaming path (large graphs): the CSR SpMM recursion step, 2S+E algorithmic bytes per launch.
+    Resident path (graphs whose per-sample slab fits in shared memory): the fused whole-layer forward
+    kernel; its algorithmic bytes are SURVEY.md section 8(d)'s fused-layer figure
+    B_fwd = (3K-4) S + (K-1) E + 4QNG + 4KHFG + 4NG (what a design that writes every T_k to HBM once would
+    move); the kernel keeps the recursion in shared memory, so its real DRAM traffic is far lower
+    (reported as `compulsory_bytes`: x + pooled output + indices + the saved basis)."""
+    from tgcn_b200.nn import functional as Fn
+    peak, src = _peak()
+    lay = model.tgcn1
+    plan = lay._plan(dev)
+    N = plan.n
+    K, Hh, Fin, G = lay.weight.shape
+    D = Hh * Fin
+    C = Q * D
+    S = 4 * N * C
+    E = 8 * plan.nnz + 4 * (N + 1)
+    reps = 20
+    if lay._use_resident(plan, D, G, K):
+        x = torch.randn(Q, N, D, device=dev)
+        w = lay.weight.detach().reshape(K, D, G).contiguous()
+        bias = lay.bias.detach().contiguous()
+        y = torch.empty(Q, N // 4, G, device=dev)
+        idx = torch.empty(Q, N // 4, G, dtype=torch.uint8, device=dev)
+        stack = torch.empty(int(lib.tgcn_resident_stack_bytes(Q, N, D, K)) // 4, device=dev)
+        wimg = torch.empty(int(lib.tgcn_resident_weights_bytes(D, G, K)) // 4, device=dev)
+        rowinfo, entries, Ep = plan.packed(lib.tgcn_resident_pack_classes(Q, N, D, 0))
+
+        def call():
+            st = torch.cuda.current_stream().cuda_stream
+            rc = lib.tgcn_resident_layer_fwd(rowinfo.data_ptr(), entries.data_ptr(), N, Ep, x.data_ptr(), w.data_ptr(),
+                                             bias.data_ptr(), 1, None, y.data_ptr(), idx.data_ptr(), 4, 1, stack.data_ptr(),
+                                             wimg.data_ptr(), Q, D, G, K, 0, st)
+            assert rc == 0
+        ms = _time_graph(call, reps, flush_buf)
+        bytes_per_launch = (3 * K - 4) * S + (K - 1) * E + 4 * Q * N * G + 4 * K * D * G + 4 * N * G
+        compulsory = 4 * Q * N * D + 5 * Q * (N // 4) * G + stack.numel() * 4 + 4 * K * D * G + 4 * N * G + E
+        achieved = bytes_per_launch / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "resident_fwd_kernel (layer 1: recursion + contraction + bias + ReLU + max-pool in one "
+                                          "launch; timed together with its weight-image prologue kernel)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bytes_per_launch": int(bytes_per_launch), "bytes_formula": "SURVEY 8d B_fwd = (3K-4)S+(K-1)E+4QNG+4KHFG+4NG",
+                "compulsory_bytes": int(compulsory), "us_per_launch": ms * 1e3, "peak_source": src}
+    stack = torch.randn(K, N, C, device=dev)
+
+    def steps():
+        st = torch.cuda.current_stream().cuda_stream
+        for k in range(1, K):
+            lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), N,
+                               stack[k - 1].data_ptr(), None, stack[k].data_ptr(), C, 1.0, 0.0, st)
+    per_launch_ms = _time_graph(steps, reps, flush_buf) / (K - 1)
     bytes_per_launch = algorithmic_step_bytes(N, C, plan.nnz, has_prev=False)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "spmm_step_vec4_kernel (layer-1 recursion step, 2S+E bytes)",

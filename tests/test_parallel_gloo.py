@@ -73,6 +73,46 @@ def test_data_parallel_flat_allreduce_matches_single_process():
     _run(_dp_worker, 2)
 
 
+def _bucket_worker(rank, world):
+    """GradientBucket: autograd-allocated gradients (set_to_none), one packed collective, p.grad re-bound to
+    the averaged flat views; an SGD step on every rank then gives identical parameters."""
+    import torch.nn.functional as F
+    from oracle import model_torch
+    from tgcn_b200.parallel import GradientBucket, broadcast_parameters, shard_range
+    r = load_golden("graph_grid28_k8_seed0.npz")
+    Ls = [torch.tensor(np.asarray(csr_from(r, "L_%d" % i).todense()), dtype=torch.float) for i in range(3)]
+    torch.manual_seed(5 + rank)
+    model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    broadcast_parameters(model, src=0)
+    model.eval()
+    gen = torch.Generator().manual_seed(3)
+    Q = 6
+    x = torch.randn(Q, Ls[0].shape[0], 5, generator=gen)
+    y = torch.randint(0, 3, (Q,), generator=gen)
+    ref_model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    ref_model.load_state_dict(model.state_dict()); ref_model.eval()
+    F.nll_loss(ref_model(x), y).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in ref_model.parameters()])
+    bucket = GradientBucket(model.parameters())
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    opt.zero_grad(set_to_none=True)
+    lo, hi = shard_range(Q, rank, world)
+    F.nll_loss(model(x[lo:hi]), y[lo:hi]).backward()
+    bucket.sync()
+    for p in model.parameters():
+        assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+    assert float((bucket.flat - ref).abs().max() / ref.abs().max()) < 1e-5
+    opt.step()
+    mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    other = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(other, mine)
+    assert all(torch.equal(o, mine) for o in other)       # replicas stay bit-identical
+
+
+def test_gradient_bucket_keeps_replicas_identical():
+    _run(_bucket_worker, 2)
+
+
 def _halo_worker(rank, world):
     import scipy.sparse as sp
     from tgcn_b200.parallel import RowPartition, halo_exchange

@@ -741,15 +741,23 @@ resident_reduce_kernel(const ResReduceParams p) {
             if (e < DG) {
                 const float* src = p.dWpart + ((int64_t)jj * p.DP + d) * p.GP + g;
                 const int64_t qs = (int64_t)p.K * p.DP * p.GP;
-                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                int q = 0;
-                for (; q + 8 <= p.Q; q += 8) {
+                // 32 independent loads in flight per round trip; fixed summation tree => deterministic
+                float f[32];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) f[u] += __ldg(src + (q + u) * qs);
+                for (int u = 0; u < 32; ++u) f[u] = 0.f;
+                int q = 0;
+                for (; q + 32 <= p.Q; q += 32) {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) f[u] += __ldg(src + (q + u) * qs);
                 }
-                for (; q < p.Q; ++q) f[0] += __ldg(src + q * qs);
-                s = (((double)f[0] + (double)f[1]) + ((double)f[2] + (double)f[3])) +
-                    (((double)f[4] + (double)f[5]) + ((double)f[6] + (double)f[7]));
+#pragma unroll
+                for (int u = 0; u < 32; ++u)
+                    if (q + u < p.Q) f[u] += __ldg(src + (q + u) * qs);
+#pragma unroll
+                for (int w = 16; w >= 1; w >>= 1)
+#pragma unroll
+                    for (int u = 0; u < w; ++u) f[u] += f[u + w];
+                s = (double)f[0];
             }
             red[jj][e_local] = s;
         }
@@ -777,21 +785,29 @@ resident_reduce_kernel(const ResReduceParams p) {
         if (p.dout) {
             if (i >= (int64_t)p.N * p.G) return;
             const int64_t NG = (int64_t)p.N * p.G;
-            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int q = 0;
-            for (; q + 8 <= p.Q; q += 8) {
+            float f[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) f[u] += __ldg(p.dout + (q + u) * NG + i);
+            for (int u = 0; u < 16; ++u) f[u] = 0.f;
+            int q = 0;
+            for (; q + 16 <= p.Q; q += 16) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) f[u] += __ldg(p.dout + (q + u) * NG + i);
             }
-            for (; q < p.Q; ++q) f[0] += __ldg(p.dout + q * NG + i);
-            p.db[i] = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (q + u < p.Q) f[u] += __ldg(p.dout + (q + u) * NG + i);
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                for (int u = 0; u < w; ++u) f[u] += f[u + w];
+            p.db[i] = f[0];
         } else {
             // one pooled element per thread: its gradient goes to the sibling idx selected in each sample
             const int pp = p.pool_p, M = p.N / pp;
             if (i >= (int64_t)M * p.G) return;
             const int64_t MG = (int64_t)M * p.G;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
+#pragma unroll 16
             for (int q = 0; q < p.Q; ++q) {
                 const int64_t off = q * MG + i;
                 const int a = p.idx[off];

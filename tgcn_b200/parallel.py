@@ -65,6 +65,43 @@ class FlatGradients:
         return self.flat
 
 
+class GradientBucket:
+    """Gradient exchange for a training step that lets autograd ALLOCATE the gradients
+    (`zero_grad(set_to_none=True)`: no zero fill, no accumulate kernels): after the backward the
+    per-parameter gradients are packed into one flat fp32 buffer by a single multi-tensor copy, averaged
+    over the ranks by ONE collective, and `p.grad` is re-bound to the views of the flat buffer so the
+    optimizer reads the averaged values.  Everything is capturable in a CUDA graph (NCCL included).
+    With world size 1 it does nothing."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def sync(self):
+        if self.world == 1:
+            return
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch._foreach_copy_(self.views, grads)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
 def broadcast_parameters(module, src=0, group=None):
     """Replicate rank `src`'s parameters and buffers (what DataParallel's replicate does per step,
     done once here)."""
