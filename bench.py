@@ -118,6 +118,7 @@ def run_b200(args):
     from tgcn_b200 import _lib, workloads as wl
     from tgcn_b200.parallel import GradientBucket, broadcast_parameters, init_distributed
 
+    os.environ.pop("NCCL_DEBUG", None)      # its version banner goes to stdout; the contract is ONE JSON line
     rank, world, local = init_distributed("nccl")
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world))
@@ -294,8 +295,12 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # ProcessGroupNCCL teardown blocks while CUDA graphs that captured collectives are alive (observed on
+        # torch 2.11 / NCCL 2.28: destroy_process_group never returns): synchronise, flush and leave.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def _peak():
