@@ -59,6 +59,24 @@ int tgcn_device_supported(void);
 /* kernel launches issued by this library so far (host counter; a launch recorded during CUDA-graph
  * capture counts once) */
 long long tgcn_launch_count(void);
+/* Kernel-variant selection for tests and sweeps (also readable from the environment as TGCN_<KEY>):
+ * "SPMM_PIPE" = blocks per SM of the persistent, software-pipelined SpMM kernel (0 = plain kernel),
+ * "SPMM_TILE" = rows per block of the row-tiled SpMM kernel (0 = off).  All variants are bit-identical. */
+int tgcn_set_tuning(const char* key, int value);
+
+/* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */
+/* For graphs with locality in their row order (meshes in coarsening order), tgcn_spmm_step and everything
+ * built on it stage the DISTINCT source rows of each block of RB consecutive rows in shared memory by bulk
+ * copies and gather from there ("SPMM_STAGED" tuning key, on by default whenever a plan is registered).
+ * tgcn_block_plan_host computes the plan arrays on the host (blk_rows_host == NULL: size query); upload
+ * them and register them with tgcn_plan_create, keyed by the device address of the CSR `col` array they
+ * belong to.  The arrays stay owned by the caller and must outlive the plan.  Results are bit-identical
+ * with and without a plan. */
+int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB,
+                             int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host);
+int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
+                         const uint16_t* lcol_dev, int RB, int maxd);
+int tgcn_plan_destroy(int64_t handle);
 
 /* ---- layout ------------------------------------------------------------------------------ */
 /* x[Q,N,D] -> slab[N,Q,D]   (replaces X.permute(1,3,2,0).reshape(N,-1), gcn_matmul.py:152-153) */

@@ -1,6 +1,8 @@
 // Library-level entry points: version, error reporting, device check.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <atomic>
 #include "common.cuh"
 
@@ -16,7 +18,34 @@ int set_error(int code, const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static const char* const kTuneNames[kTuneCount] = {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED"};
+static const int kTuneDefaults[kTuneCount] = {0, 0, 1};   // SPMM_STAGED applies only to operands with a registered plan
+static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}};
+
+int tuning_value(int key) {
+    int v = g_tune[key].load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    char name[64];
+    snprintf(name, sizeof(name), "TGCN_%s", kTuneNames[key]);
+    const char* e = getenv(name);
+    v = e ? atoi(e) : kTuneDefaults[key];
+    if (v < 0) v = kTuneDefaults[key];
+    g_tune[key].store(v, std::memory_order_relaxed);
+    return v;
+}
 }  // namespace tgcn
+
+// Select a kernel variant at run time (tests, sweeps): key in {"SPMM_TILE", "SPMM_PIPE"}; returns 0, or -1 for an
+// unknown key.  SPMM_PIPE = blocks per SM of the persistent pipelined SpMM kernel (0: one-thread-per-float4 kernel);
+// SPMM_TILE = rows per block of the row-tiled SpMM kernel (0: off).
+extern "C" int tgcn_set_tuning(const char* key, int value) {
+    for (int i = 0; i < tgcn::kTuneCount; ++i)
+        if (key && strcmp(key, tgcn::kTuneNames[i]) == 0) {
+            tgcn::g_tune[i].store(value < 0 ? tgcn::kTuneDefaults[i] : value);
+            return 0;
+        }
+    return -1;
+}
 
 extern "C" long long tgcn_launch_count(void) { return tgcn::g_launches.load(); }
 

@@ -20,6 +20,10 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // `gpu_launches`; launches recorded during graph capture count once per capture).
 void count_launch();
 
+// Run-time tuning knobs (tgcn_set_tuning / environment TGCN_<NAME> read once); -1 = built-in default.
+enum TuneKey { kTuneSpmmTile = 0, kTuneSpmmPipe = 1, kTuneSpmmStaged = 2, kTuneCount = 3 };
+int tuning_value(int key);
+
 }  // namespace tgcn
 
 #define TGCN_REQUIRE(cond, ...)                                            \

@@ -4,7 +4,12 @@
 // float4 of one output row; the dense operand rows are read as coalesced 16-byte vectors
 // (a neighbour row is C*4 contiguous bytes), CSR (col,val) pairs are warp-broadcast loads that
 // stay in L1, the axpy with T_{k-2} is fused so every slab is written exactly once.
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tgcn {
 
@@ -117,6 +122,217 @@ spmm_step_vec4_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
     out[idx] = r;
 }
 
+// Tiled variant: a block owns RB consecutive rows x one 128-byte column strip (8 float4 = one cache line per
+// gathered neighbour row).  Rows that are consecutive in the coarsening order are graph neighbours, so the
+// lines a block gathers are shared between its rows and are served from L1 instead of L2; blocks of the
+// same strip run back to back (blockIdx.x fastest), so a strip's N x 128 B working set stays in L2.
+// Same per-row summation order as spmm_step_vec4_kernel: results are bit-identical.
+template <bool kHasPrev, int RB>
+__global__ void __launch_bounds__(RB * 8)
+spmm_step_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                      const float* __restrict__ val, int N, const float4* __restrict__ in,
+                      const float4* prev, float4* out, int V, float alpha, float beta) {
+    const int v = blockIdx.y * 8 + (threadIdx.x & 7);
+    const int row = blockIdx.x * RB + (threadIdx.x >> 3);
+    if (row >= N || v >= V) return;
+    int e = __ldg(rowptr + row);
+    const int e1 = __ldg(rowptr + row + 1);
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    for (; e + 4 <= e1; e += 4) {
+        const int c0 = __ldg(col + e), c1 = __ldg(col + e + 1), c2 = __ldg(col + e + 2), c3 = __ldg(col + e + 3);
+        const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1), w2 = __ldg(val + e + 2), w3 = __ldg(val + e + 3);
+        const float4 x0 = __ldg(in + (int64_t)c0 * V + v);
+        const float4 x1 = __ldg(in + (int64_t)c1 * V + v);
+        const float4 x2 = __ldg(in + (int64_t)c2 * V + v);
+        const float4 x3 = __ldg(in + (int64_t)c3 * V + v);
+        fma4(acc0, w0, x0);
+        fma4(acc1, w1, x1);
+        fma4(acc0, w2, x2);
+        fma4(acc1, w3, x3);
+    }
+    for (; e < e1; ++e) {
+        const int c0 = __ldg(col + e);
+        const float w0 = __ldg(val + e);
+        fma4(acc0, w0, __ldg(in + (int64_t)c0 * V + v));
+    }
+    float4 r;
+    r.x = alpha * (acc0.x + acc1.x);
+    r.y = alpha * (acc0.y + acc1.y);
+    r.z = alpha * (acc0.z + acc1.z);
+    r.w = alpha * (acc0.w + acc1.w);
+    const int64_t idx = (int64_t)row * V + v;
+    if (kHasPrev) {
+        const float4 p = prev[idx];
+        r.x = fmaf(beta, p.x, r.x);
+        r.y = fmaf(beta, p.y, r.y);
+        r.z = fmaf(beta, p.z, r.z);
+        r.w = fmaf(beta, p.w, r.w);
+    }
+    out[idx] = r;
+}
+
+// Persistent, software-pipelined variant.  With ~6 stored entries per row (meshes) a thread of the plain
+// kernel spends its life in a chain of three dependent round trips (row bounds -> (col,val) -> gathers) and the
+// gathers are in flight for only one of them.  Here a thread owns one float4 column of a strided set of rows
+// and always has the NEXT batch of (col,val) pairs (same row, or the first batch of its next row) and the next
+// row's bounds in flight while the current batch's gathers are outstanding.  Summation order per row is the
+// same as spmm_step_vec4_kernel (full batches alternate two accumulators, the tail goes to the first), so the
+// results are bit-identical.
+template <bool kHasPrev>
+__global__ void __launch_bounds__(256)
+spmm_step_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                      const float* __restrict__ val, int N, const float4* __restrict__ in,
+                      const float4* prev, float4* out, int V, float alpha, float beta, int rows_per_pass) {
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int slot = (int)(gtid / V);
+    const int v = (int)(gtid - (int64_t)slot * V);
+    if (slot >= rows_per_pass || slot >= N) return;
+    int row = slot;
+    int e = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+    int c[4] = {0, 0, 0, 0};
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    int nb = 0;
+    auto fetch = [&](int ee, int ee1) {
+        nb = min(4, ee1 - ee);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nb) { c[i] = __ldg(col + ee + i); w[i] = __ldg(val + ee + i); }
+    };
+    fetch(e, e1);
+    while (true) {
+        const int nrow = row + rows_per_pass;
+        const bool has_next = nrow < N;
+        int ne = 0, ne1 = 0;
+        if (has_next) { ne = __ldg(rowptr + nrow); ne1 = __ldg(rowptr + nrow + 1); }
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        while (true) {
+            float4 x[4];
+            float cw[4];
+            const int cnb = nb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cw[i] = w[i];
+                if (i < cnb) x[i] = __ldg(in + (int64_t)c[i] * V + v);
+            }
+            e += cnb;
+            const bool more = e < e1;
+            if (more) fetch(e, e1);
+            else if (has_next) fetch(ne, ne1);
+            if (cnb == 4) {
+                fma4(a0, cw[0], x[0]);
+                fma4(a1, cw[1], x[1]);
+                fma4(a0, cw[2], x[2]);
+                fma4(a1, cw[3], x[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i < cnb) fma4(a0, cw[i], x[i]);
+            }
+            if (!more) break;
+        }
+        float4 r;
+        r.x = alpha * (a0.x + a1.x);
+        r.y = alpha * (a0.y + a1.y);
+        r.z = alpha * (a0.z + a1.z);
+        r.w = alpha * (a0.w + a1.w);
+        const int64_t idx = (int64_t)row * V + v;
+        if (kHasPrev) {
+            const float4 p = prev[idx];
+            r.x = fmaf(beta, p.x, r.x);
+            r.y = fmaf(beta, p.y, r.y);
+            r.z = fmaf(beta, p.z, r.z);
+            r.w = fmaf(beta, p.w, r.w);
+        }
+        out[idx] = r;
+        if (!has_next) break;
+        row = nrow; e = ne; e1 = ne1;
+    }
+}
+
+// Row-block staged variant (graphs with locality, e.g. the coarsening order of a mesh: siblings, cousins, ...
+// are consecutive rows).  A block owns RB consecutive rows; the DISTINCT source rows its entries reference
+// (precomputed on the host: tgcn_block_plan_host) are copied once into shared memory by 1-D bulk copies
+// (cp.async.bulk, one per source row, completion on an mbarrier) and every gather is then served from shared
+// memory through block-local column ids.  L2 -> SM traffic drops from nnz/N slabs to (distinct rows per
+// block)/RB slabs per step (mesh32k: 4.66 -> 1.87).  Same per-row summation order: bit-identical results.
+struct StagedParams {
+    const int* rowptr; const unsigned short* lcol; const float* val;
+    const int* blk_ptr; const int* blk_rows;
+    const float4* in; const float4* prev; float4* out;
+    int N, RB, V, SW;          // SW = float4 per staged row (column strip width)
+    float alpha, beta;
+};
+
+template <bool kHasPrev>
+__global__ void __launch_bounds__(256)
+spmm_step_staged_kernel(const StagedParams p) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(st_smem);
+    float4* stage = reinterpret_cast<float4*>(st_smem + 16);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int s0 = blockIdx.y * p.SW;
+    const int sw = min(p.SW, p.V - s0);
+    const int d0 = __ldg(p.blk_ptr + b), nd = __ldg(p.blk_ptr + b + 1) - d0;
+    if (tid == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nd * (uint32_t)sw * 16u);
+        __syncwarp();
+        for (int d = tid; d < nd; d += 32)
+            tc::bulk_g2s(stage + (size_t)d * p.SW, p.in + (int64_t)__ldg(p.blk_rows + d0 + d) * p.V + s0, (uint32_t)sw * 16u, bar);
+    }
+    tc::mbar_wait(bar, 0);
+    const int row0 = b * p.RB;
+    const int rows = min(p.RB, p.N - row0);
+    for (int i = tid; i < rows * sw; i += blockDim.x) {
+        const int r = i / sw, v = i - r * sw;
+        const int row = row0 + r;
+        int e = __ldg(p.rowptr + row);
+        const int e1 = __ldg(p.rowptr + row + 1);
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        for (; e + 4 <= e1; e += 4) {
+            const int c0 = __ldg(p.lcol + e), c1 = __ldg(p.lcol + e + 1), c2 = __ldg(p.lcol + e + 2), c3 = __ldg(p.lcol + e + 3);
+            const float w0 = __ldg(p.val + e), w1 = __ldg(p.val + e + 1), w2 = __ldg(p.val + e + 2), w3 = __ldg(p.val + e + 3);
+            const float4 x0 = stage[c0 * p.SW + v], x1 = stage[c1 * p.SW + v], x2 = stage[c2 * p.SW + v], x3 = stage[c3 * p.SW + v];
+            fma4(acc0, w0, x0);
+            fma4(acc1, w1, x1);
+            fma4(acc0, w2, x2);
+            fma4(acc1, w3, x3);
+        }
+        for (; e < e1; ++e) fma4(acc0, __ldg(p.val + e), stage[(int)__ldg(p.lcol + e) * p.SW + v]);
+        float4 r4;
+        r4.x = p.alpha * (acc0.x + acc1.x);
+        r4.y = p.alpha * (acc0.y + acc1.y);
+        r4.z = p.alpha * (acc0.z + acc1.z);
+        r4.w = p.alpha * (acc0.w + acc1.w);
+        const int64_t idx = (int64_t)row * p.V + s0 + v;
+        if (kHasPrev) {
+            const float4 q = p.prev[idx];
+            r4.x = fmaf(p.beta, q.x, r4.x);
+            r4.y = fmaf(p.beta, q.y, r4.y);
+            r4.z = fmaf(p.beta, q.z, r4.z);
+            r4.w = fmaf(p.beta, q.w, r4.w);
+        }
+        p.out[idx] = r4;
+    }
+}
+
+// ---- block-plan registry: plans are created by the host side once per CSR operand and looked up by the
+// device address of its `col` array (the plan's arrays stay owned by the caller)
+struct BlockPlan { const void* key; const int* blk_ptr; const int* blk_rows; const unsigned short* lcol; int RB, maxd, N; bool live; };
+static std::mutex g_plan_mu;
+static std::vector<BlockPlan> g_plans;
+
+static bool find_plan(const void* col, int N, BlockPlan* out) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (const BlockPlan& bp : g_plans)
+        if (bp.live && bp.key == col && bp.N == N) { *out = bp; return true; }
+    return false;
+}
+
 template <bool kHasPrev>
 __global__ void __launch_bounds__(256)
 spmm_step_scalar_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -141,7 +357,58 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
     if (N == 0 || C == 0) return TGCN_OK;
     TGCN_REQUIRE(in != out, "spmm_step: `in` must not alias `out`");
     const bool vec = (C % 4 == 0) && aligned16(in) && aligned16(out) && (prev == nullptr || aligned16(prev));
-    if (vec) {
+    BlockPlan bp;
+    if (vec && tuning_value(kTuneSpmmStaged) != 0 && find_plan(col, N, &bp)) {
+        const int V = (int)(C / 4);
+        const int SW = V <= 64 ? V : 64;
+        const size_t smem = 16 + (size_t)bp.maxd * SW * 16;
+        if (smem <= 160 * 1024 && ceil_div(V, SW) <= 65535) {
+            StagedParams sp{rowptr, bp.lcol, val, bp.blk_ptr, bp.blk_rows, (const float4*)in, (const float4*)prev, (float4*)out,
+                            N, bp.RB, V, SW, alpha, beta};
+            const dim3 grid((unsigned)ceil_div(N, bp.RB), (unsigned)ceil_div(V, SW));
+            auto kern = prev ? spmm_step_staged_kernel<true> : spmm_step_staged_kernel<false>;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "spmm_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            }
+            kern<<<grid, 256, smem, st>>>(sp);
+            TGCN_LAUNCH_CHECK("spmm_step");
+            return TGCN_OK;
+        }
+    }
+    const int tile_rb = tuning_value(kTuneSpmmTile);
+    const int pipe_bps = tuning_value(kTuneSpmmPipe);      // blocks per SM of the persistent kernel (0 = off)
+    if (vec && pipe_bps > 0 && C / 4 <= 4096) {
+        const int V = (int)(C / 4);
+        int64_t blocks = (int64_t)kNumSMs * pipe_bps;
+        const int64_t need = ceil_div((int64_t)N * V, 256);
+        if (blocks > need) blocks = need;
+        const int rows_per_pass = (int)((blocks * 256) / V);
+        if (rows_per_pass >= 1) {
+            if (prev) spmm_step_pipe_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in,
+                                                                                   (const float4*)prev, (float4*)out, V, alpha, beta, rows_per_pass);
+            else spmm_step_pipe_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr,
+                                                                                (float4*)out, V, alpha, beta, rows_per_pass);
+            TGCN_LAUNCH_CHECK("spmm_step");
+            return TGCN_OK;
+        }
+    }
+    if (vec && tile_rb > 0 && C / 4 >= 8 && ceil_div(C / 4, 8) <= 65535) {
+        const int V = (int)(C / 4);
+        const dim3 grid((unsigned)ceil_div(N, tile_rb), (unsigned)ceil_div(V, 8));
+#define TGCN_SPMM_TILE(RB)                                                                                         \
+        do {                                                                                                       \
+            if (prev) spmm_step_tile_kernel<true, RB><<<grid, RB * 8, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
+                                                                                (const float4*)prev, (float4*)out, V, alpha, beta); \
+            else spmm_step_tile_kernel<false, RB><<<grid, RB * 8, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
+                                                                            (float4*)out, V, alpha, beta);          \
+        } while (0)
+        if (tile_rb == 16) TGCN_SPMM_TILE(16);
+        else if (tile_rb == 64) TGCN_SPMM_TILE(64);
+        else if (tile_rb == 128) TGCN_SPMM_TILE(128);
+        else TGCN_SPMM_TILE(32);
+#undef TGCN_SPMM_TILE
+    } else if (vec) {
         const int V = (int)(C / 4);
         const int64_t total = (int64_t)N * V;
         const unsigned blocks = (unsigned)ceil_div(total, 256);
@@ -200,6 +467,60 @@ basis_to_reference_kernel(const float* __restrict__ stack, float* __restrict__ X
 }  // namespace tgcn
 
 using namespace tgcn;
+
+// Host-side: distinct source rows per block of RB consecutive rows and block-local column ids.
+// blk_ptr_host[nb+1]; blk_rows_host: capacity = nnz (NULL: size query, returns the total); lcol_host[nnz].
+// Returns the total number of distinct (block, source row) pairs, or -1 (bad arguments / a block references
+// more than 65535 distinct rows).  *maxd_host receives the largest per-block count.
+extern "C" int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB,
+                                        int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host) {
+    if (N < 0 || RB < 1 || !rowptr_host) return -1;
+    const int nb = (int)ceil_div(N, RB);
+    int64_t total = 0;
+    int maxd = 0;
+    std::vector<int32_t> tmp;
+    for (int b = 0; b < nb; ++b) {
+        const int r0 = b * RB, r1 = (int)min64((int64_t)N, (int64_t)r0 + RB);
+        const int e0 = rowptr_host[r0], e1 = rowptr_host[r1];
+        tmp.assign(col_host + e0, col_host + e1);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        if (tmp.size() > 65535) return -1;
+        if (blk_ptr_host) blk_ptr_host[b] = (int32_t)total;
+        if (blk_rows_host) std::copy(tmp.begin(), tmp.end(), blk_rows_host + total);
+        if (lcol_host)
+            for (int e = e0; e < e1; ++e)
+                lcol_host[e] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), col_host[e]) - tmp.begin());
+        total += (int64_t)tmp.size();
+        if ((int)tmp.size() > maxd) maxd = (int)tmp.size();
+    }
+    if (blk_ptr_host) blk_ptr_host[nb] = (int32_t)total;
+    if (maxd_host) *maxd_host = maxd;
+    return total;
+}
+
+// Register / drop a block plan for the CSR operand whose column array lives at device address `col_dev`.
+// All arrays are device pointers owned by the caller and must outlive the plan.  Returns a handle >= 0.
+extern "C" int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
+                                    const uint16_t* lcol_dev, int RB, int maxd) {
+    if (!col_dev || !blk_ptr_dev || !blk_rows_dev || !lcol_dev || RB < 1 || maxd < 0 || N < 1) {
+        set_error(TGCN_ERR_INVALID, "tgcn_plan_create: bad arguments");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (size_t i = 0; i < g_plans.size(); ++i)
+        if (!g_plans[i].live) { g_plans[i] = BlockPlan{col_dev, blk_ptr_dev, blk_rows_dev, lcol_dev, RB, maxd, N, true}; return (int64_t)i; }
+    g_plans.push_back(BlockPlan{col_dev, blk_ptr_dev, blk_rows_dev, lcol_dev, RB, maxd, N, true});
+    return (int64_t)g_plans.size() - 1;
+}
+
+extern "C" int tgcn_plan_destroy(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (handle < 0 || handle >= (int64_t)g_plans.size() || !g_plans[handle].live)
+        return set_error(TGCN_ERR_INVALID, "tgcn_plan_destroy: unknown handle %lld", (long long)handle);
+    g_plans[handle].live = false;
+    return TGCN_OK;
+}
 
 extern "C" int tgcn_to_slab(const float* x, float* slab, int Q, int N, int D, void* stream) {
     TGCN_REQUIRE(x && slab, "tgcn_to_slab: null pointer");

@@ -7,6 +7,13 @@ import torch
 from .. import _lib
 
 
+# Row-block staged SpMM (csr.LaplacianCSR.ensure_block_plans): measured on B200 it moves 2.5x less L2 -> SM
+# traffic on the cortical mesh but is not faster than the plain kernel (profiles/r01/spmm_variants.txt), so
+# plans are only built on request (TGCN_SPMM_STAGED=1).
+import os as _os
+_STAGED_SPMM = _os.environ.get("TGCN_SPMM_STAGED", "0") not in ("", "0")
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -58,6 +65,8 @@ class ChebLayerFunction(torch.autograd.Function):
         x = x.contiguous()
         w = weight.contiguous()
         b = None if bias is None else bias.contiguous()
+        if _STAGED_SPMM:
+            plan.ensure_block_plans()    # row-block staging of the SpMM when the row order has locality
         out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
         stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
         fw_bytes = int(lib.tgcn_layer_fwd_workspace(Q, N, D, G, K))
@@ -237,6 +246,8 @@ def cheb_basis(x, plan, K, recursion=_lib.RECURSION_REFERENCE, reference_layout=
     Q, N, D = x.shape
     dev = x.device
     x = x.contiguous()
+    if _STAGED_SPMM:
+        plan.ensure_block_plans()
     stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
     with _DeviceGuard(dev):
         rc = lib.tgcn_cheb_basis(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(stack), Q, D, K,
