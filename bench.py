@@ -35,6 +35,10 @@ WORKLOADS = {
                         classes=6),
     "mesh32k": dict(desc="BASELINE.json configs[2]: cortical-surface mesh (32492 vertices -> 41856 padded), T=30, "
                          "batch 8 per GPU, two TGCN layers + pooling", batch=8, H=30, model="hcp", classes=6),
+    "rgg1m": dict(desc="BASELINE.json configs[3]: synthetic random geometric graph, 1M vertices (mean degree 12, x-sorted), "
+                       "one TGCNCheb_H layer F=64 -> G=64, K=8, Kt=H=3, batch 1; forward + dW/db backward + SGD; graph rows "
+                       "partitioned over the GPUs with a halo exchange before every recursion step (strong scaling)",
+                  batch=1, H=3, model="rgg", classes=0),
     "mnist": dict(desc="BASELINE.json configs[0]: 28x28 8-NN grid, 4 coarsening levels, batch 100, H=12, "
                        "TGCNCheb_H(1,15,K10)->relu->fc10", batch=100, H=12, model="mnist", classes=10),
 }
@@ -303,6 +307,148 @@ def run_b200(args):
         os._exit(0)
 
 
+def run_rgg(args):
+    """Config 4: one large-graph layer, rows partitioned over the ranks (tgcn_b200.parallel.RowPartitionedLayer)."""
+    import torch.distributed as dist
+    from tgcn_b200 import _lib, workloads as wl
+    from tgcn_b200.parallel import RowPartitionedLayer, init_distributed
+    os.environ.pop("NCCL_DEBUG", None)
+    rank, world, local = init_distributed("nccl")
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    cfg = WORKLOADS["rgg1m"]
+    n = args.rgg_n
+    K, H, Fin, G, Q = 8, 3, 64, 64, args.batch or 1
+    D = H * Fin
+    L, _ = wl.random_geometric(n=n, mean_degree=12.0, seed=0)
+    layer = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev)
+    n_own = layer.n_own
+    gen = torch.Generator().manual_seed(0)
+    bound = 1.0 / (Fin * K) ** 0.5
+    W = ((torch.rand(K, D, G, generator=gen) * 2 - 1) * bound).to(dev)
+    bias = ((torch.rand(n, G, generator=gen) * 2 - 1) * bound)[layer.plan.lo:layer.plan.hi].contiguous().to(dev)
+    mW, mb = torch.zeros_like(W), torch.zeros_like(bias)
+    hx = [torch.randn(Q, n_own, D, generator=torch.Generator().manual_seed(100 + rank + 7 * i)).pin_memory() for i in range(2)]
+    x = hx[0].to(dev)
+    loss_dev = torch.zeros((), device=dev)
+    loss_host = torch.zeros((), pin_memory=True)
+    lr, mom = 0.01, 0.5
+    scale = 1.0 / (Q * n * G)
+
+    def step():
+        out = layer.forward(x, W, bias)
+        loss_dev.copy_((out * out).sum() * (0.5 * scale))      # mean-square objective; rank-local part of the loss
+        dW, db = layer.backward(out * scale)
+        mW.mul_(mom).add_(dW); W.add_(mW, alpha=-lr)
+        mb.mul_(mom).add_(db); bias.add_(mb, alpha=-lr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        barrier()
+        for i in range(nsteps):
+            ev[i][0].record()
+            if e2e:
+                x.copy_(hx[i % 2], non_blocking=True)
+            step()
+            if e2e:
+                loss_host.copy_(loss_dev, non_blocking=True)
+            ev[i][1].record()
+            if e2e:
+                ev[i][1].synchronize()
+                _ = float(loss_host)
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    c0 = lib.tgcn_launch_count(); step(); launches = lib.tgcn_launch_count() - c0
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(args.steps, False)
+    ms_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    roof = None
+    if rank == 0:
+        peak, src = _peak()
+        C = Q * D
+        b = layer._buffers(Q)
+
+        def spmm_steps():
+            st = torch.cuda.current_stream().cuda_stream
+            for j in range(1, K):
+                lib.tgcn_spmm_step(layer.rowptr.data_ptr(), layer.col.data_ptr(), layer.val.data_ptr(), n_own,
+                                   b["stack"][j - 1].data_ptr(), None, b["stack"][j].data_ptr(), C, 1.0, 0.0, st)
+        per = _time_graph(spmm_steps, 5, None) / (K - 1)
+        nbytes = 2 * 4 * n_own * C + 8 * int(layer.col.numel()) + 4 * (n_own + 1)
+        ach = nbytes / (per * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "spmm_step kernel (recursion step on this rank's rows, 2S+E bytes; slabs exceed L2)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": int(nbytes),
+                "us_per_launch": per * 1e3, "peak_source": src}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_rgg_throughput(n, K, H, Fin, G, budget_s=args.cpu_budget)
+    if rank == 0:
+        ms_step = ms / args.steps
+        line = {"metric": METRIC, "value": Q / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "rgg1m", "description": cfg["desc"], "vertices": n, "nnz": int(L.nnz), "K": K, "H": H,
+                           "F": Fin, "G": G, "batch": Q, "parallelism": "rows/%d" % world, "halo_rows_rank0": int(layer.plan.n_halo),
+                           "l2": "working set exceeds L2 (768 MB slabs at 1 GPU)", "cuda_graph": False},
+                "e2e": {"value": Q / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4),
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches), "clocks": clocks,
+                "roofline": roof, "cpu_baseline": cpu, "final_loss": float(loss_host)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
+def cpu_rgg_throughput(n, K, H, Fin, G, budget_s=20.0, sample_n=50000):
+    """The reference's CPU path (gcn_matmul.py slab form with a torch.sparse_csr L~, oracle port) on a bounded
+    sample: the first `sample_n` vertices of the x-sorted graph (a strip); the rate is scaled by sample_n / n."""
+    from oracle import model_torch
+    from tgcn_b200 import workloads as wl
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ls, _ = wl.random_geometric(n=sample_n, mean_degree=12.0, seed=0)
+    coo = Ls.tocoo()
+    Lt = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), coo.shape).coalesce().to_sparse_csr()
+    torch.manual_seed(0)
+    lay = model_torch._Conv(Lt, (K, H, Fin, G), (1, sample_n, G), Fin * K)
+    x = torch.randn(1, sample_n, H, Fin)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        lay.zero_grad()
+        out = lay(x)
+        (out * out).mean().backward()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s or len(times) >= 10:
+            break
+    med = float(np.median(times[1:] or times))
+    return {"value": (sample_n / n) / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d fwd+bwd steps of the torch-CPU port (sparse_csr slab path) on the first %d of %d vertices, batch 1, "
+                      "%d threads, median %.2f s/step; value scaled by %d/%d" % (len(times), sample_n, n, cores, med, sample_n, n),
+            "ms_per_step": med * 1e3 * (n / sample_n)}
+
+
 def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -472,9 +618,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--rgg-n", type=int, default=1_000_000, help="vertices of the rgg1m workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "rgg1m":
+        run_rgg(args)
     else:
         run_b200(args)
 

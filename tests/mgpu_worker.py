@@ -16,8 +16,8 @@ sys.path.insert(0, ROOT)
 
 from tgcn_b200 import _lib, workloads as wl  # noqa: E402
 from tgcn_b200.csr import build_csr  # noqa: E402
-from tgcn_b200.parallel import (FlatGradients, RowPartition, broadcast_parameters, halo_exchange,  # noqa: E402
-                                init_distributed, shard_range)
+from tgcn_b200.parallel import (FlatGradients, RowPartition, RowPartitionedLayer, broadcast_parameters,  # noqa: E402
+                                halo_exchange, init_distributed, shard_range)
 
 
 def check_dp(rank, world, dev):
@@ -77,15 +77,39 @@ def check_halo(rank, world, dev):
     return plan.n_halo
 
 
+def check_partitioned_layer(rank, world, dev):
+    """C. row-partitioned layer (forward, dW, db) == the same layer on one GPU holding the whole graph."""
+    L, _ = wl.random_geometric(n=30000, mean_degree=10.0, seed=2)
+    n = L.shape[0]
+    Q, D, G, K = 2, 24, 16, 5
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(Q, n, D, generator=g).to(dev)
+    W = (torch.randn(K, D, G, generator=g) * 0.2).to(dev)
+    bias = torch.randn(n, G, generator=g).to(dev)
+    dout = torch.randn(Q, n, G, generator=g).to(dev)
+    whole = RowPartitionedLayer(L, K, D, G, rank=0, world=1, device=dev)
+    ref_out = whole.forward(x, W, bias).clone()
+    ref_dW, ref_db = whole.backward(dout)
+    part = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev)
+    lo, hi = part.plan.lo, part.plan.hi
+    out = part.forward(x[:, lo:hi].contiguous(), W, bias[lo:hi].contiguous())
+    assert float((out - ref_out[:, lo:hi]).abs().max() / ref_out.abs().max()) < 1e-5
+    dW, db = part.backward(dout[:, lo:hi].contiguous())
+    assert float((dW - ref_dW).abs().max() / ref_dW.abs().max()) < 1e-4
+    assert float((db - ref_db[lo:hi]).abs().max() / ref_db.abs().max()) < 1e-5
+    return part.plan.n_halo
+
+
 def main():
     rank, world, local = init_distributed("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     e = check_dp(rank, world, dev)
     h = check_halo(rank, world, dev)
+    h2 = check_partitioned_layer(rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d" % (world, e, h))
+        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d" % (world, e, h, h2))
     dist.destroy_process_group()
 
 

@@ -255,3 +255,21 @@ def test_resident_refuses_what_does_not_fit():
     lay = Gm.TGCNCheb_H(L, 1, 8, 3, 30, engine="resident").cuda()
     with pytest.raises(RuntimeError, match="resident"):
         lay(torch.zeros(1, n, 30, device="cuda"))
+
+
+@pytest.mark.parametrize("N", [20, 4, 12])
+def test_cluster_split_with_an_empty_trailing_rank(N):
+    """Q small enough for a 4-CTA cluster while ceil(row_groups / 4) leaves the last rank without rows
+    (N = 20: 5 row groups -> 2, 2, 1, 0)."""
+    shape = ("TGCNCheb_H", 2, N, 5, 1, 4, 3, 0.4)
+    lay, L, x, kind = _build(shape, "chebyshev", "resident", seed=0)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    out = lay(xt)
+    dout = np.random.default_rng(1).standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.tensor(dout, device="cuda"))
+    W, b = lay.weight.detach().cpu().numpy(), lay.bias.detach().cpu().numpy()
+    ref = layers_np.layer_forward(L, x, W, b, kind=kind, recursion="chebyshev")
+    dW, db, dx = layers_np.layer_backward(L, x, W, dout, b.shape, kind=kind, recursion="chebyshev")
+    assert rel_err(out.detach().cpu().numpy(), ref) < TOL
+    assert rel_err(lay.weight.grad.cpu().numpy(), dW) < TOL
+    assert rel_err(xt.grad.cpu().numpy(), dx) < TOL

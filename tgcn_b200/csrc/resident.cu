@@ -197,7 +197,7 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     const int q = blockIdx.x / CL, c = blockIdx.x - q * CL;    // 1-D clusters: c is the rank in the cluster
     const int N = p.N, NP = p.NP, D = p.D, DP = p.DP, V = p.V, G = p.G, GG = p.GG, K = p.K;
     const int slab = NP * DP;                                  // floats per P buffer
-    const int rg0 = c * p.rg_per, rg1 = min(NP / 4, rg0 + p.rg_per);
+    const int rg0 = min(c * p.rg_per, NP / 4), rg1 = min(NP / 4, rg0 + p.rg_per);   // a trailing rank may own no rows
     const int row0 = rg0 * 4, row1 = min(N, rg1 * 4);          // rows this CTA computes
     const int wslab = DP * p.GP;
 

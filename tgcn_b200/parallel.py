@@ -200,3 +200,122 @@ def halo_exchange(slab_own, plan, halo_out=None, group=None):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return halo_out
+
+
+class RowPartitionedLayer:
+    """One TGCNCheb_H-style layer on a graph whose ROWS are partitioned over the ranks (SURVEY.md section 8e,
+    config 4): forward and weight/bias backward, driven straight through the C-ABI (no autograd).
+
+    Each rank keeps its rows of every basis slab in an EXTENDED slab `[n_own + n_halo, C]`: the owned rows
+    followed by the halo rows other ranks send before each recursion step (`halo_exchange`).  The contraction
+    and the weight gradient run on the extended slabs (halo rows of dOut are zero, so they add nothing to dW);
+    dW is summed over the ranks with one allreduce.  Per-row results are bit-identical to the unpartitioned
+    layer because the local CSR keeps each row's entry order.  Input gradients are not produced (first-layer
+    use, as in the reference models where the input does not require grad)."""
+
+    def __init__(self, L_csr, K, D, G, rank=0, world=1, device=None, recursion=0, engine=0, group=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.K, self.D, self.G = K, D, G
+        self.rank, self.world, self.group = rank, world, group
+        self.recursion, self.engine = recursion, engine
+        self.device = torch.device(device if device is not None else "cuda")
+        self.plan = RowPartition(L_csr, rank, world)
+        if world > 1:
+            self.plan.build_send_lists(group=group)
+        else:
+            self.plan.send_idx = [None]
+        pl = self.plan
+        self.n_own, self.n_ext = pl.n_own, pl.n_own + pl.n_halo
+        dev = self.device
+        self.rowptr = torch.tensor(pl.rowptr, device=dev)
+        self.col = torch.tensor(pl.col, device=dev)
+        self.val = torch.tensor(pl.val, device=dev)
+        self.send_idx_dev = [None if (i is None or len(i) == 0) else torch.as_tensor(i, device=dev) for i in pl.send_idx]
+        self._bufs = {}
+
+    def _buffers(self, Q):
+        b = self._bufs.get(Q)
+        if b is None:
+            lib, K, D, G, n = self.lib, self.K, self.D, self.G, self.n_ext
+            dev = self.device
+            C = Q * D
+            f32 = dict(dtype=torch.float32, device=dev)
+            b = dict(stack=torch.zeros((K, n, C), **f32), out=torch.empty((Q, n, G), **f32),
+                     dout=torch.zeros((Q, n, G), **f32), bias=torch.zeros((n, G), **f32), xext=torch.zeros((Q, n, D), **f32),
+                     wmix=torch.empty((K, D, G), **f32), dwmix=torch.empty((K, D, G), **f32),
+                     scr=torch.empty(max(int(lib.tgcn_contract_fwd_scratch(Q, n, D, G, K)), 16) // 4 + 64, **f32),
+                     ws=torch.empty(max(int(lib.tgcn_layer_bwd_workspace(Q, n, D, G, K)), 16) // 4 + 64, **f32),
+                     db=torch.empty((n, G), **f32))
+            self._bufs[Q] = b
+        return b
+
+    def _halo(self, slab_ext):
+        if self.world == 1 or self.plan.n_halo == 0:
+            return
+        pl = self.plan
+        ops, keep, off = [], [], 0
+        for q in range(pl.world):
+            cnt = pl.recv_cnt[q]
+            if q != pl.rank and cnt:
+                ops.append(dist.P2POp(dist.irecv, slab_ext[self.n_own + off:self.n_own + off + cnt], q, group=self.group))
+            off += cnt
+        for q in range(pl.world):
+            idx = self.send_idx_dev[q]
+            if q != pl.rank and idx is not None:
+                buf = slab_ext[:self.n_own].index_select(0, idx)
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def forward(self, x_own, weight, bias_own):
+        """x_own [Q, n_own, D], weight [K, D, G], bias_own [n_own, G] or None -> out [Q, n_own, G] (a view)."""
+        from . import _lib
+        lib = self.lib
+        Q = x_own.shape[0]
+        b = self._buffers(Q)
+        K, D, G, n = self.K, self.D, self.G, self.n_ext
+        C = Q * D
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        b["xext"][:, :self.n_own] = x_own
+        _lib.check(lib.tgcn_to_slab(b["xext"].data_ptr(), b["stack"][0].data_ptr(), Q, n, D, st), "tgcn_to_slab")
+        for j in range(1, K):
+            self._halo(b["stack"][j - 1])
+            prev = None
+            alpha, beta = 1.0, 0.0
+            if self.recursion == 1 and j >= 2:
+                prev, alpha, beta = b["stack"][j - 2].data_ptr(), 2.0, -1.0
+            _lib.check(lib.tgcn_spmm_step(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), self.n_own,
+                                          b["stack"][j - 1].data_ptr(), prev, b["stack"][j].data_ptr(), C, alpha, beta, st),
+                       "tgcn_spmm_step")
+        _lib.check(lib.tgcn_mix_weights(weight.data_ptr(), b["wmix"].data_ptr(), K, D * G, self.recursion, 0, st), "tgcn_mix_weights")
+        mode = 0
+        if bias_own is not None:
+            b["bias"][:self.n_own] = bias_own
+            mode = 1
+        _lib.check(lib.tgcn_contract_fwd(b["stack"].data_ptr(), b["wmix"].data_ptr(), b["bias"].data_ptr() if mode else None, mode,
+                                         b["out"].data_ptr(), b["scr"].data_ptr(), Q, n, D, G, K, self.engine, st), "tgcn_contract_fwd")
+        return b["out"][:, :self.n_own]
+
+    def backward(self, dout_own, want_bias=True):
+        """dout_own [Q, n_own, G] -> (dW [K, D, G] summed over the ranks, db_own [n_own, G] or None)."""
+        from . import _lib
+        lib = self.lib
+        Q = dout_own.shape[0]
+        b = self._buffers(Q)
+        K, D, G, n = self.K, self.D, self.G, self.n_ext
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        b["dout"][:, :self.n_own] = dout_own
+        _lib.check(lib.tgcn_contract_bwd_w(b["stack"].data_ptr(), b["dout"].data_ptr(), b["dwmix"].data_ptr(), b["ws"].data_ptr(),
+                                           Q, n, D, G, K, self.engine, st), "tgcn_contract_bwd_w")
+        dW = torch.empty((K, D, G), dtype=torch.float32, device=self.device)
+        _lib.check(lib.tgcn_mix_weights(b["dwmix"].data_ptr(), dW.data_ptr(), K, D * G, self.recursion, 1, st), "tgcn_mix_weights")
+        db = None
+        if want_bias:
+            _lib.check(lib.tgcn_bias_grad(b["dout"].data_ptr(), b["db"].data_ptr(), b["ws"].data_ptr(), Q, n, G, 1, st), "tgcn_bias_grad")
+            db = b["db"][:self.n_own]
+        if self.world > 1:
+            dist.all_reduce(dW, op=dist.ReduceOp.SUM, group=self.group)
+        return dW, db
