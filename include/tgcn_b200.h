@@ -205,6 +205,23 @@ int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, in
                             float* dW, float* db, int bias_mode, float* dx, void* workspace,
                             int Q, int D, int G, int K, int recursion, void* stream);
 
+/* ---- fused classifier head -------------------------------------------------- */
+/* logp[Q,C] = log_softmax(fc2(relu(batchnorm(fc1(x))))) with x[Q,I], W1[Hd,I], b1[Hd], gamma/beta[Hd] (NULL: 1/0),
+ * W2[C,Hd], b2[C]; replaces fc1 / dense1_bn / relu / fc2 / log_softmax of pytorch_hcp_tgcn.py:143-155 (about ten
+ * ATen launches) by two launches.  training != 0: batch statistics (biased variance) normalise and the running
+ * estimates are updated like torch.nn.BatchNorm1d (momentum, unbiased variance); else the running estimates are
+ * used.  act[Q,Hd] (post-ReLU), xhat[Q,Hd] and invstd[Hd] are saved for the backward.  C <= 32. */
+int tgcn_head_fwd(const float* x, const float* W1, const float* b1, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, int training,
+                  const float* W2, const float* b2, float* act, float* xhat, float* invstd, float* logp,
+                  int Q, int I, int Hd, int C, void* stream);
+/* Backward of tgcn_head_fwd (training statistics): gradients of every operand from dlogp[Q,C]; dx may be NULL;
+ * dh_scratch holds Q*Hd floats.  Two launches. */
+int tgcn_head_bwd(const float* dlogp, const float* logp, const float* act, const float* xhat, const float* invstd,
+                  const float* x, const float* W1, const float* gamma, const float* W2,
+                  float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2,
+                  float* dh_scratch, int Q, int I, int Hd, int C, void* stream);
+
 /* ---- host-side graph preprocessing (CPU, no device work) ----------------------------------- */
 /* One level of greedy heavy-edge (Graclus-normalised) matching: replaces the pure-Python loop
  * `metis_one_level` (gcn/coarsening.py:119-165) bit-exactly.  rr/cc/vv: COO triplets sorted by

@@ -58,6 +58,8 @@ SIGNATURES = {
     "tgcn_resident_layer_fwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "tgcn_resident_layer_bwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p,
                                      _i, _i, _i, _i, _i, _p]),
+    "tgcn_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
 }

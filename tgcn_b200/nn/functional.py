@@ -162,6 +162,7 @@ class ResidentChebFunction(torch.autograd.Function):
         if pool_p:
             ctx.save_for_backward(stack, wimg, y, idx)
             ctx.mark_non_differentiable(idx)
+            ctx.set_materialize_grads(False)      # no zero tensor for the (non-differentiable) index output
             return y, idx
         ctx.save_for_backward(stack, wimg)
         return out
@@ -169,6 +170,8 @@ class ResidentChebFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad, _didx=None):
         lib = _lib.load()
+        if grad is None:
+            return (None,) * 8
         Q, N, D, G, K = ctx.dims
         bm, recursion, pool_p, relu = ctx.cfg
         plan = ctx.plan
@@ -220,11 +223,14 @@ class PoolFunction(torch.autograd.Function):
         else:
             ctx.save_for_backward(idx)
         ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
         return y, idx
 
     @staticmethod
-    def backward(ctx, dy, _didx):
+    def backward(ctx, dy, _didx=None):
         lib = _lib.load()
+        if dy is None:
+            return None, None, None
         saved = ctx.saved_tensors
         idx = saved[0]
         x = saved[1] if ctx.relu else None

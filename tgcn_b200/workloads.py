@@ -112,7 +112,8 @@ class NetTGCN_HCP(nn.Module):
     -> fc(n_classes) -> log_softmax   (pytorch_hcp_tgcn.py:93-155; dropout layers omitted: rate-0
     equivalent, they are elementwise and outside the measured path)."""
 
-    def __init__(self, L, horizon=15, K=10, g1=32, g2=64, hidden=200, n_classes=6, fused_relu_pool=True, **layer_kw):
+    def __init__(self, L, horizon=15, K=10, g1=32, g2=64, hidden=200, n_classes=6, fused_relu_pool=True, fused_head=True,
+                 **layer_kw):
         super().__init__()
         self.tgcn1 = TGCNCheb_H(L[0], 1, g1, K, horizon, **layer_kw)
         self.gcn2 = GCNCheb(L[2], g1, g2, K, **layer_kw)
@@ -121,6 +122,7 @@ class NetTGCN_HCP(nn.Module):
         self.dense1_bn = nn.BatchNorm1d(hidden)
         self.fc2 = nn.Linear(hidden, n_classes)
         self.fused = fused_relu_pool
+        self.fused_head = fused_head
 
     def forward(self, x):
         if self.fused:
@@ -129,6 +131,9 @@ class NetTGCN_HCP(nn.Module):
             x = gcn_pool_4(F.relu(self.tgcn1(x)))
             x = gcn_pool_4(F.relu(self.gcn2(x)))
         x = x.reshape(x.shape[0], -1)
+        if self.fused_head and x.is_cuda and (self.training and x.shape[0] > 1 or not self.training):
+            from .nn.head import fused_head
+            return fused_head(x, self.fc1, self.dense1_bn, self.fc2)
         x = F.relu(self.dense1_bn(self.fc1(x)))
         return F.log_softmax(self.fc2(x), dim=1)
 
