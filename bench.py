@@ -519,9 +519,13 @@ def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
         bytes_per_launch = (3 * K - 4) * S + (K - 1) * E + 4 * Q * N * G + 4 * K * D * G + 4 * N * G
         compulsory = 4 * Q * N * D + 5 * Q * (N // 4) * G + stack.numel() * 4 + 4 * K * D * G + 4 * N * G + E
         achieved = bytes_per_launch / (ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the hcp360 layer-1 shape from the round's
+        # `ncu --set full` capture (profiles/r01/resident_kernels_ncu.txt): the saved basis is still in L2 when the
+        # kernel ends, so DRAM sees little more than the input read
+        traffic = 1657088 + 49664 if (Q, N, D, G, K) == (64, 384, 15, 32, 10) else None
         return {"bound": "hbm", "kernel": "resident_fwd_kernel (layer 1: recursion + contraction + bias + ReLU + max-pool in one "
                                           "launch; timed together with its weight-image prologue kernel)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "bytes_per_launch": int(bytes_per_launch), "bytes_formula": "SURVEY 8d B_fwd = (3K-4)S+(K-1)E+4QNG+4KHFG+4NG",
                 "compulsory_bytes": int(compulsory), "us_per_launch": ms * 1e3, "peak_source": src}
     stack = torch.randn(K, N, C, device=dev)
