@@ -273,3 +273,26 @@ def test_cluster_split_with_an_empty_trailing_rank(N):
     assert rel_err(out.detach().cpu().numpy(), ref) < TOL
     assert rel_err(lay.weight.grad.cpu().numpy(), dW) < TOL
     assert rel_err(xt.grad.cpu().numpy(), dx) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES[:2] + SHAPES[4:5] + SHAPES[6:7])
+def test_tcgen05_and_ffma_contraction_of_the_resident_forward_agree(shape):
+    """RES_TC tuning key: the contraction of the resident forward kernel on tcgen05 (3xTF32, TMEM accumulators)
+    against the same kernel with the fp32 FFMA contraction, and both against the float64 oracle."""
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    lay, L, x, kind = _build(shape, "reference", "resident", seed=0)
+    xt = torch.tensor(x, device="cuda")
+    outs = {}
+    try:
+        for tc in (1, 0):
+            assert lib.tgcn_set_tuning(b"RES_TC", tc) == 0
+            with torch.no_grad():
+                outs[tc] = lay(xt).cpu().numpy()
+    finally:
+        lib.tgcn_set_tuning(b"RES_TC", -1)
+    W, b = lay.weight.detach().cpu().numpy(), lay.bias.detach().cpu().numpy()
+    ref = layers_np.layer_forward(L, x, W, b, kind=kind, recursion="reference")
+    assert rel_err(outs[0], ref) < 2e-6
+    assert rel_err(outs[1], ref) < 2e-5
+    assert rel_err(outs[1], outs[0]) < 2e-5

@@ -18,9 +18,9 @@ int set_error(int code, const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static const char* const kTuneNames[kTuneCount] = {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED"};
-static const int kTuneDefaults[kTuneCount] = {0, 0, 1};   // SPMM_STAGED applies only to operands with a registered plan
-static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}};
+static const char* const kTuneNames[kTuneCount] = {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC"};
+static const int kTuneDefaults[kTuneCount] = {0, 0, 1, 0};   // SPMM_STAGED applies only to operands with a registered plan
+static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}};
 
 int tuning_value(int key) {
     int v = g_tune[key].load(std::memory_order_relaxed);
@@ -35,8 +35,8 @@ int tuning_value(int key) {
 }
 }  // namespace tgcn
 
-// Select a kernel variant at run time (tests, sweeps): key in {"SPMM_TILE", "SPMM_PIPE"}; returns 0, or -1 for an
-// unknown key.  SPMM_PIPE = blocks per SM of the persistent pipelined SpMM kernel (0: one-thread-per-float4 kernel);
+// Select a kernel variant at run time (tests, sweeps): key in {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC"};
+// returns 0, or -1 for an unknown key.  RES_TC = 1: contraction of the resident forward kernel on tcgen05 (3xTF32).  SPMM_PIPE = blocks per SM of the persistent pipelined SpMM kernel (0: one-thread-per-float4 kernel);
 // SPMM_TILE = rows per block of the row-tiled SpMM kernel (0: off).
 extern "C" int tgcn_set_tuning(const char* key, int value) {
     for (int i = 0; i < tgcn::kTuneCount; ++i)

@@ -38,6 +38,7 @@ constexpr int kRingStages = 3;
 
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int round_up2(int v) { return (v + 1) & ~1; }
+__host__ __device__ inline int round_up16(int v) { return (v + 15) & ~15; }
 
 __device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) {
     acc.x = fmaf(w, x.x, acc.x);
@@ -52,11 +53,13 @@ __device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) {
 // recursion) and its transpose Wt[j][g][d] ([K][GP][DP]) for the dx recursion.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-resident_prep_kernel(const float* __restrict__ W, float* __restrict__ Wm, float* __restrict__ Wt, int K, int D, int G,
-                     int DP, int GP, int recursion) {
+resident_prep_kernel(const float* __restrict__ W, float* __restrict__ Wm, float* __restrict__ Wt, uint8_t* __restrict__ Wtc,
+                     int K, int D, int G, int DP, int GP, int GP16, int recursion) {
+    // one thread per (d, g) of the padded 32 x GP16 tile the tensor-core image covers
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= DP * GP) return;
-    const int d = i / GP, g = i - d * GP;
+    const int rows_d = DP > 32 ? DP : 32;
+    if (i >= rows_d * GP16) return;
+    const int d = i / GP16, g = i - d * GP16;
     const bool valid = d < D && g < G;
     float w[kResMaxK];
 #pragma unroll
@@ -77,8 +80,18 @@ resident_prep_kernel(const float* __restrict__ W, float* __restrict__ Wm, float*
             }
             m = (float)s;
         }
-        Wm[((int64_t)j * DP + d) * GP + g] = m;
-        Wt[((int64_t)j * GP + g) * DP + d] = m;
+        if (d < DP && g < GP) {
+            Wm[((int64_t)j * DP + d) * GP + g] = m;
+            Wt[((int64_t)j * GP + g) * DP + d] = m;
+        }
+        if (Wtc && d < 32) {
+            // K-major B operand of the contraction: rows = g, 32 fp32 of d per 128-byte row, SWIZZLE_128B; hi then lo
+            uint8_t* base = Wtc + (int64_t)j * 2 * GP16 * kRowBytes;
+            const uint32_t off = sw128_offset((uint32_t)g, (uint32_t)d);
+            const float h = tf32_hi(m);
+            *reinterpret_cast<float*>(base + off) = h;
+            *reinterpret_cast<float*>(base + (int64_t)GP16 * kRowBytes + off) = m - h;
+        }
     }
 }
 
@@ -156,6 +169,7 @@ struct ResFwdParams {
     const int2* rowinfo; const int2* entries;   // packed CSR of L~
     const float* x;        // [Q,N,D]
     const float* Wm;       // [K][DP][GP] mixed, padded weights (resident_prep_kernel)
+    const uint8_t* Wtc;    // [K][hi|lo][GP16][128 B] tensor-core image of the same weights (kTC)
     const float* bias;     // [N,G] / [G] / null
     float* out;            // [Q,N,G] or null
     float* y;              // [Q,N/p,G] or null (fused pool)
@@ -164,14 +178,23 @@ struct ResFwdParams {
     int N, NP, E, D, DP, V, G, GP, GG, K;
     int bias_mode, recursion, pool_p, relu;
     int CL, rg_per;        // CTAs per sample (cluster size) and row groups (of 4 rows) per CTA
+    int GP16, MT;          // kTC: padded filter count of the MMA and number of 128-row tiles of this CTA's rows
 };
 
-struct ResSmemFwd { size_t bars, P, W, csr, rowinfo, total; };
+struct ResSmemFwd { size_t aimg, wimg, bars, P, W, csr, rowinfo, total; };
 
-static ResSmemFwd res_fwd_smem(int N, int64_t E, int DP, int GP, int K, bool csr_smem, bool w_smem) {
+constexpr uint32_t kTcTile = 128 * 128;      // one 128-row x 32-fp32 operand tile
+
+static ResSmemFwd res_fwd_smem(int N, int64_t E, int DP, int GP, int K, bool csr_smem, bool w_smem, int tc_tiles = 0,
+                               int GP16 = 0) {
     ResSmemFwd s{};
     const int NP = round_up4(N);
     size_t o = 0;
+    if (tc_tiles > 0) {       // 1024-byte aligned operand images first (the kernel aligns its window, +1024 slack)
+        s.aimg = o;    o += (size_t)tc_tiles * 2 * kTcTile;
+        s.wimg = o;    o += (size_t)2 * 2 * GP16 * kRowBytes;
+        o += 1024;
+    }
     s.bars = o;    o += 64;
     s.P = o;       o += sizeof(float) * 2 * (size_t)NP * DP;
     s.W = o;       o += w_smem ? sizeof(float) * (size_t)K * DP * GP : 0;
@@ -181,11 +204,28 @@ static ResSmemFwd res_fwd_smem(int N, int64_t E, int DP, int GP, int K, bool csr
     return s;
 }
 
-template <int THREADS, int TPT, bool kCsrSmem, bool kWSmem>
+// tcgen05 path of the contraction (kTC): the SpMM threads also write the hi/lo TF32 images of their new rows into a
+// SWIZZLE_128B operand tile; one thread issues, per recursion step, 3 MMAs (lo*hi, hi*lo, hi*hi: 3xTF32) per
+// 8-wide k-step and 128-row tile against the step's weight image (bulk-copied, double buffered); the layer output
+// accumulates in TMEM across all K steps while the next SpMM step runs; the epilogue reads it back with tcgen05.ld.
+__device__ __forceinline__ void store_image4(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& r) {
+    float4 h, l;
+    h.x = tf32_hi(r.x); h.y = tf32_hi(r.y); h.z = tf32_hi(r.z); h.w = tf32_hi(r.w);
+    l.x = r.x - h.x; l.y = r.y - h.y; l.z = r.z - h.z; l.w = r.w - h.w;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+template <int THREADS, int TPT, bool kCsrSmem, bool kWSmem, bool kTC>
 __global__ void __launch_bounds__(THREADS, 1)
 resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);     // [0] prologue loads, [1],[2] peer rows
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
+    if (kTC) { const uint32_t a = smem_u32(smem_raw); smem = smem_raw + (((a + 1023u) & ~1023u) - a); }
+    uint8_t* aimg = smem + lay.aimg;                                   // [MT][hi 16 KB | lo 16 KB]
+    uint8_t* wimg = smem + lay.wimg;                                   // 2 stages x [hi | lo] x GP16 x 128 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);     // [0] prologue loads, [1],[2] peer rows,
+                                                                       // [3],[4] weight image stages, [5] MMAs done
     float* Pbuf = reinterpret_cast<float*>(smem + lay.P);
     float* Wsm = reinterpret_cast<float*>(smem + lay.W);
     int2* csr_s = reinterpret_cast<int2*>(smem + lay.csr);
@@ -201,11 +241,29 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     const int row0 = rg0 * 4, row1 = min(N, rg1 * 4);          // rows this CTA computes
     const int wslab = DP * p.GP;
 
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[6]);
+    const uint32_t wstage = 2u * (uint32_t)p.GP16 * kRowBytes;        // one weight image: hi + lo
     if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
+    uint32_t tmem_acc = 0;
+    if (kTC) {
+        if (tid < 32) tmem_alloc(tmem_slot, tmem_cols_pow2((uint32_t)(p.MT * p.GP16)));
+        tcgen05_fence_before();
+    }
     __syncthreads();
+    if (kTC) {
+        tcgen05_fence_after();
+        tmem_acc = *tmem_slot;
+        // rows beyond this CTA's share and the k-padding columns of the A image must be finite: zero it once
+        float4* z = reinterpret_cast<float4*>(aimg);
+        for (int i = tid; i < p.MT * 2 * (int)(kTcTile / 16); i += T) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[3], wstage);
+            bulk_g2s(wimg, p.Wtc, wstage, &bars[3]);
+        }
+    }
     if (tid == 0) {   // operands that are used as they are: bulk copies straight into shared memory
         const uint32_t b_ri = (uint32_t)sizeof(int2) * (uint32_t)round_up2(N);
         const uint32_t b_csr = kCsrSmem ? (uint32_t)sizeof(int2) * (uint32_t)p.E : 0u;
@@ -249,12 +307,18 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
             }
         }
         __syncthreads();
-        if (stq) {
+        if (stq || kTC) {
             const float4* P4 = reinterpret_cast<const float4*>(Pbuf);
             float4* st4 = reinterpret_cast<float4*>(stq);
             for (int i = row0 * V + tid; i < rg1 * 4 * V; i += T) {
                 const int n = i / V, v = i - n * V;
-                st4[(n * K) * V + v] = P4[i];
+                const float4 r = P4[i];
+                if (stq) st4[(n * K) * V + v] = r;
+                if (kTC) {
+                    const uint32_t rl = (uint32_t)(n - row0);
+                    uint8_t* tile = aimg + (size_t)(rl >> 7) * 2 * kTcTile;
+                    store_image4(tile, tile + kTcTile, sw128_offset(rl & 127u, (uint32_t)(4 * v)), r);
+                }
             }
         }
     }
@@ -277,17 +341,52 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[s][r] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    auto issue_mma = [&](int j) {      // one thread: this step's 3xTF32 MMAs for every 128-row tile, then the commit
+        mbar_wait(&bars[3 + (j & 1)], (uint32_t)((j >> 1) & 1));      // weight image of step j has landed
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_tf32(128u, (uint32_t)p.GP16, 0u, 0u);
+        const uint8_t* wst = wimg + (size_t)(j & 1) * wstage;
+        const uint64_t dbh = make_desc_kmajor(smem_u32(wst)), dbl = make_desc_kmajor(smem_u32(wst + (size_t)p.GP16 * kRowBytes));
+        const int nks = (DP + 7) >> 3;
+        for (int mt = 0; mt < p.MT; ++mt) {
+            const uint8_t* tile = aimg + (size_t)mt * 2 * kTcTile;
+            const uint64_t dah = make_desc_kmajor(smem_u32(tile)), dal = make_desc_kmajor(smem_u32(tile + kTcTile));
+            const uint32_t acc_col = tmem_acc + (uint32_t)(mt * p.GP16);
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);          // 8 fp32 = 32 bytes along K inside the swizzle row
+                umma_tf32(acc_col, dal + adv, dbh + adv, idesc, (j | ks) ? 1u : 0u);
+                umma_tf32(acc_col, dah + adv, dbl + adv, idesc, 1u);
+                umma_tf32(acc_col, dah + adv, dbh + adv, idesc, 1u);
+            }
+        }
+        umma_commit(&bars[5]);
+        if (j + 1 < K) {   // next step's weight image into the other stage (its last reader, MMA j-1, has completed)
+            mbar_arrive_expect_tx(&bars[3 + ((j + 1) & 1)], wstage);
+            bulk_g2s(wimg + (size_t)((j + 1) & 1) * wstage, p.Wtc + (size_t)(j + 1) * wstage, wstage, &bars[3 + ((j + 1) & 1)]);
+        }
+    };
+    if (kTC) {
+        fence_proxy_async_smem();          // the image stores above (generic proxy) -> visible to the tensor core
+        __syncthreads();
+    }
+
     for (int j = 0; j < K; ++j) {
         float* Pcur = Pbuf + (j & 1) * slab;
         if (j > 0) {
             const int b = j & 1;                                  // peer rows of step j are counted on bars[1 + b]
-            if (CL > 1 && tid == 0) mbar_arrive_expect_tx(&bars[1 + b], rx_bytes);
+            if (CL > 1) {
+                if (j > 1) mbar_wait(&bars[1 + (b ^ 1)], (uint32_t)(((j - 2) >> 1) & 1));   // peers' rows of P_{j-1}
+                if (tid == 0) mbar_arrive_expect_tx(&bars[1 + b], rx_bytes);
+            }
             const float4* in4 = reinterpret_cast<const float4*>(Pbuf + ((j - 1) & 1) * slab);
             float4* out4 = reinterpret_cast<float4*>(Pcur);
             float4* st4 = p.stack ? reinterpret_cast<float4*>(p.stack + (int64_t)q * NP * K * DP) + j * V : nullptr;
             const bool cheb = (p.recursion == TGCN_RECURSION_CHEBYSHEV) && j >= 2;
             const uint32_t boff = (uint32_t)(b * slab) * 4u;
-            for (int i = row0 * V + tid; i < row1 * V; i += T) {
+            bool img_free = false;
+            // kTC: the last warp only issues MMAs, so the issue never delays a warp that also owns rows
+            const int TW = kTC ? T - 32 : T;
+            for (int i = row0 * V + tid; i < row1 * V && tid < TW; i += TW) {
                 const int n = i / V, v = i - n * V;
                 float4 r = gather_row<kCsrSmem>(ent, rowinfo_s[n], in4, V, v);
                 if (cheb) {   // T_j = 2 L~ T_{j-1} - T_{j-2}; T_{j-2} is what the output buffer still holds
@@ -305,9 +404,24 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
                     }
                 }
                 if (st4) st4[(n * K) * V + v] = r;
+                if (kTC) {
+                    if (!img_free) {   // MMAs of step j-1 have drained the image: one poller per warp
+                        const unsigned grp = __activemask();          // lanes that arrived together
+                        if ((tid & 31) == __ffs(grp) - 1) mbar_wait(&bars[5], (uint32_t)((j - 1) & 1));
+                        __syncwarp(grp);
+                        img_free = true;
+                    }
+                    const uint32_t rl = (uint32_t)(n - row0);
+                    uint8_t* tile = aimg + (size_t)(rl >> 7) * 2 * kTcTile;
+                    store_image4(tile, tile + kTcTile, sw128_offset(rl & 127u, (uint32_t)(4 * v)), r);
+                }
             }
+            if (kTC) fence_proxy_async_smem();
             __syncthreads();
-            if (CL > 1) mbar_wait(&bars[1 + b], (uint32_t)(((j - 1) >> 1) & 1));
+        }
+        if (kTC) {
+            if (tid == T - 1) issue_mma(j);
+            continue;
         }
         // contraction step: acc[tile] += P_j[4 rows][DP] * W'_j[DP][4 g]
         const float4* P4 = reinterpret_cast<const float4*>(Pcur);
@@ -337,6 +451,83 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
                 }
             }
         }
+    }
+    // the peers' rows of the last step must have landed before this CTA may leave (remote stores into a dead CTA)
+    if (CL > 1 && K > 1) mbar_wait(&bars[1 + ((K - 1) & 1)], (uint32_t)(((K - 2) >> 1) & 1));
+
+    if (kTC) {
+        // ---- epilogue from TMEM: warp w reads lanes [32 (w % 4), +32) of tile w / 4; lane = one output row
+        mbar_wait(&bars[5], (uint32_t)((K - 1) & 1));
+        tcgen05_fence_after();
+        const int warp = tid >> 5, lane = tid & 31;
+        const int pp = p.pool_p;
+        if (warp < 4 * p.MT) {
+            const int mt = warp >> 2;
+            const int rl = mt * 128 + (warp & 3) * 32 + lane;
+            const int n = row0 + rl;
+            const bool live = n < row1;
+            for (int cb = 0; cb < p.GP16; cb += 16) {
+                float v[16];
+                tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * p.GP16 + cb), v);
+                if (cb >= G) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int g = cb + i;
+                    if (live && g < G) {
+                        if (p.bias_mode == TGCN_BIAS_PER_VERTEX) v[i] += __ldg(p.bias + (int64_t)n * G + g);
+                        else if (p.bias_mode == TGCN_BIAS_PER_FILTER) v[i] += __ldg(p.bias + g);
+                    }
+                }
+                if (p.out && live) {
+                    float* dst = p.out + ((int64_t)q * N + n) * G + cb;
+                    if ((G & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            if (cb + i < G) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (cb + i < G) dst[i] = v[i];
+                    }
+                }
+                if (p.y) {      // siblings are adjacent lanes: the leader of each group of pp lanes takes the first maximum
+                    float best[16];
+                    unsigned arg[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x0 = v[i];
+                        if (p.relu) x0 = (x0 != x0) ? x0 : fmaxf(x0, 0.f);
+                        float b0 = x0;
+                        int a0 = 0;
+                        for (int s2 = 1; s2 < pp; ++s2) {
+                            const float xs = __shfl_down_sync(0xffffffffu, x0, s2);
+                            take_max_r(xs, s2, b0, a0);
+                        }
+                        best[i] = b0; arg[i] = (unsigned)a0;
+                    }
+                    if (live && (lane % pp) == 0) {
+                        const int64_t off = ((int64_t)q * (N / pp) + n / pp) * G + cb;
+                        if ((G & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                if (cb + i < G) {
+                                    *reinterpret_cast<float4*>(p.y + off + i) = make_float4(best[i], best[i + 1], best[i + 2], best[i + 3]);
+                                    *reinterpret_cast<uchar4*>(p.idx + off + i) =
+                                        make_uchar4((unsigned char)arg[i], (unsigned char)arg[i + 1], (unsigned char)arg[i + 2],
+                                                    (unsigned char)arg[i + 3]);
+                                }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (cb + i < G) { p.y[off + i] = best[i]; p.idx[off + i] = (uint8_t)arg[i]; }
+                        }
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(tmem_acc, tmem_cols_pow2((uint32_t)(p.MT * p.GP16)));
+        return;
     }
 
     // epilogue: bias, optional ReLU + max-pool over the tile's sibling rows
@@ -834,7 +1025,7 @@ resident_reduce_kernel(const ResReduceParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct ResPlan { bool ok, csr_smem, w_smem; int NP, DP, V, GP, GG, threads, tpt, split, rg_per, Vh, R, dwt; size_t smem; };
+struct ResPlan { bool ok, csr_smem, w_smem, tc; int NP, DP, V, GP, GG, GP16, MT, threads, tpt, split, rg_per, Vh, R, dwt; size_t smem; };
 
 static bool res_dims_ok(int N, int D, int G, int K, int64_t E) {
     if (N < 1 || D < 1 || G < 1 || K < 1 || K > kResMaxK || E < 0 || E > (int64_t)INT32_MAX / 16) return false;
@@ -860,6 +1051,17 @@ static ResPlan res_plan_fwd(int Q, int N, int D, int G, int K, int64_t E) {
     pl.split = CL;
     pl.rg_per = (RG + CL - 1) / CL;
     const int ntiles = pl.rg_per * pl.GG;
+    pl.GP16 = round_up16(G);
+    pl.MT = (pl.rg_per * 4 + 127) / 128;
+    // tensor-core contraction: one 32-wide k-block, accumulators of all row tiles in TMEM, images in shared memory
+    if (tuning_value(kTuneResTc) != 0 && pl.DP <= 32 && pl.GP16 <= 256 && pl.MT * pl.GP16 <= 512 && pl.MT <= 4) {
+        for (int cs = 1; cs >= 0 && !pl.ok; --cs) {
+            pl.csr_smem = cs != 0; pl.w_smem = false;
+            pl.smem = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, false, pl.MT, pl.GP16).total;
+            pl.ok = pl.smem <= kResSmemLimit;
+        }
+        if (pl.ok) { pl.tc = true; pl.threads = 1024; pl.tpt = 1; return pl; }
+    }
     pl.threads = (ntiles <= 1024 && env_int("TGCN_RES_T", 1024) == 1024) ? 1024 : 512;
     pl.tpt = (ntiles + pl.threads - 1) / pl.threads;
     if (pl.tpt > 4) return pl;
@@ -990,7 +1192,8 @@ extern "C" int64_t tgcn_resident_stack_bytes(int Q, int N, int D, int K) {
 // weight images written by the forward and read by the backward: [Wm | Wt], K*DP*GP floats each
 extern "C" int64_t tgcn_resident_weights_bytes(int D, int G, int K) {
     if (D < 1 || G < 1 || K < 1) return 0;
-    return (int64_t)sizeof(float) * 2 * K * round_up4(D) * round_up4(G);
+    // [Wm | Wt] fp32 images, then the tensor-core image [K][hi|lo][G^16][128 B] (16-byte aligned)
+    return (int64_t)sizeof(float) * 2 * K * round_up4(D) * round_up4(G) + (int64_t)K * 2 * round_up16(G) * 128;
 }
 
 extern "C" int64_t tgcn_resident_bwd_workspace(int Q, int N, int D, int G, int K) {
@@ -1022,18 +1225,33 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* en
     cudaStream_t st = as_stream(stream);
     float* Wm = wimages;
     float* Wt = wimages + (int64_t)K * pl.DP * pl.GP;
-    resident_prep_kernel<<<(unsigned)ceil_div(pl.DP * pl.GP, 256), 256, 0, st>>>(W, Wm, Wt, K, D, G, pl.DP, pl.GP, recursion);
+    uint8_t* Wtc = reinterpret_cast<uint8_t*>(wimages + (int64_t)2 * K * pl.DP * pl.GP);
+    {
+        const int rows_d = pl.DP > 32 ? pl.DP : 32;
+        resident_prep_kernel<<<(unsigned)ceil_div(rows_d * pl.GP16, 256), 256, 0, st>>>(W, Wm, Wt, pl.DP <= 32 ? Wtc : nullptr, K, D, G,
+                                                                                      pl.DP, pl.GP, pl.GP16, recursion);
+    }
     TGCN_LAUNCH_CHECK("resident_prep");
     ResFwdParams p{};
     p.rowinfo = reinterpret_cast<const int2*>(rowinfo); p.entries = reinterpret_cast<const int2*>(entries);
-    p.x = x; p.Wm = Wm; p.bias = bias; p.out = out; p.y = y; p.idx = idx;
+    p.x = x; p.Wm = Wm; p.Wtc = Wtc; p.GP16 = pl.GP16; p.MT = pl.MT; p.bias = bias; p.out = out; p.y = y; p.idx = idx;
     p.stack = stack; p.N = N; p.NP = pl.NP; p.E = (int)E; p.D = D; p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP;
     p.GG = pl.GG; p.K = K; p.bias_mode = bias_mode; p.recursion = recursion; p.pool_p = y ? pool_p : 4; p.relu = relu;
     p.CL = pl.split; p.rg_per = pl.rg_per;
-    const ResSmemFwd lay = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, pl.w_smem);
+    const ResSmemFwd lay = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, pl.w_smem, pl.tc ? pl.MT : 0, pl.GP16);
     const dim3 grid((unsigned)(Q * pl.split));
+    if (pl.tc) {
+        if (pl.csr_smem)
+            TGCN_PROPAGATE(res_launch(resident_fwd_kernel<1024, 1, true, false, true>, grid, 1024, pl.split, lay.total, st,
+                                      "resident_layer_fwd", p, lay));
+        else
+            TGCN_PROPAGATE(res_launch(resident_fwd_kernel<1024, 1, false, false, true>, grid, 1024, pl.split, lay.total, st,
+                                      "resident_layer_fwd", p, lay));
+        TGCN_LAUNCH_CHECK("resident_layer_fwd");
+        return TGCN_OK;
+    }
 #define TGCN_RES_FWD2(TH, TPT, CS, WS) \
-    TGCN_PROPAGATE(res_launch(resident_fwd_kernel<TH, TPT, CS, WS>, grid, TH, pl.split, lay.total, st, "resident_layer_fwd", p, lay))
+    TGCN_PROPAGATE(res_launch(resident_fwd_kernel<TH, TPT, CS, WS, false>, grid, TH, pl.split, lay.total, st, "resident_layer_fwd", p, lay))
 #define TGCN_RES_FWD1(TH, TPT)                                                                                       \
     do {                                                                                                             \
         if (pl.csr_smem) { if (pl.w_smem) TGCN_RES_FWD2(TH, TPT, true, true); else TGCN_RES_FWD2(TH, TPT, true, false); }   \
