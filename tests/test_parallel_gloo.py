@@ -93,7 +93,8 @@ def _bucket_worker(rank, world):
     ref_model.load_state_dict(model.state_dict()); ref_model.eval()
     F.nll_loss(ref_model(x), y).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in ref_model.parameters()])
-    bucket = GradientBucket(model.parameters())
+    bucket = GradientBucket(model.parameters(), late=list(model.tgcn1.parameters()))    # two buckets, early one overlapped
+    assert bucket.late and bucket.early and len(bucket._hooks) == len(bucket.early)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     opt.zero_grad(set_to_none=True)
     lo, hi = shard_range(Q, rank, world)
@@ -101,7 +102,8 @@ def _bucket_worker(rank, world):
     bucket.sync()
     for p in model.parameters():
         assert p.grad.data_ptr() >= bucket.flat.data_ptr()
-    assert float((bucket.flat - ref).abs().max() / ref.abs().max()) < 1e-5
+    got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])     # model order (the flat buffer is early|late)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
     opt.step()
     mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     other = [torch.empty_like(mine) for _ in range(world)]

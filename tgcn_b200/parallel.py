@@ -68,15 +68,23 @@ class FlatGradients:
 class GradientBucket:
     """Gradient exchange for a training step that lets autograd ALLOCATE the gradients
     (`zero_grad(set_to_none=True)`: no zero fill, no accumulate kernels): after the backward the
-    per-parameter gradients are packed into one flat fp32 buffer by a single multi-tensor copy, averaged
-    over the ranks by ONE collective, and `p.grad` is re-bound to the views of the flat buffer so the
-    optimizer reads the averaged values.  Everything is capturable in a CUDA graph (NCCL included).
-    With world size 1 it does nothing."""
+    per-parameter gradients are packed into one flat fp32 buffer by multi-tensor copies, averaged over the
+    ranks, and `p.grad` is re-bound to the views of the flat buffer so the optimizer reads the averaged values.
 
-    def __init__(self, params, group=None):
-        self.params = [p for p in params if p.requires_grad]
-        if not self.params:
+    Overlap: parameters listed in `late` (the layers whose gradients are produced LAST by the backward, i.e.
+    the first layers of the model) form a second bucket.  As soon as every other gradient exists (autograd
+    post-accumulate hooks) the first bucket's allreduce is issued asynchronously, so it runs under the
+    remaining backward; `sync()` reduces the late bucket and joins.  Everything is capturable in a CUDA graph
+    (NCCL included).  With world size 1 it does nothing."""
+
+    def __init__(self, params, group=None, late=()):
+        params = [p for p in params if p.requires_grad]
+        if not params:
             raise ValueError("no trainable parameters")
+        late_ids = {id(p) for p in late}
+        self.early = [p for p in params if id(p) not in late_ids]
+        self.late = [p for p in params if id(p) in late_ids]
+        self.params = self.early + self.late
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         dev = self.params[0].device
@@ -87,16 +95,44 @@ class GradientBucket:
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.n_early = sum(p.numel() for p in self.early)
+        self._pending = None
+        self._seen = 0
+        self._hooks = []
+        if self.world > 1 and self.late and self.early:
+            for p in self.early:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _reduce(self, lo, hi, async_op):
+        buf = self.flat[lo:hi]
+        if dist.get_backend(self.group) == "nccl":
+            return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def _pack(self, params, views):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        torch._foreach_copy_(views, grads)
+
+    def _on_grad(self, _param):
+        self._seen += 1
+        if self._seen == len(self.early):          # every early gradient exists: reduce them under the rest of the backward
+            self._pack(self.early, self.views[:len(self.early)])
+            self._pending = self._reduce(0, self.n_early, async_op=True)
 
     def sync(self):
         if self.world == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self.views, grads)
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        ne = len(self.early)
+        if self._pending is None:                  # no hooks (single bucket) or a gradient never arrived: do it now
+            self._pack(self.early, self.views[:ne])
+            self._reduce(0, self.n_early, async_op=False)
+        if self.late:
+            self._pack(self.late, self.views[ne:])
+            self._reduce(self.n_early, self.flat.numel(), async_op=False)
+        if self._pending is not None:
+            self._pending.wait()
+        self._pending, self._seen = None, 0
+        if dist.get_backend(self.group) != "nccl":
             self.flat.div_(self.world)
         for p, v in zip(self.params, self.views):
             p.grad = v
