@@ -540,7 +540,7 @@ def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
     per_launch_ms = _time_graph(steps, reps, flush_buf) / (K - 1)
     bytes_per_launch = algorithmic_step_bytes(N, C, plan.nnz, has_prev=False)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "spmm_step_vec4_kernel (layer-1 recursion step, 2S+E bytes)",
+    return {"bound": "hbm", "kernel": "spmm_step_pipe_kernel (layer-1 recursion step, 2S+E bytes)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "bytes_per_launch": int(bytes_per_launch), "us_per_launch": per_launch_ms * 1e3, "peak_source": src}
 

@@ -19,7 +19,7 @@ int set_error(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static const char* const kTuneNames[kTuneCount] = {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC"};
-static const int kTuneDefaults[kTuneCount] = {0, 0, 1, 0};   // SPMM_STAGED applies only to operands with a registered plan
+static const int kTuneDefaults[kTuneCount] = {0, 4, 1, 0};   // persistent pipelined SpMM, 4 blocks per SM   // SPMM_STAGED applies only to operands with a registered plan
 static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}};
 
 int tuning_value(int key) {

@@ -131,7 +131,10 @@ class NetTGCN_HCP(nn.Module):
             x = gcn_pool_4(F.relu(self.tgcn1(x)))
             x = gcn_pool_4(F.relu(self.gcn2(x)))
         x = x.reshape(x.shape[0], -1)
-        if self.fused_head and x.is_cuda and (self.training and x.shape[0] > 1 or not self.training):
+        # the fused head is a latency optimisation for small dense tails (parcellation-sized graphs); a large fc1
+        # (cortical mesh: 167 424 x 200) is a bandwidth-bound GEMM and stays with cuBLAS
+        small = self.fc1.in_features * self.fc1.out_features <= (1 << 21)
+        if self.fused_head and small and x.is_cuda and (self.training and x.shape[0] > 1 or not self.training):
             from .nn.head import fused_head
             return fused_head(x, self.fc1, self.dense1_bn, self.fc2)
         x = F.relu(self.dense1_bn(self.fc1(x)))
