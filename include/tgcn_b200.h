@@ -63,7 +63,9 @@ long long tgcn_launch_count(void);
  * "SPMM_PIPE" = blocks per SM of the persistent, software-pipelined SpMM kernel (0 = plain kernel),
  * "SPMM_TILE" = rows per block of the row-tiled SpMM kernel (0 = off), "SPMM_STAGED" = use registered row-block
  * plans (1), "RES_TC" = contraction of the resident forward kernel on tcgen05 with 3xTF32 operands and TMEM
- * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes).  The SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
+ * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes), "RES_ENT" =
+ * keep each thread's CSR entries in registers across the K steps of the resident forward (bit-identical; 0 default:
+ * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us).  The SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
 int tgcn_set_tuning(const char* key, int value);
 
 /* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */

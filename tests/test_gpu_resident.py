@@ -296,3 +296,22 @@ def test_tcgen05_and_ffma_contraction_of_the_resident_forward_agree(shape):
     assert rel_err(outs[0], ref) < 2e-6
     assert rel_err(outs[1], ref) < 2e-5
     assert rel_err(outs[1], outs[0]) < 2e-5
+
+
+def test_register_cached_csr_variant_is_bit_identical():
+    """RES_ENT tuning key: the forward variant that keeps each thread's CSR entries in registers across the K
+    steps follows the same even/odd summation order, so its output is bit-identical to the default kernel."""
+    from tgcn_b200 import _lib
+    lib = _lib.load()
+    for shape in (SHAPES[0], SHAPES[1], SHAPES[4]):
+        lay, L, x, kind = _build(shape, "reference", "resident", seed=0)
+        xt = torch.tensor(x, device="cuda")
+        outs = []
+        try:
+            for v in (0, 1):
+                assert lib.tgcn_set_tuning(b"RES_ENT", v) == 0
+                with torch.no_grad():
+                    outs.append(lay(xt))
+        finally:
+            lib.tgcn_set_tuning(b"RES_ENT", -1)
+        assert torch.equal(outs[0], outs[1])

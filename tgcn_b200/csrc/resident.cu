@@ -112,13 +112,14 @@ __device__ __forceinline__ int2 ld_one(const int2* p) {
     return __ldg(p);
 }
 
-// sum_e val[e] * in[col[e]][v] for one row and one float4 column group (fixed summation order)
+// a0 / a1 += val[e] * in[col[e]][v] over entries [k0, len) of one row (k0 even): even positions go to a0, odd
+// positions to a1 -- the ONE summation order every resident variant follows, so results do not depend on the
+// variant (or on the batch / cluster split that selects it)
 template <bool kCsrSmem>
-__device__ __forceinline__ float4 gather_row(const int2* __restrict__ ent, const int2 info,
-                                             const float4* __restrict__ in4, const int V, const int v) {
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+__device__ __forceinline__ void gather_accum(const int2* __restrict__ ent, const int2 info, int k,
+                                             const float4* __restrict__ in4, const int V, const int v,
+                                             float4& a0, float4& a1) {
     const int2* e = ent + info.x;
-    int k = 0;
     for (; k + 4 <= info.y; k += 4) {
         const int4 p01 = ld_pair<kCsrSmem>(e + k), p23 = ld_pair<kCsrSmem>(e + k + 2);
         const float4 x0 = in4[p01.x * V + v], x1 = in4[p01.z * V + v], x2 = in4[p23.x * V + v], x3 = in4[p23.z * V + v];
@@ -138,6 +139,14 @@ __device__ __forceinline__ float4 gather_row(const int2* __restrict__ ent, const
         const int2 p0 = ld_one<kCsrSmem>(e + k);
         fma4s(a0, __int_as_float(p0.y), in4[p0.x * V + v]);
     }
+}
+
+// sum_e val[e] * in[col[e]][v] for one row and one float4 column group (fixed summation order)
+template <bool kCsrSmem>
+__device__ __forceinline__ float4 gather_row(const int2* __restrict__ ent, const int2 info,
+                                             const float4* __restrict__ in4, const int V, const int v) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    gather_accum<kCsrSmem>(ent, info, 0, in4, V, v, a0, a1);
     return make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
 }
 
@@ -216,7 +225,10 @@ __device__ __forceinline__ void store_image4(uint8_t* hi, uint8_t* lo, uint32_t 
     *reinterpret_cast<float4*>(lo + off) = l;
 }
 
-template <int THREADS, int TPT, bool kCsrSmem, bool kWSmem, bool kTC>
+// ENT > 0 (needs at most one (row, float4) item per thread): the first ENT packed entries of the thread's row live
+// in registers for all K steps -- the CSR operand is read once per launch instead of once per step, and the
+// unrolled gathers of a step are all in flight together.
+template <int THREADS, int TPT, bool kCsrSmem, bool kWSmem, bool kTC, int ENT = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -333,6 +345,24 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     if (CL > 1) cluster_sync_all();   // every CTA of the cluster runs and has initialised its barriers
     else __syncthreads();
 
+    int ec[ENT > 0 ? ENT : 1];
+    float ew[ENT > 0 ? ENT : 1];
+    if (ENT > 0) {
+        const int i = row0 * V + tid;
+#pragma unroll
+        for (int k = 0; k < ENT; ++k) { ec[k] = 0; ew[k] = 0.f; }
+        if (i < row1 * V) {
+            const int n = i / V, v = i - n * V;
+            const int2 info = rowinfo_s[n];
+#pragma unroll
+            for (int k = 0; k < ENT; ++k)
+                if (k < info.y) {
+                    const int2 pe = ld_one<kCsrSmem>(ent + info.x + k);
+                    ec[k] = pe.x * V + v;            // float4 index of the gathered element, fixed for all steps
+                    ew[k] = __int_as_float(pe.y);
+                }
+        }
+    }
     const uint32_t rx_bytes = (uint32_t)(N - (row1 - row0)) * (uint32_t)DP * 4u;   // rows the peers send per step
     const int ntiles = (rg1 - rg0) * GG;
     float4 acc[TPT][4];
@@ -388,7 +418,20 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
             const int TW = kTC ? T - 32 : T;
             for (int i = row0 * V + tid; i < row1 * V && tid < TW; i += TW) {
                 const int n = i / V, v = i - n * V;
-                float4 r = gather_row<kCsrSmem>(ent, rowinfo_s[n], in4, V, v);
+                float4 r;
+                if (ENT > 0) {
+                    const int2 info = rowinfo_s[n];
+                    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+                    for (int k = 0; k < ENT; k += 2) {
+                        if (k < info.y) fma4s(a0, ew[k], in4[ec[k]]);
+                        if (k + 1 < info.y) fma4s(a1, ew[k + 1], in4[ec[k + 1]]);
+                    }
+                    if (info.y > ENT) gather_accum<kCsrSmem>(ent, info, ENT, in4, V, v, a0, a1);
+                    r = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+                } else {
+                    r = gather_row<kCsrSmem>(ent, rowinfo_s[n], in4, V, v);
+                }
                 if (cheb) {   // T_j = 2 L~ T_{j-1} - T_{j-2}; T_{j-2} is what the output buffer still holds
                     const float4 o = out4[i];
                     r.x = fmaf(-1.f, o.x, 2.f * r.x); r.y = fmaf(-1.f, o.y, 2.f * r.y);
@@ -1025,7 +1068,7 @@ resident_reduce_kernel(const ResReduceParams p) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct ResPlan { bool ok, csr_smem, w_smem, tc; int NP, DP, V, GP, GG, GP16, MT, threads, tpt, split, rg_per, Vh, R, dwt; size_t smem; };
+struct ResPlan { bool ok, csr_smem, w_smem, tc; int ent; int NP, DP, V, GP, GG, GP16, MT, threads, tpt, split, rg_per, Vh, R, dwt; size_t smem; };
 
 static bool res_dims_ok(int N, int D, int G, int K, int64_t E) {
     if (N < 1 || D < 1 || G < 1 || K < 1 || K > kResMaxK || E < 0 || E > (int64_t)INT32_MAX / 16) return false;
@@ -1063,6 +1106,8 @@ static ResPlan res_plan_fwd(int Q, int N, int D, int G, int K, int64_t E) {
         if (pl.ok) { pl.tc = true; pl.threads = 1024; pl.tpt = 1; return pl; }
     }
     pl.threads = (ntiles <= 1024 && env_int("TGCN_RES_T", 1024) == 1024) ? 1024 : 512;
+    // at most one (row, float4) item and one tile per thread with 768 threads: cache the row's entries in registers
+    if (tuning_value(kTuneResEnt) != 0 && pl.rg_per * 4 * pl.V <= 768 && ntiles <= 768) { pl.threads = 768; pl.ent = 16; }
     pl.tpt = (ntiles + pl.threads - 1) / pl.threads;
     if (pl.tpt > 4) return pl;
     for (int opt = 0; opt < 4 && !pl.ok; ++opt) {
@@ -1257,7 +1302,13 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* en
         if (pl.csr_smem) { if (pl.w_smem) TGCN_RES_FWD2(TH, TPT, true, true); else TGCN_RES_FWD2(TH, TPT, true, false); }   \
         else             { if (pl.w_smem) TGCN_RES_FWD2(TH, TPT, false, true); else TGCN_RES_FWD2(TH, TPT, false, false); } \
     } while (0)
-    if (pl.threads == 1024) {
+    if (pl.ent > 0) {
+#define TGCN_RES_FWD_E(CS, WS) \
+    TGCN_PROPAGATE(res_launch(resident_fwd_kernel<768, 1, CS, WS, false, 16>, grid, 768, pl.split, lay.total, st, "resident_layer_fwd", p, lay))
+        if (pl.csr_smem) { if (pl.w_smem) TGCN_RES_FWD_E(true, true); else TGCN_RES_FWD_E(true, false); }
+        else             { if (pl.w_smem) TGCN_RES_FWD_E(false, true); else TGCN_RES_FWD_E(false, false); }
+#undef TGCN_RES_FWD_E
+    } else if (pl.threads == 1024) {
         TGCN_RES_FWD1(1024, 1);
     } else {
         switch (pl.tpt) { case 1: TGCN_RES_FWD1(512, 1); break; case 2: TGCN_RES_FWD1(512, 2); break;
