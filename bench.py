@@ -120,7 +120,7 @@ def algorithmic_step_bytes(N, C, nnz, has_prev):
 def run_b200(args):
     import torch.distributed as dist
     from tgcn_b200 import _lib, workloads as wl
-    from tgcn_b200.parallel import GradientBucket, broadcast_parameters, init_distributed
+    from tgcn_b200.parallel import GradientBucket, PeerAllreduceSGD, broadcast_parameters, init_distributed
 
     os.environ.pop("NCCL_DEBUG", None)      # its version banner goes to stdout; the contract is ONE JSON line
     rank, world, local = init_distributed("nccl")
@@ -146,9 +146,25 @@ def run_b200(args):
     N0 = Ls[0].shape[0]
     # the first layer's gradients are produced last: their (small) bucket is reduced after the others,
     # whose allreduce runs under the layer-1 backward
-    grads = GradientBucket(model.parameters(), late=list(model.tgcn1.parameters()))
-    # pytorch_hcp_tgcn.py defaults (lr 0.01, momentum 0.5); torch's fused multi-tensor implementation: one launch
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.5, fused=True)
+    # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
+    # --dp nccl: two-bucket NCCL allreduce overlapped with the layer-1 backward + torch's fused SGD
+    use_peer = world > 1 and args.dp == "peer"
+    if use_peer:
+        # collective decision: if CUDA IPC is unavailable on any rank, every rank falls back to the NCCL path
+        try:
+            opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:                       # noqa: BLE001
+            sys.stderr.write("[bench] peer-memory allreduce unavailable on rank %d: %s\n" % (rank, exc))
+            opt, ok = None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        use_peer = bool(ok.item() > 0)
+    if use_peer:
+        grads = None
+    else:
+        grads = GradientBucket(model.parameters(), late=list(model.tgcn1.parameters()))
+        # pytorch_hcp_tgcn.py defaults (lr 0.01, momentum 0.5); torch's fused multi-tensor implementation: one launch
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.5, fused=True)
 
     # synthetic data: a few distinct pinned host batches per rank, cycled
     n_host = 4
@@ -169,7 +185,8 @@ def run_b200(args):
         loss_dev.copy_(loss.detach())
 
     def finish_step():
-        grads.sync()                         # world > 1: one flat NCCL allreduce (average)
+        if grads is not None:
+            grads.sync()                     # world > 1, --dp nccl: bucketed NCCL allreduce (average)
         opt.step()
 
     # warm-up (eager, side stream) then capture the whole training step (forward, loss, backward, gradient
@@ -287,6 +304,8 @@ def run_b200(args):
             "config": {"workload": args.workload, "description": cfg["desc"], "per_gpu_batch": Q, "global_batch": world * Q,
                        "N_padded": [int(L.shape[0]) for L in Ls], "nnz_L0": int(Ls[0].nnz), "K": 10, "H": H,
                        "parallelism": "dp%d" % world, "engine": args.engine,
+                       "gradient_exchange": ("peer-memory allreduce fused with SGD (NVLink P2P loads)" if use_peer else
+                                             "NCCL allreduce, 2 buckets" if world > 1 else "none"),
                        "l2": "flushed between timed steps (256 MB write)" if flush else "working set exceeds L2 (K-slab stack > 126 MB)",
                        "cuda_graph": use_graph,
                        "e2e_pipeline": "batch i+1 is uploaded (pinned host -> device, copy stream) while step i runs; the loss is read back and synchronised every step"},
@@ -628,6 +647,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--rgg-n", type=int, default=1_000_000, help="vertices of the rgg1m workload")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="gradient exchange for N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

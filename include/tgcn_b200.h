@@ -226,6 +226,24 @@ int tgcn_head_bwd(const float* dlogp, const float* logp, const float* act, const
                   float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2,
                   float* dh_scratch, int Q, int I, int Hd, int C, void* stream);
 
+/* ---- data-parallel step tail: gradient allreduce fused with SGD over NVLink peer memory -------- */
+/* Replaces DataParallel's gradient gather + optim.SGD(momentum).step() (pytorch_hcp_tgcn.py:164-169, 271-272).
+ * Every rank allocates one region (tgcn_peer_region_bytes(n, nseg) bytes for n gradient elements in nseg tensors) with
+ * tgcn_peer_alloc, exports its 64-byte IPC handle, and imports the peers' handles (same node; the handles travel
+ * over any host channel, e.g. torch.distributed.all_gather_object).  tgcn_peer_allreduce_sgd then issues two
+ * launches: pack this rank's gradients into its region and publish a step flag; wait for every rank's flag, read
+ * all ranks' gradients over NVLink in rank order (bit-identical replicas), average, and apply
+ * buf = momentum * buf + g; param -= lr * buf.  Capturable in a CUDA graph; bounded waits.  world <= 8. */
+int tgcn_peer_alloc(int64_t bytes, void** ptr_out);
+int tgcn_peer_free(void* ptr);
+int tgcn_peer_export(void* ptr, unsigned char* handle64_host);
+int tgcn_peer_import(const unsigned char* handle64_host, void** ptr_out);
+int tgcn_peer_close(void* ptr);
+int64_t tgcn_peer_region_bytes(int64_t n, int nseg);
+int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int rank, const float* const* grads_host,
+                            float* const* params_host, float* const* moms_host, const int64_t* numels_host,
+                            int nseg, float lr, float momentum, unsigned int* state, void* stream);
+
 /* ---- host-side graph preprocessing (CPU, no device work) ----------------------------------- */
 /* One level of greedy heavy-edge (Graclus-normalised) matching: replaces the pure-Python loop
  * `metis_one_level` (gcn/coarsening.py:119-165) bit-exactly.  rr/cc/vv: COO triplets sorted by

@@ -16,8 +16,8 @@ sys.path.insert(0, ROOT)
 
 from tgcn_b200 import _lib, workloads as wl  # noqa: E402
 from tgcn_b200.csr import build_csr  # noqa: E402
-from tgcn_b200.parallel import (FlatGradients, RowPartition, RowPartitionedLayer, broadcast_parameters,  # noqa: E402
-                                halo_exchange, init_distributed, shard_range)
+from tgcn_b200.parallel import (FlatGradients, PeerAllreduceSGD, RowPartition, RowPartitionedLayer,  # noqa: E402
+                                broadcast_parameters, halo_exchange, init_distributed, shard_range)
 
 
 def check_dp(rank, world, dev):
@@ -100,6 +100,33 @@ def check_partitioned_layer(rank, world, dev):
     return part.plan.n_halo
 
 
+def check_peer_sgd(rank, world, dev):
+    """D. fused peer-memory allreduce + SGD == NCCL allreduce (mean) + torch SGD, and the replicas stay identical."""
+    torch.manual_seed(3)                                           # same initial parameters on every rank
+    shapes = [(10, 15, 32), (384, 32), (200, 1536), (6,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    opt_a = PeerAllreduceSGD(pa, lr=0.05, momentum=0.5)
+    opt_b = torch.optim.SGD(pb, lr=0.05, momentum=0.5)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)        # different gradients per rank
+    for it in range(5):
+        for p, q in zip(pa, pb):
+            gr = torch.randn(p.shape, device=dev, generator=g)
+            p.grad = gr.clone()
+            avg = gr.clone()
+            dist.all_reduce(avg, op=dist.ReduceOp.AVG)
+            q.grad = avg
+        opt_a.step(); opt_b.step()
+    torch.cuda.synchronize()
+    err = max(float((p - q).abs().max() / q.abs().max()) for p, q in zip(pa, pb))
+    assert err < 1e-5, err
+    mine = torch.cat([p.detach().reshape(-1) for p in pa])
+    others = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(others, mine)
+    assert all(torch.equal(o, mine) for o in others), "replicas diverged"
+    return err
+
+
 def main():
     rank, world, local = init_distributed("nccl")
     dev = torch.device("cuda", local)
@@ -107,9 +134,10 @@ def main():
     e = check_dp(rank, world, dev)
     h = check_halo(rank, world, dev)
     h2 = check_partitioned_layer(rank, world, dev)
+    pe = check_peer_sgd(rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d" % (world, e, h, h2))
+        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d peer_sgd_err=%.2e" % (world, e, h, h2, pe))
     dist.destroy_process_group()
 
 

@@ -97,3 +97,44 @@ def test_row_partitioned_layer_single_rank_matches_module():
     dW, db = part.backward(dout)
     assert rel_err(dW.cpu().numpy(), lay.weight.grad.reshape(K, H * F, Gc).cpu().numpy()) < 1e-4
     assert rel_err(db.cpu().numpy(), lay.bias.grad[0].cpu().numpy()) < 1e-5
+
+
+def test_peer_allreduce_sgd_single_rank_matches_torch_sgd():
+    """csrc/peer.cu with world 1 (own region only): same trajectory as torch.optim.SGD(lr, momentum), eager and
+    replayed from a CUDA graph."""
+    from tgcn_b200.parallel import PeerAllreduceSGD
+    torch.manual_seed(0)
+    shapes = [(10, 15, 32), (1, 384, 32), (200,), (6, 200), (7,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    opt_a = PeerAllreduceSGD(pa, lr=0.05, momentum=0.5)
+    opt_b = torch.optim.SGD(pb, lr=0.05, momentum=0.5)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(4):
+        grads = [torch.randn(p.shape, device="cuda", generator=g) for p in pa]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone(); q.grad = gr.clone()
+        if it == 2:
+            pa[3].grad = None; pb[3].grad = torch.zeros_like(pb[3])      # a missing gradient counts as zero
+        opt_a.step(); opt_b.step()
+        for p, q in zip(pa, pb):
+            assert rel_err(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-6
+    assert int(opt_a.state[0]) == 4
+    # CUDA-graph replay: the step number lives in device memory
+    static = [torch.randn(p.shape, device="cuda", generator=g) for p in pa]
+    for p, q, gr in zip(pa, pb, static):
+        p.grad = gr; q.grad = gr.clone()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        opt_a.step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt_a.step()
+    graph.replay(); graph.replay()
+    for _ in range(3):                      # one eager warm-up step + two replays (capture itself does not execute)
+        opt_b.step()
+    torch.cuda.synchronize()
+    assert int(opt_a.state[0]) == 7
+    for p, q in zip(pa, pb):
+        assert rel_err(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 1e-5

@@ -60,6 +60,13 @@ SIGNATURES = {
                                      _i, _i, _i, _i, _i, _p]),
     "tgcn_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_peer_alloc": (_i, [_l, _p]),
+    "tgcn_peer_free": (_i, [_p]),
+    "tgcn_peer_export": (_i, [_p, _p]),
+    "tgcn_peer_import": (_i, [_p, _p]),
+    "tgcn_peer_close": (_i, [_p]),
+    "tgcn_peer_region_bytes": (_l, [_l, _i]),
+    "tgcn_peer_allreduce_sgd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _f, _f, _p, _p]),
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
 }

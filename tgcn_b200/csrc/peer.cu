@@ -1,0 +1,249 @@
+// Gradient allreduce fused with the SGD-momentum update over NVLink peer memory.
+//
+// The data-parallel step ends with "average the gradients over the ranks, then update the parameters"
+// (reference: torch.nn.DataParallel's gather + optim.SGD.step, pytorch_hcp_tgcn.py:164-169,271-272).  With NCCL that
+// is a multi-tensor copy, an allreduce kernel and an optimizer kernel, ~35 us of mostly launch/latency at the
+// 1.4 MB gradient size of the parcellation model.  Here every rank owns one cudaMalloc'ed region that its peers
+// map through CUDA IPC:  [ flat gradients, buffer 0 | buffer 1 | ready flag ].
+//   peer_pack_kernel   : copies this rank's gradients into flat[step & 1], then publishes `ready = step + 1`
+//                        (system-scope fence + release store) from the last block to finish;
+//   peer_reduce_sgd_kernel : waits until every rank's flag shows the step, then each thread reads ITS elements from
+//                        all ranks' buffers straight over NVLink (P2P loads), sums them in rank order -- the same
+//                        order on every rank, so the replicas stay bit-identical --, scales by 1/world and applies
+//                        buf = momentum * buf + g;  param -= lr * buf.  No intermediate averaged-gradient tensor.
+// Buffers alternate with the step parity, so a rank may start writing step s+2 only after all peers have posted
+// ready(s+1), i.e. after they finished reading step s: one flag exchange per step is the only synchronisation.
+// Waits are bounded (trap after ~2 s) so a lost peer cannot hang the device.  Step numbers live in device memory,
+// so the two launches are CUDA-graph capturable.
+#include <cstring>
+#include "common.cuh"
+
+namespace tgcn {
+
+constexpr int kPeerMaxSeg = 24;
+constexpr int kPeerMaxWorld = 8;
+constexpr unsigned long long kPeerSpinLimit = 4000000000ull;
+
+struct PeerSegs {
+    const float* grad[kPeerMaxSeg];
+    float* param[kPeerMaxSeg];
+    float* mom[kPeerMaxSeg];
+    int64_t off[kPeerMaxSeg + 1];     // offsets into the flat buffer (multiples of 4 elements)
+    int64_t len[kPeerMaxSeg];         // elements of each tensor
+    int nseg;
+};
+
+struct PeerRanks {
+    const float* flat[kPeerMaxWorld];           // each rank's region base
+    const unsigned int* flag[kPeerMaxWorld];    // each rank's ready flag
+    int world, rank;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Segment offsets are multiples of 4 elements, so every tensor is walked as float4 (plus a scalar tail) and ONE
+// grid-wide index space covers all tensors: one float4 per thread, all loads of a thread in flight at once -- the
+// remote (NVLink) round trip is paid once per thread, not once per element.
+__device__ __forceinline__ int find_seg(const PeerSegs& segs, int64_t e) {
+    int s = 0;
+#pragma unroll 1
+    while (s + 1 < segs.nseg && segs.off[s + 1] <= e) ++s;
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+peer_pack_kernel(const PeerSegs segs, float* flat_base, int64_t n, unsigned int* my_flag, const unsigned int* step_ctr,
+                 unsigned int* done_blocks) {
+    const unsigned int step = *step_ctr;
+    float* flat = flat_base + (int64_t)(step & 1u) * n;
+    for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 4 * i4;
+        const int s = find_seg(segs, e);
+        const int64_t loc = e - segs.off[s], len = segs.len[s];
+        const float* src = segs.grad[s];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src) {
+            if (loc + 4 <= len) v = *reinterpret_cast<const float4*>(src + loc);
+            else {
+                if (loc + 0 < len) v.x = src[loc + 0];
+                if (loc + 1 < len) v.y = src[loc + 1];
+                if (loc + 2 < len) v.z = src[loc + 2];
+            }
+        }
+        *reinterpret_cast<float4*>(flat + e) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        if (prev == gridDim.x - 1) {           // last block: every block's stores are fenced; publish
+            *done_blocks = 0u;
+            __threadfence_system();
+            st_release_sys(my_flag, step + 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 ldcv4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+peer_reduce_sgd_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, float lr, float momentum,
+                       unsigned int* step_ctr, unsigned int* done_blocks) {
+    const unsigned int step = *step_ctr;
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = clock64();
+        for (int r = 0; r < ranks.world; ++r)
+            while (ld_acquire_sys(ranks.flag[r]) < step + 1u)
+                if (clock64() - t0 > kPeerSpinLimit) __trap();
+    }
+    __syncthreads();
+    const int64_t par = (int64_t)(step & 1u) * n;
+    const float inv = 1.0f / (float)ranks.world;
+    for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 4 * i4;
+        float4 gr[kPeerMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < ranks.world) gr[r] = ldcv4(ranks.flat[r] + par + e);          // all ranks' loads in flight together
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < ranks.world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }   // rank order: same on every rank
+        const int s = find_seg(segs, e);
+        const int64_t loc = e - segs.off[s], len = segs.len[s];
+        float* prm = segs.param[s] + loc;
+        float* mom = segs.mom[s] + loc;
+        const float gg[4] = {g.x * inv, g.y * inv, g.z * inv, g.w * inv};
+        if (loc + 4 <= len) {
+            float4 m = *reinterpret_cast<float4*>(mom), w = *reinterpret_cast<float4*>(prm);
+            m.x = fmaf(momentum, m.x, gg[0]); m.y = fmaf(momentum, m.y, gg[1]);
+            m.z = fmaf(momentum, m.z, gg[2]); m.w = fmaf(momentum, m.w, gg[3]);
+            w.x = fmaf(-lr, m.x, w.x); w.y = fmaf(-lr, m.y, w.y); w.z = fmaf(-lr, m.z, w.z); w.w = fmaf(-lr, m.w, w.w);
+            *reinterpret_cast<float4*>(mom) = m;
+            *reinterpret_cast<float4*>(prm) = w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (loc + c < len) {
+                    const float bcur = fmaf(momentum, mom[c], gg[c]);
+                    mom[c] = bcur;
+                    prm[c] = fmaf(-lr, bcur, prm[c]);
+                }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_blocks = 0u;
+            *step_ctr = step + 1u;
+        }
+    }
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+// ---- peer regions -------------------------------------------------------------------------------------------
+extern "C" int tgcn_peer_alloc(int64_t bytes, void** ptr_out) {
+    TGCN_REQUIRE(bytes > 0 && ptr_out, "tgcn_peer_alloc: bad arguments");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_alloc: %s", cudaGetErrorString(e));
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_alloc: %s", cudaGetErrorString(e));
+    *ptr_out = p;
+    return TGCN_OK;
+}
+
+extern "C" int tgcn_peer_free(void* ptr) {
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_free: %s", cudaGetErrorString(e));
+    return TGCN_OK;
+}
+
+// 64-byte opaque handle another process on the same node can open (cudaIpcGetMemHandle)
+extern "C" int tgcn_peer_export(void* ptr, unsigned char* handle64_host) {
+    TGCN_REQUIRE(ptr && handle64_host, "tgcn_peer_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_export: %s", cudaGetErrorString(e));
+    memcpy(handle64_host, &h, 64);
+    return TGCN_OK;
+}
+
+extern "C" int tgcn_peer_import(const unsigned char* handle64_host, void** ptr_out) {
+    TGCN_REQUIRE(handle64_host && ptr_out, "tgcn_peer_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_import: %s", cudaGetErrorString(e));
+    *ptr_out = p;
+    return TGCN_OK;
+}
+
+extern "C" int tgcn_peer_close(void* ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_peer_close: %s", cudaGetErrorString(e));
+    return TGCN_OK;
+}
+
+// bytes of one rank's region for n gradient elements in nseg tensors (each padded to 4 elements): two flat
+// buffers + the flag line
+extern "C" int64_t tgcn_peer_region_bytes(int64_t n, int nseg) {
+    return (n < 0 || nseg < 0) ? 0 : 2 * (n + 3 * (int64_t)nseg) * (int64_t)sizeof(float) + 256;
+}
+
+// One data-parallel optimizer step.  regions_host[r]: rank r's region base as seen from THIS process (own region
+// for r == rank); grads/params/moms/numels: nseg host arrays describing the parameter tensors in a fixed order
+// (identical on every rank); state: device buffer of 4 uint32 owned by this rank (step counter, block counters).
+extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int rank, const float* const* grads_host,
+                                       float* const* params_host, float* const* moms_host, const int64_t* numels_host,
+                                       int nseg, float lr, float momentum, unsigned int* state, void* stream) {
+    TGCN_REQUIRE(regions_host && grads_host && params_host && moms_host && numels_host && state, "tgcn_peer_allreduce_sgd: null pointer");
+    TGCN_SUPPORTED(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "tgcn_peer_allreduce_sgd: world %d rank %d", world, rank);
+    TGCN_SUPPORTED(nseg >= 1 && nseg <= kPeerMaxSeg, "tgcn_peer_allreduce_sgd: %d parameter tensors (max %d)", nseg, kPeerMaxSeg);
+    PeerSegs segs{};
+    segs.nseg = nseg;
+    int64_t n = 0;
+    for (int s = 0; s < nseg; ++s) {
+        TGCN_REQUIRE(params_host[s] && moms_host[s] && numels_host[s] >= 0, "tgcn_peer_allreduce_sgd: bad segment %d", s);
+        segs.grad[s] = grads_host[s]; segs.param[s] = params_host[s]; segs.mom[s] = moms_host[s];
+        segs.off[s] = n;
+        segs.len[s] = numels_host[s];
+        n += (numels_host[s] + 3) & ~(int64_t)3;
+        TGCN_REQUIRE(aligned16(params_host[s]) && aligned16(moms_host[s]) && (!grads_host[s] || aligned16(grads_host[s])),
+                     "tgcn_peer_allreduce_sgd: segment %d is not 16-byte aligned", s);
+    }
+    segs.off[nseg] = n;
+    PeerRanks ranks{};
+    ranks.world = world; ranks.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        TGCN_REQUIRE(regions_host[r], "tgcn_peer_allreduce_sgd: null region for rank %d", r);
+        ranks.flat[r] = reinterpret_cast<const float*>(regions_host[r]);
+        ranks.flag[r] = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(regions_host[r]) + 2 * n * sizeof(float));
+    }
+    float* my_flat = reinterpret_cast<float*>(regions_host[rank]);
+    unsigned int* my_flag = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[rank]) + 2 * n * sizeof(float));
+    cudaStream_t st = as_stream(stream);
+    const int blocks = (int)min64(ceil_div(n > 0 ? n / 4 : 1, 256), (int64_t)kNumSMs * 8);
+    peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, my_flat, n, my_flag, state, state + 1);
+    TGCN_LAUNCH_CHECK("peer_pack");
+    peer_reduce_sgd_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);
+    TGCN_LAUNCH_CHECK("peer_reduce_sgd");
+    return TGCN_OK;
+}

@@ -138,6 +138,76 @@ class GradientBucket:
             p.grad = v
 
 
+class PeerAllreduceSGD:
+    """Data-parallel optimizer step as ONE fused operation over NVLink peer memory (csrc/peer.cu): pack the local
+    gradients into this rank's IPC-shared region, then read every rank's gradients with P2P loads, average them in
+    rank order and apply SGD with momentum -- two launches, no NCCL, no averaged-gradient tensor.  Semantics of
+    `torch.optim.SGD(params, lr, momentum)` (no weight decay / dampening / nesterov), with the gradient averaged
+    over the ranks; replicas stay bit-identical.  Single node, world <= 8.  CUDA-graph capturable."""
+
+    def __init__(self, params, lr, momentum=0.0, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self._ct = ctypes
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.momentum = float(lr), float(momentum)
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        dev = self.params[0].device
+        self.device = dev
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev or not p.is_contiguous():
+                raise ValueError("PeerAllreduceSGD needs contiguous fp32 parameters on one CUDA device")
+        self.n = sum(p.numel() for p in self.params)
+        self.moms = [torch.zeros_like(p) for p in self.params]
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        nbytes = int(self.lib.tgcn_peer_region_bytes(self.n, len(self.params)))
+        own = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.tgcn_peer_alloc(nbytes, ctypes.byref(own)), "tgcn_peer_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(self.lib.tgcn_peer_export(own, handle), "tgcn_peer_export")
+            handles = [bytes(handle)]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self.regions = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.regions.append(own.value)
+                else:
+                    ptr = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                    _lib.check(self.lib.tgcn_peer_import(buf, ctypes.byref(ptr)), "tgcn_peer_import")
+                    self.regions.append(ptr.value)
+        if self.world > 1:
+            dist.barrier(group=group)
+        self._regions_c = (ctypes.c_void_p * self.world)(*self.regions)
+        self._numels_c = (ctypes.c_int64 * len(self.params))(*[p.numel() for p in self.params])
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self):
+        from . import _lib
+        ct = self._ct
+        k = len(self.params)
+        grads = (ct.c_void_p * k)(*[None if p.grad is None else p.grad.contiguous().data_ptr() for p in self.params])
+        prms = (ct.c_void_p * k)(*[p.data_ptr() for p in self.params])
+        moms = (ct.c_void_p * k)(*[m.data_ptr() for m in self.moms])
+        with torch.cuda.device(self.device):
+            rc = self.lib.tgcn_peer_allreduce_sgd(self._regions_c, self.world, self.rank, grads, prms, moms, self._numels_c, k,
+                                                  self.lr, self.momentum, self.state.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "tgcn_peer_allreduce_sgd")
+
+
 def broadcast_parameters(module, src=0, group=None):
     """Replicate rank `src`'s parameters and buffers (what DataParallel's replicate does per step,
     done once here)."""

@@ -134,7 +134,9 @@ class NetTGCN_HCP(nn.Module):
         # the fused head is a latency optimisation for small dense tails (parcellation-sized graphs); a large fc1
         # (cortical mesh: 167 424 x 200) is a bandwidth-bound GEMM and stays with cuBLAS
         small = self.fc1.in_features * self.fc1.out_features <= (1 << 21)
-        if self.fused_head and small and x.is_cuda and (self.training and x.shape[0] > 1 or not self.training):
+        # (its backward covers training-mode batch statistics; evaluation mode is fused for inference only)
+        usable = (self.training and x.shape[0] > 1) or (not self.training and not torch.is_grad_enabled())
+        if self.fused_head and small and x.is_cuda and usable:
             from .nn.head import fused_head
             return fused_head(x, self.fc1, self.dense1_bn, self.fc2)
         x = F.relu(self.dense1_bn(self.fc1(x)))
