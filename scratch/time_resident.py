@@ -38,7 +38,7 @@ def run(name, L, Q, D, G, K, bias_mode, need_dx, pool_p=4, reps=30):
         b.record(); b.synchronize()
         print("%-10s %s Q=%d N=%d D=%d G=%d nnz=%d: %.1f us" % (name, nm, Q, N, D, G, plan.nnz, a.elapsed_time(b) / reps * 1e3), flush=True)
 Q = int(os.environ.get("Q", "64"))
-run("hcp-L1", Ls[0], Q, 15, 32, 10, 1, False)
-run("hcp-L2", Ls[2], Q, 32, 64, 10, 2, True)
+run("hcp-L1", Ls[0], Q, 15, 32, int(os.environ.get("KK", "10")), 1, False)
+run("hcp-L2", Ls[2], Q, 32, 64, int(os.environ.get("KK", "10")), 2, True)
 g2, p2, Lm, nr = wl.mnist_grid()
 run("mnist-L1", Lm[0], 100, 12, 15, 10, 1, False, pool_p=2)
