@@ -290,7 +290,7 @@ def run_b200(args):
     ms_warm = a.elapsed_time(b)
     clocks = sampler.stop() if rank == 0 else None
 
-    roof = measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf) if rank == 0 else None
+    roof = measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf) if (rank == 0 and not args.no_roofline) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_throughput(args.workload, Ls, perm, n_real, cfg, budget_s=args.cpu_budget)
@@ -645,6 +645,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tcgen05"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the separate roofline timing loop (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--rgg-n", type=int, default=1_000_000, help="vertices of the rgg1m workload")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="gradient exchange for N > 1")
