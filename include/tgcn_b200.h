@@ -72,11 +72,12 @@ int tgcn_set_tuning(const char* key, int value);
 /* For graphs with locality in their row order (meshes in coarsening order), tgcn_spmm_step and everything
  * built on it stage the DISTINCT source rows of each block of RB consecutive rows in shared memory by bulk
  * copies and gather from there ("SPMM_STAGED" tuning key, on by default whenever a plan is registered).
- * tgcn_block_plan_host computes the plan arrays on the host (blk_rows_host == NULL: size query); upload
+ * tgcn_block_plan_host computes the plan arrays on the host (blk_rows_host == NULL: size query; at most `cap`
+ * rows are staged per block, the remaining entries are gathered from global memory); upload
  * them and register them with tgcn_plan_create, keyed by the device address of the CSR `col` array they
  * belong to.  The arrays stay owned by the caller and must outlive the plan.  Results are bit-identical
  * with and without a plan. */
-int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB,
+int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB, int cap,
                              int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host);
 int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
                          const uint16_t* lcol_dev, int RB, int maxd);

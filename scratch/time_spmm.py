@@ -8,7 +8,7 @@ def run(name, L, C, K=5, reps=5):
     plan = build_csr(L, dev)
     N = plan.n
     if os.environ.get("STAGED"):
-        info = plan.ensure_block_plans(rows_per_block=int(os.environ["STAGED"]))
+        info = plan.ensure_block_plans(rows_per_block=int(os.environ["STAGED"]), cap=int(os.environ.get("CAP", "65534")))
         print("block plans:", [i[2] for i in info], flush=True)
     stack = torch.randn(K, N, C, device=dev)
     def steps():

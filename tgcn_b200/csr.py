@@ -33,7 +33,7 @@ class LaplacianCSR:
                                (self.rowptr, self.col, self.val, self.rowptr_t, self.col_t, self.val_t))
         return self._host
 
-    def ensure_block_plans(self, rows_per_block=16, min_gain=1.3):
+    def ensure_block_plans(self, rows_per_block=16, min_gain=1.3, cap=65534):
         """Row-block plans for the streaming SpMM kernels (include/tgcn_b200.h, tgcn_plan_create): built once
         per device for L (and L^T when it differs) and registered with the library when the graph's row order
         has enough locality (gathers / distinct source rows per block >= min_gain).  Idempotent."""
@@ -57,7 +57,7 @@ class LaplacianCSR:
                 blk_rows = np.zeros(max(c.size, 1), dtype=np.int32)
                 lcol = np.zeros(max(c.size, 1), dtype=np.uint16)
                 maxd = np.zeros(1, dtype=np.int32)
-                total = int(lib.tgcn_block_plan_host(rp.ctypes.data, c.ctypes.data, self.n, rows_per_block, blk_ptr.ctypes.data,
+                total = int(lib.tgcn_block_plan_host(rp.ctypes.data, c.ctypes.data, self.n, rows_per_block, cap, blk_ptr.ctypes.data,
                                                      blk_rows.ctypes.data, lcol.ctypes.data, maxd.ctypes.data))
                 if total <= 0 or c.size / total < min_gain:
                     continue

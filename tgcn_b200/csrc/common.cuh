@@ -21,10 +21,28 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 void count_launch();
 
 // Run-time tuning knobs (tgcn_set_tuning / environment TGCN_<NAME> read once); -1 = built-in default.
-enum TuneKey { kTuneSpmmTile = 0, kTuneSpmmPipe = 1, kTuneSpmmStaged = 2, kTuneResTc = 3, kTuneResEnt = 4, kTuneCount = 5 };
+enum TuneKey { kTuneSpmmTile = 0, kTuneSpmmPipe = 1, kTuneSpmmStaged = 2, kTuneResTc = 3, kTuneResEnt = 4, kTuneSpmmWarpRow = 5, kTuneCount = 6 };
 int tuning_value(int key);
 
 }  // namespace tgcn
+
+// acc += w * x on a float4 as TWO packed FFMA2 instructions (Blackwell fma.rn.f32x2: two IEEE fp32 fused
+// multiply-adds per issue slot, bit-identical to four scalar fmaf) -- the gather kernels are issue-bound, not
+// bandwidth-bound, so halving the FMA instruction count is what buys throughput.
+#ifdef __CUDACC__
+__device__ __forceinline__ void fma4_packed(float4& acc, float w, const float4& x) {
+    unsigned long long a01, a23, x01, x23, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "f"(acc.z), "f"(acc.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x01) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x23) : "f"(x.z), "f"(x.w));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a01) : "l"(ww), "l"(x01));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a23) : "l"(ww), "l"(x23));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a23));
+}
+#endif
 
 #define TGCN_REQUIRE(cond, ...)                                            \
     do {                                                                   \

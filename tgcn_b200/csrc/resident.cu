@@ -40,12 +40,7 @@ __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int round_up2(int v) { return (v + 1) & ~1; }
 __host__ __device__ inline int round_up16(int v) { return (v + 15) & ~15; }
 
-__device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) {
-    acc.x = fmaf(w, x.x, acc.x);
-    acc.y = fmaf(w, x.y, acc.y);
-    acc.z = fmaf(w, x.z, acc.z);
-    acc.w = fmaf(w, x.w, acc.w);
-}
+__device__ __forceinline__ void fma4s(float4& acc, float w, const float4& x) { fma4_packed(acc, w, x); }
 
 // ------------------------------------------------------------------------------------------------
 // weight images: Wm[j][d][g] ([K][DP][GP], zero padded) = W'_j of the reference recursion

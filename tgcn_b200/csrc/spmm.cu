@@ -5,6 +5,7 @@
 // (a neighbour row is C*4 contiguous bytes), CSR (col,val) pairs are warp-broadcast loads that
 // stay in L1, the axpy with T_{k-2} is fused so every slab is written exactly once.
 #include <algorithm>
+#include <utility>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -69,12 +70,7 @@ static int swap_axes(const float* in, float* out, int A, int B, int D, cudaStrea
 // ------------------------------------------------------------------------------------------------
 // SpMM step
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
-    acc.x = fmaf(w, x.x, acc.x);
-    acc.y = fmaf(w, x.y, acc.y);
-    acc.z = fmaf(w, x.z, acc.z);
-    acc.w = fmaf(w, x.w, acc.w);
-}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) { fma4_packed(acc, w, x); }
 
 // V = C/4 vectors per row; one thread = one float4 of one row.  `prev` may alias `out`.
 template <bool kHasPrev>
@@ -249,6 +245,91 @@ spmm_step_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
     }
 }
 
+// Warp-per-row variant.  In the kernels above every lane re-loads the row's (col, val) pairs (broadcast loads that
+// still occupy the L1 pipe: at 12 entries per row they are 26 of a warp's 38 load instructions).  Here a warp
+// owns whole rows: the lanes load 32 entries of the row with ONE coalesced load each for col and val, the entries
+// are broadcast with shuffles, and the loads that reach memory are only the gathers -- each lane accumulates
+// NV = ceil(V / 32) float4 of the row.  Same summation order as spmm_step_vec4_kernel (full groups of four entries
+// alternate two accumulators, the tail goes to the first): bit-identical.
+template <bool kHasPrev, int NV>
+__global__ void __launch_bounds__(256)
+spmm_step_warprow_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                         const float* __restrict__ val, int N, const float4* __restrict__ in,
+                         const float4* prev, float4* out, int V, float alpha, float beta) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const unsigned full = 0xffffffffu;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < N; row += gridDim.x * wpb) {
+        int e0 = 0, e1 = 0;
+        if (lane < 2) e0 = __ldg(rowptr + row + lane);
+        e1 = __shfl_sync(full, e0, 1);
+        e0 = __shfl_sync(full, e0, 0);
+        const int len = e1 - e0;
+        const int full4 = len & ~3;                         // entries in complete groups of four
+        float4 a0[NV], a1[NV];
+#pragma unroll
+        for (int u = 0; u < NV; ++u) { a0[u] = make_float4(0.f, 0.f, 0.f, 0.f); a1[u] = a0[u]; }
+        for (int base = 0; base < len; base += 32) {
+            const int cnt = min(32, len - base);
+            int mc = 0;
+            float mw = 0.f;
+            if (lane < cnt) { mc = __ldg(col + e0 + base + lane); mw = __ldg(val + e0 + base + lane); }
+            int k = 0;
+            for (; k + 4 <= cnt && base + k + 4 <= full4; k += 4) {
+                int c[4];
+                float w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { c[t] = __shfl_sync(full, mc, k + t); w[t] = __shfl_sync(full, mw, k + t); }
+                float4 x[4][NV];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < NV; ++u)
+                        if (u * 32 + lane < V) x[t][u] = __ldg(in + (int64_t)c[t] * V + u * 32 + lane);
+#pragma unroll
+                for (int u = 0; u < NV; ++u)
+                    if (u * 32 + lane < V) {
+                        fma4(a0[u], w[0], x[0][u]);
+                        fma4(a1[u], w[1], x[1][u]);
+                        fma4(a0[u], w[2], x[2][u]);
+                        fma4(a1[u], w[3], x[3][u]);
+                    }
+            }
+            for (; k < cnt; ++k) {                           // tail of the row (< 4 entries), or a group split by the 32-chunk
+                const int c = __shfl_sync(full, mc, k);
+                const float w = __shfl_sync(full, mw, k);
+                const bool in_full = base + k < full4;       // position inside a complete group: alternate accumulators
+                const bool odd = ((base + k) & 1) != 0;
+#pragma unroll
+                for (int u = 0; u < NV; ++u)
+                    if (u * 32 + lane < V) {
+                        const float4 x = __ldg(in + (int64_t)c * V + u * 32 + lane);
+                        if (in_full && odd) fma4(a1[u], w, x); else fma4(a0[u], w, x);
+                    }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int v = u * 32 + lane;
+            if (v >= V) continue;
+            float4 r;
+            r.x = alpha * (a0[u].x + a1[u].x);
+            r.y = alpha * (a0[u].y + a1[u].y);
+            r.z = alpha * (a0[u].z + a1[u].z);
+            r.w = alpha * (a0[u].w + a1[u].w);
+            const int64_t idx = (int64_t)row * V + v;
+            if (kHasPrev) {
+                const float4 q = prev[idx];
+                r.x = fmaf(beta, q.x, r.x);
+                r.y = fmaf(beta, q.y, r.y);
+                r.z = fmaf(beta, q.z, r.z);
+                r.w = fmaf(beta, q.w, r.w);
+            }
+            out[idx] = r;
+        }
+    }
+}
+
 // Row-block staged variant (graphs with locality, e.g. the coarsening order of a mesh: siblings, cousins, ...
 // are consecutive rows).  A block owns RB consecutive rows; the DISTINCT source rows its entries reference
 // (precomputed on the host: tgcn_block_plan_host) are copied once into shared memory by 1-D bulk copies
@@ -256,7 +337,7 @@ spmm_step_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
 // memory through block-local column ids.  L2 -> SM traffic drops from nnz/N slabs to (distinct rows per
 // block)/RB slabs per step (mesh32k: 4.66 -> 1.87).  Same per-row summation order: bit-identical results.
 struct StagedParams {
-    const int* rowptr; const unsigned short* lcol; const float* val;
+    const int* rowptr; const unsigned short* lcol; const float* val; const int* col;
     const int* blk_ptr; const int* blk_rows;
     const float4* in; const float4* prev; float4* out;
     int N, RB, V, SW;          // SW = float4 per staged row (column strip width)
@@ -293,16 +374,21 @@ spmm_step_staged_kernel(const StagedParams p) {
         int e = __ldg(p.rowptr + row);
         const int e1 = __ldg(p.rowptr + row + 1);
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        // local id 0xFFFF: the source row was not among the block's staged rows (plan cap): gather it from global memory
+        auto fetch = [&](int ee) -> float4 {
+            const int lc = __ldg(p.lcol + ee);
+            if (lc != 0xFFFF) return stage[lc * p.SW + v];
+            return __ldg(p.in + (int64_t)__ldg(p.col + ee) * p.V + s0 + v);
+        };
         for (; e + 4 <= e1; e += 4) {
-            const int c0 = __ldg(p.lcol + e), c1 = __ldg(p.lcol + e + 1), c2 = __ldg(p.lcol + e + 2), c3 = __ldg(p.lcol + e + 3);
             const float w0 = __ldg(p.val + e), w1 = __ldg(p.val + e + 1), w2 = __ldg(p.val + e + 2), w3 = __ldg(p.val + e + 3);
-            const float4 x0 = stage[c0 * p.SW + v], x1 = stage[c1 * p.SW + v], x2 = stage[c2 * p.SW + v], x3 = stage[c3 * p.SW + v];
+            const float4 x0 = fetch(e), x1 = fetch(e + 1), x2 = fetch(e + 2), x3 = fetch(e + 3);
             fma4(acc0, w0, x0);
             fma4(acc1, w1, x1);
             fma4(acc0, w2, x2);
             fma4(acc1, w3, x3);
         }
-        for (; e < e1; ++e) fma4(acc0, __ldg(p.val + e), stage[(int)__ldg(p.lcol + e) * p.SW + v]);
+        for (; e < e1; ++e) fma4(acc0, __ldg(p.val + e), fetch(e));
         float4 r4;
         r4.x = p.alpha * (acc0.x + acc1.x);
         r4.y = p.alpha * (acc0.y + acc1.y);
@@ -363,7 +449,7 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         const int SW = V <= 64 ? V : 64;
         const size_t smem = 16 + (size_t)bp.maxd * SW * 16;
         if (smem <= 160 * 1024 && ceil_div(V, SW) <= 65535) {
-            StagedParams sp{rowptr, bp.lcol, val, bp.blk_ptr, bp.blk_rows, (const float4*)in, (const float4*)prev, (float4*)out,
+            StagedParams sp{rowptr, bp.lcol, val, col, bp.blk_ptr, bp.blk_rows, (const float4*)in, (const float4*)prev, (float4*)out,
                             N, bp.RB, V, SW, alpha, beta};
             const dim3 grid((unsigned)ceil_div(N, bp.RB), (unsigned)ceil_div(V, SW));
             auto kern = prev ? spmm_step_staged_kernel<true> : spmm_step_staged_kernel<false>;
@@ -375,6 +461,25 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
         }
+    }
+    const int warprow = tuning_value(kTuneSpmmWarpRow);       // blocks per SM of the warp-per-row kernel (0 = off)
+    if (vec && warprow > 0 && C / 4 <= 128) {
+        const int V = (int)(C / 4);
+        const int NV = (V + 31) / 32;
+        int64_t blocks = (int64_t)kNumSMs * warprow;
+        const int64_t need = ceil_div(N, 8);
+        if (blocks > need) blocks = need;
+#define TGCN_SPMM_WR(NVV)                                                                                           \
+        do {                                                                                                        \
+            if (prev) spmm_step_warprow_kernel<true, NVV><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
+                                                                                           (const float4*)prev, (float4*)out, V, alpha, beta); \
+            else spmm_step_warprow_kernel<false, NVV><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
+                                                                                        (float4*)out, V, alpha, beta); \
+        } while (0)
+        if (NV == 1) TGCN_SPMM_WR(1); else if (NV == 2) TGCN_SPMM_WR(2); else if (NV == 3) TGCN_SPMM_WR(3); else TGCN_SPMM_WR(4);
+#undef TGCN_SPMM_WR
+        TGCN_LAUNCH_CHECK("spmm_step");
+        return TGCN_OK;
     }
     const int tile_rb = tuning_value(kTuneSpmmTile);
     const int pipe_bps = tuning_value(kTuneSpmmPipe);      // blocks per SM of the persistent kernel (0 = off)
@@ -470,29 +575,43 @@ using namespace tgcn;
 
 // Host-side: distinct source rows per block of RB consecutive rows and block-local column ids.
 // blk_ptr_host[nb+1]; blk_rows_host: capacity = nnz (NULL: size query, returns the total); lcol_host[nnz].
-// Returns the total number of distinct (block, source row) pairs, or -1 (bad arguments / a block references
-// more than 65535 distinct rows).  *maxd_host receives the largest per-block count.
-extern "C" int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB,
+// At most `cap` rows are staged per block (the most referenced ones); entries whose source row is not staged get
+// the local id 0xFFFF and are gathered from global memory by the kernel.  Returns the total number of staged
+// (block, source row) pairs, or -1 on bad arguments.  *maxd_host receives the largest per-block count (<= cap).
+extern "C" int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB, int cap,
                                         int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host) {
-    if (N < 0 || RB < 1 || !rowptr_host) return -1;
+    if (N < 0 || RB < 1 || !rowptr_host || cap < 1 || cap > 65534) return -1;
     const int nb = (int)ceil_div(N, RB);
     int64_t total = 0;
     int maxd = 0;
-    std::vector<int32_t> tmp;
+    std::vector<int32_t> tmp, keep;
+    std::vector<std::pair<int32_t, int32_t>> cnt;
     for (int b = 0; b < nb; ++b) {
         const int r0 = b * RB, r1 = (int)min64((int64_t)N, (int64_t)r0 + RB);
         const int e0 = rowptr_host[r0], e1 = rowptr_host[r1];
         tmp.assign(col_host + e0, col_host + e1);
         std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        if (tmp.size() > 65535) return -1;
+        // distinct source rows with their reference counts; when there are more than `cap`, the most referenced stay
+        cnt.clear();
+        for (size_t i = 0; i < tmp.size();) {
+            size_t j = i;
+            while (j < tmp.size() && tmp[j] == tmp[i]) ++j;
+            cnt.push_back({-(int32_t)(j - i), tmp[i]});
+            i = j;
+        }
+        if ((int)cnt.size() > cap) { std::sort(cnt.begin(), cnt.end()); cnt.resize(cap); }
+        keep.clear();
+        for (const auto& c : cnt) keep.push_back(c.second);
+        std::sort(keep.begin(), keep.end());
         if (blk_ptr_host) blk_ptr_host[b] = (int32_t)total;
-        if (blk_rows_host) std::copy(tmp.begin(), tmp.end(), blk_rows_host + total);
+        if (blk_rows_host) std::copy(keep.begin(), keep.end(), blk_rows_host + total);
         if (lcol_host)
-            for (int e = e0; e < e1; ++e)
-                lcol_host[e] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), col_host[e]) - tmp.begin());
-        total += (int64_t)tmp.size();
-        if ((int)tmp.size() > maxd) maxd = (int)tmp.size();
+            for (int e = e0; e < e1; ++e) {
+                const auto it = std::lower_bound(keep.begin(), keep.end(), col_host[e]);
+                lcol_host[e] = (it != keep.end() && *it == col_host[e]) ? (uint16_t)(it - keep.begin()) : (uint16_t)0xFFFF;
+            }
+        total += (int64_t)keep.size();
+        if ((int)keep.size() > maxd) maxd = (int)keep.size();
     }
     if (blk_ptr_host) blk_ptr_host[nb] = (int32_t)total;
     if (maxd_host) *maxd_host = maxd;

@@ -75,13 +75,37 @@ def cortical_mesh(n_real=32492, levels=4, seed=0):
     return _coarsened_laplacians(A, levels, seed) + (n_real,)
 
 
-def random_geometric(n=1_000_000, mean_degree=12.0, seed=0):
-    """Config 4: points uniform in the unit square sorted by x (strip partition friendly), edges
-    within r = sqrt(mean_degree / (pi n)), Gaussian weights; no coarsening.  Returns L~ (CSR)."""
+def _morton2(ix, iy):
+    """Interleave the bits of two uint32 arrays (Z-order code)."""
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0xFFFFFFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+    return spread(ix) | (spread(iy) << np.uint64(1))
+
+
+def random_geometric(n=1_000_000, mean_degree=12.0, seed=0, order="strip-morton", strips=8):
+    """Config 4: points uniform in the unit square, edges within r = sqrt(mean_degree / (pi n)), Gaussian weights;
+    no coarsening.  Returns L~ (CSR) and the points in vertex order.
+
+    Vertex order ("sorted by x (strip partition) or Morton order"): `strips` vertical strips of equal
+    population in x order -- so a contiguous row partition over <= `strips` ranks is a strip partition with thin
+    halos -- and Z-order (Morton) inside each strip, so that consecutive rows are spatial neighbours and share most
+    of their gathered rows.  order="x" keeps the plain x sort."""
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(seed)
     pts = rng.random((n, 2))
-    pts = pts[np.argsort(pts[:, 0])]
+    pts = pts[np.argsort(pts[:, 0], kind="stable")]
+    if order == "strip-morton":
+        strip = (np.arange(n) * strips) // n                      # equal-population strips of the x-sorted points
+        code = _morton2((pts[:, 0] * 65535).astype(np.uint32), (pts[:, 1] * 65535).astype(np.uint32))
+        pts = pts[np.lexsort((code, strip))]
+    elif order != "x":
+        raise ValueError(order)
     r = math.sqrt(mean_degree / (math.pi * n))
     pairs = cKDTree(pts).query_pairs(r, output_type='ndarray')
     d = np.linalg.norm(pts[pairs[:, 0]] - pts[pairs[:, 1]], axis=1)
