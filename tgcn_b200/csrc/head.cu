@@ -14,7 +14,7 @@
 
 namespace tgcn {
 
-constexpr int kHeadFB = 4;        // hidden features per CTA in head_fwd1 / head_bwd1
+constexpr int kHeadFB = 2;        // hidden features per CTA in head_fwd1 / head_bwd1
 constexpr int kHeadThreads = 256;
 constexpr int kHeadFwd1Threads = 512;
 
