@@ -148,8 +148,10 @@ def run_b200(args):
     # whose allreduce runs under the layer-1 backward
     # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
     # --dp nccl: two-bucket NCCL allreduce overlapped with the layer-1 backward + torch's fused SGD
-    use_peer = world > 1 and args.dp == "peer"
-    if use_peer:
+    use_peer = args.dp == "peer"
+    if use_peer and world == 1:
+        opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)     # world 1: one fused update launch
+    elif use_peer:
         # collective decision: if CUDA IPC is unavailable on any rank, every rank falls back to the NCCL path
         try:
             opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)
@@ -304,8 +306,9 @@ def run_b200(args):
             "config": {"workload": args.workload, "description": cfg["desc"], "per_gpu_batch": Q, "global_batch": world * Q,
                        "N_padded": [int(L.shape[0]) for L in Ls], "nnz_L0": int(Ls[0].nnz), "K": 10, "H": H,
                        "parallelism": "dp%d" % world, "engine": args.engine,
-                       "gradient_exchange": ("peer-memory allreduce fused with SGD (NVLink P2P loads)" if use_peer else
-                                             "NCCL allreduce, 2 buckets" if world > 1 else "none"),
+                       "gradient_exchange": ("none" if world == 1 else
+                                             "peer-memory allreduce fused with SGD (NVLink P2P loads)" if use_peer else
+                                             "NCCL allreduce, 2 buckets"),
                        "l2": "flushed between timed steps (256 MB write)" if flush else "working set exceeds L2 (K-slab stack > 126 MB)",
                        "cuda_graph": use_graph,
                        "e2e_pipeline": "batch i+1 is uploaded (pinned host -> device, copy stream) while step i runs; the loss is read back and synchronised every step"},

@@ -116,17 +116,41 @@ head_fwd1_kernel(const float* __restrict__ x, const float* __restrict__ W1, cons
     }
 }
 
-// one warp per sample: logits = act W2^T + b2, log_softmax
+// one warp per sample: logits = act W2^T + b2, log_softmax.  The sample's activation row is read once into
+// registers (all loads independent), then dotted with the C rows of W2.
+constexpr int kHeadActRegs = 8;           // 32 lanes x 8 = 256 hidden units per pass
 __global__ void __launch_bounds__(kHeadThreads)
 head_fwd2_kernel(const float* __restrict__ act, const float* __restrict__ W2, const float* __restrict__ b2,
                  float* __restrict__ logp, int Q, int Hd, int C) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= Q) return;
     float mine = 0.f;                                // lane c (< 32) keeps logit c
-    for (int c = 0; c < C; ++c) {
-        float s = 0.f;
-        for (int f = lane; f < Hd; f += 32) s = fmaf(__ldg(act + (int64_t)q * Hd + f), __ldg(W2 + (int64_t)c * Hd + f), s);
-        s = warp_sum(s) + (b2 ? __ldg(b2 + c) : 0.f);
+    float part[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) part[c] = 0.f;
+    for (int f0 = 0; f0 < Hd; f0 += 32 * kHeadActRegs) {
+        float a[kHeadActRegs];
+#pragma unroll
+        for (int u = 0; u < kHeadActRegs; ++u) {
+            const int f = f0 + u * 32 + lane;
+            a[u] = f < Hd ? __ldg(act + (int64_t)q * Hd + f) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (c >= C) break;
+            float s = 0.f;
+#pragma unroll
+            for (int u = 0; u < kHeadActRegs; ++u) {
+                const int f = f0 + u * 32 + lane;
+                if (f < Hd) s = fmaf(a[u], __ldg(W2 + (int64_t)c * Hd + f), s);
+            }
+            part[c] += s;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        if (c >= C) break;
+        const float s = warp_sum(part[c]) + (b2 ? __ldg(b2 + c) : 0.f);
         if (lane == c) mine = s;
     }
     float m = lane < C ? mine : -INFINITY;
@@ -198,7 +222,7 @@ head_bwd1_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp
 // column blocks of CB input features: dW1[:, cols] = dh^T x[:, cols];  dx[:, cols] = dh W1[:, cols].
 // dh, the x columns and the W1 columns are staged in shared memory; register tiles of 4 hidden features (dW1) and
 // 4 samples x 4 hidden features per step (dx) keep the shared-memory traffic at ~0.5 loads per FMA.
-constexpr int kHeadCB = 32;
+constexpr int kHeadCB = 16;
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd2_kernel(const float* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ W1,
                  float* __restrict__ dW1, float* __restrict__ dx, int Q, int I, int Hd, int HdP) {
@@ -217,15 +241,15 @@ head_bwd2_kernel(const float* __restrict__ dh, const float* __restrict__ x, cons
         if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
         __syncthreads();
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)Q * Hd * 4u + (uint32_t)Q * 128u + (dx ? (uint32_t)Hd * 128u : 0u);
+            const uint32_t bytes = (uint32_t)Q * Hd * 4u + (uint32_t)Q * (kHeadCB * 4u) + (dx ? (uint32_t)Hd * (kHeadCB * 4u) : 0u);
             tc::mbar_arrive_expect_tx(&bar, bytes);
             tc::bulk_g2s(dhs, dh, (uint32_t)Q * Hd * 4u, &bar);
         }
         __syncthreads();
         const int nrows = Q + (dx ? Hd : 0);
         for (int r = tid; r < nrows; r += T) {
-            if (r < Q) tc::bulk_g2s(xs + r * kHeadCB, x + (int64_t)r * I + i0, 128u, &bar);
-            else tc::bulk_g2s(ws + (r - Q) * kHeadCB, W1 + (int64_t)(r - Q) * I + i0, 128u, &bar);
+            if (r < Q) tc::bulk_g2s(xs + r * kHeadCB, x + (int64_t)r * I + i0, kHeadCB * 4u, &bar);
+            else tc::bulk_g2s(ws + (r - Q) * kHeadCB, W1 + (int64_t)(r - Q) * I + i0, kHeadCB * 4u, &bar);
         }
         tc::mbar_wait(&bar, 0);
     } else {
@@ -303,7 +327,7 @@ extern "C" int tgcn_head_fwd(const float* x, const float* W1, const float* b1, c
     head_fwd1_kernel<<<(unsigned)ceil_div(Hd, kHeadFB), kHeadFwd1Threads, smem, st>>>(x, W1, b1, gamma, beta, running_mean, running_var,
                                                                                  momentum, eps, training, act, xhat, invstd, Q, I, Hd);
     TGCN_LAUNCH_CHECK("head_fwd1");
-    head_fwd2_kernel<<<(unsigned)ceil_div(Q, kHeadThreads / 32), kHeadThreads, 0, st>>>(act, W2, b2, logp, Q, Hd, C);
+    head_fwd2_kernel<<<(unsigned)ceil_div(Q, 2), 64, 0, st>>>(act, W2, b2, logp, Q, Hd, C);
     TGCN_LAUNCH_CHECK("head_fwd2");
     return TGCN_OK;
 }

@@ -152,6 +152,41 @@ peer_reduce_sgd_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, fl
     }
 }
 
+// world == 1: no exchange; the same update read straight from the gradient tensors (one launch)
+__global__ void __launch_bounds__(256)
+sgd_direct_kernel(const PeerSegs segs, int64_t n, float lr, float momentum, unsigned int* step_ctr, unsigned int* done_blocks) {
+    for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 4 * i4;
+        const int s = find_seg(segs, e);
+        const int64_t loc = e - segs.off[s], len = segs.len[s];
+        const float* src = segs.grad[s];
+        float* prm = segs.param[s] + loc;
+        float* mom = segs.mom[s] + loc;
+        if (loc + 4 <= len) {
+            const float4 g = src ? *reinterpret_cast<const float4*>(src + loc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 m = *reinterpret_cast<float4*>(mom), w = *reinterpret_cast<float4*>(prm);
+            m.x = fmaf(momentum, m.x, g.x); m.y = fmaf(momentum, m.y, g.y);
+            m.z = fmaf(momentum, m.z, g.z); m.w = fmaf(momentum, m.w, g.w);
+            w.x = fmaf(-lr, m.x, w.x); w.y = fmaf(-lr, m.y, w.y); w.z = fmaf(-lr, m.z, w.z); w.w = fmaf(-lr, m.w, w.w);
+            *reinterpret_cast<float4*>(mom) = m;
+            *reinterpret_cast<float4*>(prm) = w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (loc + c < len) {
+                    const float bcur = fmaf(momentum, mom[c], src ? src[loc + c] : 0.f);
+                    mom[c] = bcur;
+                    prm[c] = fmaf(-lr, bcur, prm[c]);
+                }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        if (prev == gridDim.x - 1) { *done_blocks = 0u; *step_ctr = *step_ctr + 1u; }
+    }
+}
+
 }  // namespace tgcn
 
 using namespace tgcn;
@@ -241,6 +276,11 @@ extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int
     unsigned int* my_flag = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[rank]) + 2 * n * sizeof(float));
     cudaStream_t st = as_stream(stream);
     const int blocks = (int)min64(ceil_div(n > 0 ? n / 4 : 1, 256), (int64_t)kNumSMs * 8);
+    if (world == 1) {
+        sgd_direct_kernel<<<blocks, 256, 0, st>>>(segs, n, lr, momentum, state, state + 2);
+        TGCN_LAUNCH_CHECK("sgd_direct");
+        return TGCN_OK;
+    }
     peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, my_flat, n, my_flag, state, state + 1);
     TGCN_LAUNCH_CHECK("peer_pack");
     peer_reduce_sgd_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);

@@ -1307,7 +1307,7 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* en
     uint8_t* Wtc = reinterpret_cast<uint8_t*>(wimages + (int64_t)2 * K * pl.DP * pl.GP);
     {
         const int rows_d = pl.DP > 32 ? pl.DP : 32;
-        resident_prep_kernel<<<(unsigned)ceil_div(rows_d * pl.GP16, 256), 256, 0, st>>>(W, Wm, Wt, pl.DP <= 32 ? Wtc : nullptr, K, D, G,
+        resident_prep_kernel<<<(unsigned)ceil_div(rows_d * pl.GP16, 256), 256, 0, st>>>(W, Wm, Wt, pl.tc ? Wtc : nullptr, K, D, G,
                                                                                       pl.DP, pl.GP, pl.GP16, recursion);
     }
     TGCN_LAUNCH_CHECK("resident_prep");
