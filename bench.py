@@ -61,39 +61,111 @@ def build_graph(name):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  The timed region of the small workloads is a
+    few milliseconds, far shorter than one `nvidia-smi` start-up, so the samples come from NVML in a thread of this
+    process (one query is ~0.1 ms and releases the GIL); `nvidia-smi -lms` is only the fall-back when NVML cannot be
+    loaded.  `mark()`/`unmark()` bracket the timed loops: `sm_mhz` is the median of the samples taken inside."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.001):
         self.index = index
+        self.period = period_s
         self.proc = None
+        self.nvml = None
+        self.handle = None
         self.lines = []
+        self.samples = []          # (inside timed region, sm MHz, reason bit mask)
+        self.inside = False
+        self.running = False
+        self.sm_max = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                       # CUDA_VISIBLE_DEVICES may renumber: go through the PCI address of the torch device
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.sm_max = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.inside = True
+
+    def unmark(self):
+        self.inside = False
+
+    def _poll(self):
+        n = self.nvml
+        while self.running:
+            try:
+                inside = self.inside
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((inside and self.inside, mhz, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((self.inside, line.strip()))
 
     def stop(self):
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            n = self.nvml
+            bits = ((n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                    (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (n.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                    (n.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+            inside = [s for s in self.samples if s[0]]
+            use = inside if inside else self.samples
+            reasons = sorted({nm for _, _, m in use for bit, nm in bits if m & bit})
+            sm = [s[1] for s in use]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(inside), "samples_total": len(self.samples), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        sm, mx, reasons, n_in = [], [], set(), 0
+        inside_any = any(i for i, _ in self.lines)
+        for ins, ln in self.lines:
+            if inside_any and not ins:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -101,11 +173,12 @@ class ClockSampler:
                 sm.append(float(parts[0])); mx.append(float(parts[1]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[2:6]):
+            n_in += int(ins)
+            for nm, val in zip(self.NAMES, parts[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": n_in, "samples_total": len(self.lines), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -248,6 +321,7 @@ def run_b200(args):
                 ys[i % 2].copy_(hy[i % n_host], non_blocking=True)
                 copied[i].record(copy_stream)
         barrier()
+        sampler.mark()
         t0 = time.perf_counter()
         for i in range(nsteps):
             if flush:
@@ -268,6 +342,7 @@ def run_b200(args):
                 ev[i][1].synchronize()         # the user reads the loss every step
                 _ = float(loss_host)
         barrier()
+        sampler.unmark()
         wall = time.perf_counter() - t0
         ms = sum(a.elapsed_time(b) for a, b in ev)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -275,11 +350,11 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), wall
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
     ms_total, wall = timed(args.steps, e2e=False)
     ms_e2e, wall_e2e = timed(args.steps, e2e=True)
     # back-to-back (no flush, no per-step events) for reference
@@ -377,6 +452,7 @@ def run_rgg(args):
     def timed(nsteps, e2e):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
         barrier()
+        sampler.mark()
         for i in range(nsteps):
             ev[i][0].record()
             if e2e:
@@ -389,17 +465,18 @@ def run_rgg(args):
                 ev[i][1].synchronize()
                 _ = float(loss_host)
         barrier()
+        sampler.unmark()
         t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    c0 = lib.tgcn_launch_count(); step(); launches = lib.tgcn_launch_count() - c0
-    for _ in range(max(args.warmup, 3) - 1):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    c0 = lib.tgcn_launch_count(); step(); launches = lib.tgcn_launch_count() - c0
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
     ms = timed(args.steps, False)
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
