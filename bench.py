@@ -221,13 +221,17 @@ def run_b200(args):
     # whose allreduce runs under the layer-1 backward
     # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
     # --dp nccl: two-bucket NCCL allreduce overlapped with the layer-1 backward + torch's fused SGD
-    use_peer = args.dp == "peer"
+    use_peer = args.dp in ("peer", "peer-overlap")
+    # the conv layers' gradients come last in the backward: with --dp peer-overlap the head's (large) exchange + update
+    # is launched from autograd hooks on a side stream under the conv backward, only the conv group remains at the end
+    late = [] if args.dp != "peer-overlap" else [p for n_, m in model.named_children() if n_ in ("tgcn1", "gcn2")
+                                                for p in m.parameters()]
     if use_peer and world == 1:
         opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)     # world 1: one fused update launch
     elif use_peer:
         # collective decision: if CUDA IPC is unavailable on any rank, every rank falls back to the NCCL path
         try:
-            opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)
+            opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5, late=late)
             ok = torch.ones(1, device=dev)
         except Exception as exc:                       # noqa: BLE001
             sys.stderr.write("[bench] peer-memory allreduce unavailable on rank %d: %s\n" % (rank, exc))
@@ -382,7 +386,8 @@ def run_b200(args):
                        "N_padded": [int(L.shape[0]) for L in Ls], "nnz_L0": int(Ls[0].nnz), "K": 10, "H": H,
                        "parallelism": "dp%d" % world, "engine": args.engine,
                        "gradient_exchange": ("none" if world == 1 else
-                                             "peer-memory allreduce fused with SGD (NVLink P2P loads)" if use_peer else
+                                             ("peer-memory allreduce fused with SGD (NVLink P2P loads)" +
+                                              ("; head group exchanged under the conv backward" if late else "")) if use_peer else
                                              "NCCL allreduce, 2 buckets"),
                        "l2": "flushed between timed steps (256 MB write)" if flush else "working set exceeds L2 (K-slab stack > 126 MB)",
                        "cuda_graph": use_graph,
@@ -728,7 +733,9 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the separate roofline timing loop (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--rgg-n", type=int, default=1_000_000, help="vertices of the rgg1m workload")
-    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="gradient exchange for N > 1")
+    ap.add_argument("--dp", default="peer", choices=["peer", "peer-overlap", "nccl"],
+                    help="gradient exchange for N > 1: peer = fused peer-memory allreduce+SGD after the backward; peer-overlap = "
+                         "the head group's exchange runs under the conv backward; nccl = bucketed NCCL + torch SGD")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

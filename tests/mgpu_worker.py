@@ -127,6 +127,59 @@ def check_peer_sgd(rank, world, dev):
     return err
 
 
+def check_peer_sgd_overlap(rank, world, dev):
+    """E. `late=`: the early group's exchange + update is launched from autograd hooks on a side stream during the
+    backward, the late group at step(); same result as NCCL-averaged gradients + torch SGD, eager and graph-replayed."""
+    def make():
+        torch.manual_seed(5)
+        return torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.ReLU(), torch.nn.Linear(64, 200),
+                                   torch.nn.ReLU(), torch.nn.Linear(200, 6)).to(dev)
+    ma, mb = make(), make()
+    opt_a = PeerAllreduceSGD(ma.parameters(), lr=0.05, momentum=0.5, late=list(ma[0].parameters()))
+    assert opt_a._early is not None and len(opt_a._main.params) == 2
+    opt_b = torch.optim.SGD(mb.parameters(), lr=0.05, momentum=0.5)
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    xs = [torch.randn(32, 40, device=dev, generator=g) for _ in range(6)]
+    x_static = xs[0].clone()
+
+    def step_a():
+        opt_a.zero_grad(set_to_none=True)
+        ma(x_static).square().mean().backward()
+        opt_a.step()
+
+    def step_b(x):
+        opt_b.zero_grad(set_to_none=True)
+        mb(x).square().mean().backward()
+        for q in mb.parameters():
+            dist.all_reduce(q.grad, op=dist.ReduceOp.AVG)
+        opt_b.step()
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for it in range(3):                                        # eager, hooks fire inside backward
+            x_static.copy_(xs[it]); step_a()
+    torch.cuda.current_stream().wait_stream(s)
+    for it in range(3):
+        step_b(xs[it])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):                                  # the whole step (both groups, fork/join) in one graph
+        step_a()
+    x_static.copy_(xs[3]); torch.cuda.synchronize()
+    # the capture itself does not execute: replay for batches 3..5
+    for it in range(3, 6):
+        x_static.copy_(xs[it]); graph.replay(); step_b(xs[it])
+    torch.cuda.synchronize()
+    err = max(float((p - q).abs().max() / q.abs().max()) for p, q in zip(ma.parameters(), mb.parameters()))
+    assert err < 1e-5, err
+    mine = torch.cat([p.detach().reshape(-1) for p in ma.parameters()])
+    others = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(others, mine)
+    assert all(torch.equal(o, mine) for o in others), "replicas diverged"
+    return err
+
+
 def main():
     rank, world, local = init_distributed("nccl")
     dev = torch.device("cuda", local)
@@ -135,9 +188,11 @@ def main():
     h = check_halo(rank, world, dev)
     h2 = check_partitioned_layer(rank, world, dev)
     pe = check_peer_sgd(rank, world, dev)
+    po = check_peer_sgd_overlap(rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d peer_sgd_err=%.2e" % (world, e, h, h2, pe))
+        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d peer_sgd_err=%.2e peer_overlap_err=%.2e"
+              % (world, e, h, h2, pe, po))
     dist.destroy_process_group()
 
 

@@ -109,7 +109,8 @@ def test_batch_sharding_invariance():
 
 
 @pytest.mark.parametrize("variant", [("SPMM_PIPE", 4), ("SPMM_PIPE", 1), ("SPMM_TILE", 32), ("SPMM_TILE", 16),
-                                     ("SPMM_WARPROW", 8), ("SPMM_WARPROW", 1)])
+                                     ("SPMM_WARPROW", 8), ("SPMM_WARPROW", 1),
+                                     ("SPMM_CSM", 4), ("SPMM_CSM", 8), ("SPMM_CSM", 12)])
 @pytest.mark.parametrize("has_prev", [False, True])
 def test_spmm_variants_are_bit_identical(variant, has_prev):
     """The persistent pipelined and the row-tiled SpMM kernels keep the per-row summation order of the plain
@@ -136,14 +137,56 @@ def test_spmm_variants_are_bit_identical(variant, has_prev):
         return out
     try:
         assert lib.tgcn_set_tuning(b"SPMM_PIPE", 0) == 0 and lib.tgcn_set_tuning(b"SPMM_TILE", 0) == 0
-        assert lib.tgcn_set_tuning(b"SPMM_WARPROW", 0) == 0
+        assert lib.tgcn_set_tuning(b"SPMM_WARPROW", 0) == 0 and lib.tgcn_set_tuning(b"SPMM_CSM", 0) == 0
         base = run()
         assert lib.tgcn_set_tuning(variant[0].encode(), variant[1]) == 0
         got = run()
     finally:
-        lib.tgcn_set_tuning(b"SPMM_PIPE", -1); lib.tgcn_set_tuning(b"SPMM_TILE", -1); lib.tgcn_set_tuning(b"SPMM_WARPROW", -1)
+        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+            lib.tgcn_set_tuning(key, -1)
     assert torch.equal(base, got)
     assert lib.tgcn_set_tuning(b"NOPE", 1) == -1
+
+
+@pytest.mark.parametrize("u", [4, 8, 12])
+@pytest.mark.parametrize("C", [8, 72, 192])
+def test_spmm_staged_csr_dense_rows_fall_back_to_global_entries(u, C):
+    """Staged-CSR kernel on a graph whose row blocks hold more entries than the staging buffer (1536): those blocks
+    read (col, val) from global memory; rows of 0, 1, 2, 3, 5 and ~150 entries; bit-identical to the plain kernel."""
+    from tgcn_b200 import _lib
+    from tgcn_b200.csr import build_csr
+    import scipy.sparse as sp
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    n = 301
+    A = sp.random(n, n, density=0.5, random_state=2, format="lil", dtype=np.float32)
+    for r, k in ((0, 0), (1, 1), (2, 2), (3, 3), (4, 5), (300, 0)):
+        A[r, :] = 0
+        A[r, :k] = 0.5
+    for r in range(200, 264):                # a stretch of short rows: this block IS staged
+        A[r, :] = 0
+        A[r, r % 7:r % 7 + 6] = 0.25
+    plan = build_csr(A.tocsr(), torch.device("cuda"))
+    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    prev = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        out = torch.full((n, C), float("nan"), device="cuda")
+        rc = lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), n, x.data_ptr(),
+                                prev.data_ptr(), out.data_ptr(), C, 2.0, -1.0, st)
+        assert rc == 0, _lib.last_error()
+        return out
+    try:
+        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+            assert lib.tgcn_set_tuning(key, 0) == 0
+        base = run()
+        assert lib.tgcn_set_tuning(b"SPMM_CSM", u) == 0
+        got = run()
+    finally:
+        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+            lib.tgcn_set_tuning(key, -1)
+    assert torch.equal(base, got)
 
 
 @pytest.mark.parametrize("rb,cap", [(4, 65534), (16, 65534), (64, 65534), (16, 12), (32, 3)])   # small caps: global-gather fallback

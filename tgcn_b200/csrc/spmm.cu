@@ -406,6 +406,107 @@ spmm_step_staged_kernel(const StagedParams p) {
     }
 }
 
+// Block-staged CSR variant.  A block owns RB consecutive rows: their (col, val) entries are ONE contiguous run of
+// the CSR arrays, copied into shared memory by coalesced loads (col pre-multiplied by the row pitch and paired with
+// val, so an entry is one 8-byte shared load instead of two global broadcast loads per lane), after which a thread
+// walks its row with up to U gathers in flight and no global round trip between them -- the dependent chain of the
+// plain kernel (row bounds -> entries -> gathers, per batch of four) becomes bounds -> entries (once per block) ->
+// gathers.  Blocks whose entry run exceeds the staging capacity read the entries from global memory instead.
+// Accumulation order per output element is that of spmm_step_vec4_kernel (entries of complete groups of four
+// alternate two accumulators, the tail goes to the first): bit-identical results.
+constexpr int kCsmCap = 1536;      // staged entries per block (12 KB)
+constexpr int kCsmMaxRows = 64;
+
+template <bool kHasPrev, int U, bool kStaged>
+__device__ __forceinline__ void csm_rows(const int2* __restrict__ s_ent, const int* __restrict__ s_rp,
+                                         const int* __restrict__ col, const float* __restrict__ val,
+                                         const float4* __restrict__ in, const float4* prev, float4* out,
+                                         int row0, int rows, int V, float alpha, float beta) {
+    static_assert(U % 2 == 0, "U must be even: entry parity selects the accumulator");
+    const int e_lo = s_rp[0];
+    for (int item = threadIdx.x; item < rows * V; item += blockDim.x) {
+        const int r = item / V, v = item - r * V;
+        const int eb = s_rp[r], cnt = s_rp[r + 1] - eb;
+        const int full4 = cnt & ~3;
+        const int64_t idx = (int64_t)(row0 + r) * V + v;
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kHasPrev) pv = prev[idx];
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        for (int b = 0; b < cnt; b += U) {
+            int off[U];
+            float w[U];
+            float4 x[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                if (b + i < cnt) {
+                    if (kStaged) {
+                        const int2 en = s_ent[eb - e_lo + b + i];
+                        off[i] = en.x; w[i] = __int_as_float(en.y);
+                    } else {
+                        off[i] = __ldg(col + eb + b + i) * V; w[i] = __ldg(val + eb + b + i);
+                    }
+                }
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                if (b + i < cnt) x[i] = __ldg(in + (off[i] + v));
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                if (b + i < cnt) {
+                    if ((i & 1) && b + i < full4) fma4(acc1, w[i], x[i]);
+                    else fma4(acc0, w[i], x[i]);
+                }
+        }
+        float4 r4;
+        r4.x = alpha * (acc0.x + acc1.x);
+        r4.y = alpha * (acc0.y + acc1.y);
+        r4.z = alpha * (acc0.z + acc1.z);
+        r4.w = alpha * (acc0.w + acc1.w);
+        if (kHasPrev) {
+            r4.x = fmaf(beta, pv.x, r4.x);
+            r4.y = fmaf(beta, pv.y, r4.y);
+            r4.z = fmaf(beta, pv.z, r4.z);
+            r4.w = fmaf(beta, pv.w, r4.w);
+        }
+        out[idx] = r4;
+    }
+}
+
+template <bool kHasPrev, int U>
+__global__ void __launch_bounds__(256, (U <= 4 ? 4 : U <= 8 ? 3 : 2))
+spmm_step_csm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                     int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int RB,
+                     float alpha, float beta) {
+    __shared__ int2 s_ent[kCsmCap];
+    __shared__ int s_rp[kCsmMaxRows + 1];
+    const int row0 = blockIdx.x * RB;
+    const int rows = min(RB, N - row0);
+    if ((int)threadIdx.x <= rows) s_rp[threadIdx.x] = __ldg(rowptr + row0 + threadIdx.x);
+    __syncthreads();
+    const int e_lo = s_rp[0], n_ent = s_rp[rows] - e_lo;
+    if (n_ent <= kCsmCap) {
+        for (int i = threadIdx.x; i < n_ent; i += blockDim.x)
+            s_ent[i] = make_int2(__ldg(col + e_lo + i) * V, __float_as_int(__ldg(val + e_lo + i)));
+        __syncthreads();
+        csm_rows<kHasPrev, U, true>(s_ent, s_rp, col, val, in, prev, out, row0, rows, V, alpha, beta);
+    } else {
+        csm_rows<kHasPrev, U, false>(s_ent, s_rp, col, val, in, prev, out, row0, rows, V, alpha, beta);
+    }
+}
+
+// rows per block of the staged-CSR kernel: at most 4 passes of the 256 threads over RB * V items, as full as possible
+static int csm_rows_per_block(int V) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int rb = 1; rb <= kCsmMaxRows; ++rb) {
+        const int64_t items = (int64_t)rb * V;
+        const int64_t passes = ceil_div(items, 256);
+        if (passes > 4 && rb > 1) break;
+        const double eff = (double)items / (double)(passes * 256);
+        if (eff >= best_eff) { best_eff = eff; best = rb; }
+    }
+    return best;
+}
+
 // ---- block-plan registry: plans are created by the host side once per CSR operand and looked up by the
 // device address of its `col` array (the plan's arrays stay owned by the caller)
 struct BlockPlan { const void* key; const int* blk_ptr; const int* blk_rows; const unsigned short* lcol; int RB, maxd, N; bool live; };
@@ -461,6 +562,23 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
         }
+    }
+    const int csm_u = tuning_value(kTuneSpmmCsm);          // gathers in flight per thread of the staged-CSR kernel (0 = off)
+    if (vec && csm_u > 0 && (int64_t)N * (C / 4) < (int64_t)INT32_MAX) {
+        const int V = (int)(C / 4);
+        const int RB = csm_rows_per_block(V);
+        const unsigned blocks = (unsigned)ceil_div(N, RB);
+#define TGCN_SPMM_CSM(UU)                                                                                          \
+        do {                                                                                                       \
+            if (prev) spmm_step_csm_kernel<true, UU><<<blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
+                                                                              (const float4*)prev, (float4*)out, V, RB, alpha, beta); \
+            else spmm_step_csm_kernel<false, UU><<<blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
+                                                                          (float4*)out, V, RB, alpha, beta);          \
+        } while (0)
+        if (csm_u >= 12) TGCN_SPMM_CSM(12); else if (csm_u >= 8) TGCN_SPMM_CSM(8); else TGCN_SPMM_CSM(4);
+#undef TGCN_SPMM_CSM
+        TGCN_LAUNCH_CHECK("spmm_step");
+        return TGCN_OK;
     }
     const int warprow = tuning_value(kTuneSpmmWarpRow);       // blocks per SM of the warp-per-row kernel (0 = off)
     if (vec && warprow > 0 && C / 4 <= 128) {

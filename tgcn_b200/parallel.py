@@ -138,18 +138,75 @@ class GradientBucket:
             p.grad = v
 
 
+class _PeerGroup:
+    """One IPC-shared gradient region (two flat buffers + ready flag, csrc/peer.cu) for a fixed list of parameters,
+    with its own momentum buffers and device-side step counter."""
+
+    def __init__(self, lib, params, world, rank, group):
+        import ctypes
+        from . import _lib
+        self.lib, self._ct = lib, ctypes
+        self.params = params
+        self.world, self.rank = world, rank
+        dev = params[0].device
+        self.device = dev
+        self.n = sum(p.numel() for p in params)
+        self.moms = [torch.zeros_like(p) for p in params]
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        nbytes = int(lib.tgcn_peer_region_bytes(self.n, len(params)))
+        own = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.tgcn_peer_alloc(nbytes, ctypes.byref(own)), "tgcn_peer_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.tgcn_peer_export(own, handle), "tgcn_peer_export")
+            handles = [bytes(handle)]
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self.regions = []
+            for r in range(world):
+                if r == rank:
+                    self.regions.append(own.value)
+                else:
+                    ptr = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                    _lib.check(lib.tgcn_peer_import(buf, ctypes.byref(ptr)), "tgcn_peer_import")
+                    self.regions.append(ptr.value)
+        if world > 1:
+            dist.barrier(group=group)
+        self._regions_c = (ctypes.c_void_p * world)(*self.regions)
+        self._numels_c = (ctypes.c_int64 * len(params))(*[p.numel() for p in params])
+
+    def launch(self, lr, momentum, stream):
+        from . import _lib
+        ct = self._ct
+        k = len(self.params)
+        grads = (ct.c_void_p * k)(*[None if p.grad is None else p.grad.contiguous().data_ptr() for p in self.params])
+        prms = (ct.c_void_p * k)(*[p.data_ptr() for p in self.params])
+        moms = (ct.c_void_p * k)(*[m.data_ptr() for m in self.moms])
+        with torch.cuda.device(self.device):
+            rc = self.lib.tgcn_peer_allreduce_sgd(self._regions_c, self.world, self.rank, grads, prms, moms, self._numels_c, k,
+                                                  lr, momentum, self.state.data_ptr(), stream.cuda_stream)
+        _lib.check(rc, "tgcn_peer_allreduce_sgd")
+
+
 class PeerAllreduceSGD:
     """Data-parallel optimizer step as ONE fused operation over NVLink peer memory (csrc/peer.cu): pack the local
     gradients into this rank's IPC-shared region, then read every rank's gradients with P2P loads, average them in
     rank order and apply SGD with momentum -- two launches, no NCCL, no averaged-gradient tensor.  Semantics of
     `torch.optim.SGD(params, lr, momentum)` (no weight decay / dampening / nesterov), with the gradient averaged
-    over the ranks; replicas stay bit-identical.  Single node, world <= 8.  CUDA-graph capturable."""
+    over the ranks; replicas stay bit-identical.  Single node, world <= 8.  CUDA-graph capturable.
 
-    def __init__(self, params, lr, momentum=0.0, group=None):
-        import ctypes
+    Overlap (`late`, world > 1): the parameters listed in `late` are the ones whose gradients the backward produces
+    LAST (the first layers of the model).  All other parameters form an early group with its own region: as soon as
+    the last of their gradients exists (autograd post-accumulate hooks) their exchange + update is launched on a
+    side stream and runs under the rest of the backward; `step()` then exchanges only the late group and joins the
+    side stream.  Requirement: nothing enqueued after the last early gradient reads an early parameter (true for a
+    feed-forward model whose `late` parameters belong to its first layers)."""
+
+    def __init__(self, params, lr, momentum=0.0, group=None, late=()):
         from . import _lib
         self.lib = _lib.load()
-        self._ct = ctypes
         self.params = [p for p in params if p.requires_grad]
         self.lr, self.momentum = float(lr), float(momentum)
         self.group = group
@@ -160,32 +217,32 @@ class PeerAllreduceSGD:
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev or not p.is_contiguous():
                 raise ValueError("PeerAllreduceSGD needs contiguous fp32 parameters on one CUDA device")
+        late_ids = {id(p) for p in late}
+        early = [p for p in self.params if id(p) not in late_ids]
+        latep = [p for p in self.params if id(p) in late_ids]
+        self._hooks, self._seen, self._launched = [], 0, False
+        if self.world > 1 and early and latep:
+            self._early = _PeerGroup(self.lib, early, self.world, self.rank, group)
+            self._main = _PeerGroup(self.lib, latep, self.world, self.rank, group)
+            self._side = torch.cuda.Stream(device=dev)
+            for p in early:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        else:
+            self._early = None
+            self._main = _PeerGroup(self.lib, self.params, self.world, self.rank, group)
         self.n = sum(p.numel() for p in self.params)
-        self.moms = [torch.zeros_like(p) for p in self.params]
-        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
-        nbytes = int(self.lib.tgcn_peer_region_bytes(self.n, len(self.params)))
-        own = ctypes.c_void_p()
-        with torch.cuda.device(dev):
-            _lib.check(self.lib.tgcn_peer_alloc(nbytes, ctypes.byref(own)), "tgcn_peer_alloc")
-            handle = (ctypes.c_ubyte * 64)()
-            _lib.check(self.lib.tgcn_peer_export(own, handle), "tgcn_peer_export")
-            handles = [bytes(handle)]
-            if self.world > 1:
-                handles = [None] * self.world
-                dist.all_gather_object(handles, bytes(handle), group=group)
-            self.regions = []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.regions.append(own.value)
-                else:
-                    ptr = ctypes.c_void_p()
-                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
-                    _lib.check(self.lib.tgcn_peer_import(buf, ctypes.byref(ptr)), "tgcn_peer_import")
-                    self.regions.append(ptr.value)
-        if self.world > 1:
-            dist.barrier(group=group)
-        self._regions_c = (ctypes.c_void_p * self.world)(*self.regions)
-        self._numels_c = (ctypes.c_int64 * len(self.params))(*[p.numel() for p in self.params])
+
+    @property
+    def moms(self):
+        return (self._early.moms if self._early else []) + self._main.moms
+
+    def _on_grad(self, _param):
+        self._seen += 1
+        if self._seen == len(self._early.params):      # every early gradient exists: exchange + update them now
+            cur = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(cur)
+            self._early.launch(self.lr, self.momentum, self._side)
+            self._launched = True
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -195,17 +252,13 @@ class PeerAllreduceSGD:
                 p.grad.zero_()
 
     def step(self):
-        from . import _lib
-        ct = self._ct
-        k = len(self.params)
-        grads = (ct.c_void_p * k)(*[None if p.grad is None else p.grad.contiguous().data_ptr() for p in self.params])
-        prms = (ct.c_void_p * k)(*[p.data_ptr() for p in self.params])
-        moms = (ct.c_void_p * k)(*[m.data_ptr() for m in self.moms])
-        with torch.cuda.device(self.device):
-            rc = self.lib.tgcn_peer_allreduce_sgd(self._regions_c, self.world, self.rank, grads, prms, moms, self._numels_c, k,
-                                                  self.lr, self.momentum, self.state.data_ptr(),
-                                                  torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(rc, "tgcn_peer_allreduce_sgd")
+        cur = torch.cuda.current_stream(self.device)
+        if self._early is not None and not self._launched:     # gradients were set by hand (no backward): do it here
+            self._early.launch(self.lr, self.momentum, cur)
+        self._main.launch(self.lr, self.momentum, cur)
+        if self._launched:
+            cur.wait_stream(self._side)
+        self._seen, self._launched = 0, False
 
 
 def broadcast_parameters(module, src=0, group=None):
