@@ -7,7 +7,7 @@ lib = _lib.load()
 dev = torch.device("cuda")
 KEYS = (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM", b"SPMM_STAGED")
 VARIANTS = [("plain", {}), ("pipe4", {b"SPMM_PIPE": 4}), ("pipe8", {b"SPMM_PIPE": 8}),
-            ("csm4", {b"SPMM_CSM": 4}), ("csm8", {b"SPMM_CSM": 8}), ("csm12", {b"SPMM_CSM": 12})]
+            ("csm4", {b"SPMM_CSM": 4}), ("csm6", {b"SPMM_CSM": 6}), ("csm8", {b"SPMM_CSM": 8})]
 
 
 def run(name, L, C, K=5, reps=5, has_prev=False):

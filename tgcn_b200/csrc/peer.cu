@@ -4,10 +4,13 @@
 // (reference: torch.nn.DataParallel's gather + optim.SGD.step, pytorch_hcp_tgcn.py:164-169,271-272).  With NCCL that
 // is a multi-tensor copy, an allreduce kernel and an optimizer kernel, ~35 us of mostly launch/latency at the
 // 1.4 MB gradient size of the parcellation model.  Here every rank owns one cudaMalloc'ed region that its peers
-// map through CUDA IPC:  [ flat gradients, buffer 0 | buffer 1 | ready flag ].
-//   peer_pack_kernel   : copies this rank's gradients into flat[step & 1], then publishes `ready = step + 1`
-//                        (system-scope fence + release store) from the last block to finish;
-//   peer_reduce_sgd_kernel : waits until every rank's flag shows the step, then each thread reads ITS elements from
+// map through CUDA IPC:  [ flat gradients, buffer 0 | buffer 1 | ready flags, one per source rank ].
+//   peer_pack_kernel   : copies this rank's gradients into flat[step & 1], then the last block to finish PUSHES
+//                        `ready = step + 1` into slot [rank] of EVERY rank's flag line (system-scope fence, then one
+//                        remote release store per peer, issued by different threads);
+//   peer_reduce_sgd_kernel : polls its OWN flag line (local memory, one thread per source rank -- no NVLink round
+//                        trip per poll and no serial walk over the peers) until every slot shows the step, then each
+//                        thread reads ITS elements from
 //                        all ranks' buffers straight over NVLink (P2P loads), sums them in rank order -- the same
 //                        order on every rank, so the replicas stay bit-identical --, scales by 1/world and applies
 //                        buf = momentum * buf + g;  param -= lr * buf.  No intermediate averaged-gradient tensor.
@@ -35,7 +38,7 @@ struct PeerSegs {
 
 struct PeerRanks {
     const float* flat[kPeerMaxWorld];           // each rank's region base
-    const unsigned int* flag[kPeerMaxWorld];    // each rank's ready flag
+    unsigned int* flag[kPeerMaxWorld];          // each rank's flag line (kPeerMaxWorld slots, slot s written by rank s)
     int world, rank;
 };
 
@@ -59,8 +62,9 @@ __device__ __forceinline__ int find_seg(const PeerSegs& segs, int64_t e) {
 }
 
 __global__ void __launch_bounds__(256)
-peer_pack_kernel(const PeerSegs segs, float* flat_base, int64_t n, unsigned int* my_flag, const unsigned int* step_ctr,
+peer_pack_kernel(const PeerSegs segs, const PeerRanks ranks, float* flat_base, int64_t n, const unsigned int* step_ctr,
                  unsigned int* done_blocks) {
+    __shared__ int s_last;
     const unsigned int step = *step_ctr;
     float* flat = flat_base + (int64_t)(step & 1u) * n;
     for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
@@ -83,11 +87,13 @@ peer_pack_kernel(const PeerSegs segs, float* flat_base, int64_t n, unsigned int*
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(done_blocks, 1u);
-        if (prev == gridDim.x - 1) {           // last block: every block's stores are fenced; publish
-            *done_blocks = 0u;
-            __threadfence_system();
-            st_release_sys(my_flag, step + 1u);
-        }
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *done_blocks = 0u;
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < ranks.world) {   // last block: every block's stores are fenced; publish to all ranks
+        __threadfence_system();
+        st_release_sys(ranks.flag[threadIdx.x] + ranks.rank, step + 1u);
     }
 }
 
@@ -101,11 +107,11 @@ __global__ void __launch_bounds__(256)
 peer_reduce_sgd_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, float lr, float momentum,
                        unsigned int* step_ctr, unsigned int* done_blocks) {
     const unsigned int step = *step_ctr;
-    if (threadIdx.x == 0) {
+    if ((int)threadIdx.x < ranks.world) {              // own flag line: slot r is pushed by rank r's pack kernel
         const unsigned long long t0 = clock64();
-        for (int r = 0; r < ranks.world; ++r)
-            while (ld_acquire_sys(ranks.flag[r]) < step + 1u)
-                if (clock64() - t0 > kPeerSpinLimit) __trap();
+        const unsigned int* slot = ranks.flag[ranks.rank] + threadIdx.x;
+        while (ld_acquire_sys(slot) < step + 1u)
+            if (clock64() - t0 > kPeerSpinLimit) __trap();
     }
     __syncthreads();
     const int64_t par = (int64_t)(step & 1u) * n;
@@ -270,10 +276,9 @@ extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int
     for (int r = 0; r < world; ++r) {
         TGCN_REQUIRE(regions_host[r], "tgcn_peer_allreduce_sgd: null region for rank %d", r);
         ranks.flat[r] = reinterpret_cast<const float*>(regions_host[r]);
-        ranks.flag[r] = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(regions_host[r]) + 2 * n * sizeof(float));
+        ranks.flag[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[r]) + 2 * n * sizeof(float));
     }
     float* my_flat = reinterpret_cast<float*>(regions_host[rank]);
-    unsigned int* my_flag = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[rank]) + 2 * n * sizeof(float));
     cudaStream_t st = as_stream(stream);
     const int blocks = (int)min64(ceil_div(n > 0 ? n / 4 : 1, 256), (int64_t)kNumSMs * 8);
     if (world == 1) {
@@ -281,7 +286,7 @@ extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int
         TGCN_LAUNCH_CHECK("sgd_direct");
         return TGCN_OK;
     }
-    peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, my_flat, n, my_flag, state, state + 1);
+    peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, ranks, my_flat, n, state, state + 1);
     TGCN_LAUNCH_CHECK("peer_pack");
     peer_reduce_sgd_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);
     TGCN_LAUNCH_CHECK("peer_reduce_sgd");

@@ -408,53 +408,71 @@ spmm_step_staged_kernel(const StagedParams p) {
 
 // Block-staged CSR variant.  A block owns RB consecutive rows: their (col, val) entries are ONE contiguous run of
 // the CSR arrays, copied into shared memory by coalesced loads (col pre-multiplied by the row pitch and paired with
-// val, so an entry is one 8-byte shared load instead of two global broadcast loads per lane), after which a thread
-// walks its row with up to U gathers in flight and no global round trip between them -- the dependent chain of the
-// plain kernel (row bounds -> entries -> gathers, per batch of four) becomes bounds -> entries (once per block) ->
-// gathers.  Blocks whose entry run exceeds the staging capacity read the entries from global memory instead.
+// val, so an entry is one 8-byte shared load instead of two global broadcast loads per lane).  Threads are laid out
+// (float4 column, row lane): no per-element division, and per entry the instruction stream is LDS.64 + address +
+// LDG.128 + 2 FFMA2 -- less than half of the plain kernel's -- at the same or higher occupancy (MINB blocks per SM).
+// Blocks whose entry run exceeds the staging capacity walk the global CSR arrays instead (same order, rare).
 // Accumulation order per output element is that of spmm_step_vec4_kernel (entries of complete groups of four
 // alternate two accumulators, the tail goes to the first): bit-identical results.
 constexpr int kCsmCap = 1536;      // staged entries per block (12 KB)
 constexpr int kCsmMaxRows = 64;
 
-template <bool kHasPrev, int U, bool kStaged>
-__device__ __forceinline__ void csm_rows(const int2* __restrict__ s_ent, const int* __restrict__ s_rp,
-                                         const int* __restrict__ col, const float* __restrict__ val,
-                                         const float4* __restrict__ in, const float4* prev, float4* out,
-                                         int row0, int rows, int V, float alpha, float beta) {
-    static_assert(U % 2 == 0, "U must be even: entry parity selects the accumulator");
-    const int e_lo = s_rp[0];
-    for (int item = threadIdx.x; item < rows * V; item += blockDim.x) {
-        const int r = item / V, v = item - r * V;
+template <bool kHasPrev, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_step_csm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                     int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int RB,
+                     float alpha, float beta) {
+    __shared__ int2 s_ent[kCsmCap];
+    __shared__ int s_rp[kCsmMaxRows + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+    const int tid = ty * V + tx, nthr = V * TY;
+    const int row0 = blockIdx.x * RB;
+    const int rows = min(RB, N - row0);
+    for (int i = tid; i <= rows; i += nthr) s_rp[i] = __ldg(rowptr + row0 + i);
+    __syncthreads();
+    const int e_lo = s_rp[0], n_ent = s_rp[rows] - e_lo;
+    const bool staged = n_ent <= kCsmCap;
+    if (staged) {
+        for (int i = tid; i < n_ent; i += nthr)
+            s_ent[i] = make_int2(__ldg(col + e_lo + i) * V, __float_as_int(__ldg(val + e_lo + i)));
+    }
+    __syncthreads();
+    const float4* inv = in + tx;
+    for (int r = ty; r < rows; r += TY) {
         const int eb = s_rp[r], cnt = s_rp[r + 1] - eb;
-        const int full4 = cnt & ~3;
-        const int64_t idx = (int64_t)(row0 + r) * V + v;
+        const int64_t idx = (int64_t)(row0 + r) * V + tx;
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kHasPrev) pv = prev[idx];
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-        for (int b = 0; b < cnt; b += U) {
-            int off[U];
-            float w[U];
-            float4 x[U];
-#pragma unroll
-            for (int i = 0; i < U; ++i)
-                if (b + i < cnt) {
-                    if (kStaged) {
-                        const int2 en = s_ent[eb - e_lo + b + i];
-                        off[i] = en.x; w[i] = __int_as_float(en.y);
-                    } else {
-                        off[i] = __ldg(col + eb + b + i) * V; w[i] = __ldg(val + eb + b + i);
-                    }
-                }
-#pragma unroll
-            for (int i = 0; i < U; ++i)
-                if (b + i < cnt) x[i] = __ldg(in + (off[i] + v));
-#pragma unroll
-            for (int i = 0; i < U; ++i)
-                if (b + i < cnt) {
-                    if ((i & 1) && b + i < full4) fma4(acc1, w[i], x[i]);
-                    else fma4(acc0, w[i], x[i]);
-                }
+        if (staged) {
+            const int2* ep = s_ent + (eb - e_lo);
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {
+                const int2 a = ep[j], b = ep[j + 1], c = ep[j + 2], d = ep[j + 3];
+                const float4 x0 = __ldg(inv + a.x), x1 = __ldg(inv + b.x), x2 = __ldg(inv + c.x), x3 = __ldg(inv + d.x);
+                fma4(acc0, __int_as_float(a.y), x0);
+                fma4(acc1, __int_as_float(b.y), x1);
+                fma4(acc0, __int_as_float(c.y), x2);
+                fma4(acc1, __int_as_float(d.y), x3);
+            }
+            const int rem = cnt - j;                       // 0..3 tail entries, gathered together
+            if (rem > 0) {
+                const int2 a = ep[j];
+                const int2 b = rem > 1 ? ep[j + 1] : a;
+                const int2 c = rem > 2 ? ep[j + 2] : a;
+                const float4 x0 = __ldg(inv + a.x), x1 = __ldg(inv + b.x), x2 = __ldg(inv + c.x);
+                fma4(acc0, __int_as_float(a.y), x0);
+                if (rem > 1) fma4(acc0, __int_as_float(b.y), x1);
+                if (rem > 2) fma4(acc0, __int_as_float(c.y), x2);
+            }
+        } else {
+            int e = eb;
+            const int e1 = eb + cnt, ef = eb + (cnt & ~3);
+            for (; e < ef; e += 2) {
+                fma4(acc0, __ldg(val + e), __ldg(inv + __ldg(col + e) * V));
+                fma4(acc1, __ldg(val + e + 1), __ldg(inv + __ldg(col + e + 1) * V));
+            }
+            for (; e < e1; ++e) fma4(acc0, __ldg(val + e), __ldg(inv + __ldg(col + e) * V));
         }
         float4 r4;
         r4.x = alpha * (acc0.x + acc1.x);
@@ -469,42 +487,6 @@ __device__ __forceinline__ void csm_rows(const int2* __restrict__ s_ent, const i
         }
         out[idx] = r4;
     }
-}
-
-template <bool kHasPrev, int U>
-__global__ void __launch_bounds__(256, (U <= 4 ? 4 : U <= 8 ? 3 : 2))
-spmm_step_csm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
-                     int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int RB,
-                     float alpha, float beta) {
-    __shared__ int2 s_ent[kCsmCap];
-    __shared__ int s_rp[kCsmMaxRows + 1];
-    const int row0 = blockIdx.x * RB;
-    const int rows = min(RB, N - row0);
-    if ((int)threadIdx.x <= rows) s_rp[threadIdx.x] = __ldg(rowptr + row0 + threadIdx.x);
-    __syncthreads();
-    const int e_lo = s_rp[0], n_ent = s_rp[rows] - e_lo;
-    if (n_ent <= kCsmCap) {
-        for (int i = threadIdx.x; i < n_ent; i += blockDim.x)
-            s_ent[i] = make_int2(__ldg(col + e_lo + i) * V, __float_as_int(__ldg(val + e_lo + i)));
-        __syncthreads();
-        csm_rows<kHasPrev, U, true>(s_ent, s_rp, col, val, in, prev, out, row0, rows, V, alpha, beta);
-    } else {
-        csm_rows<kHasPrev, U, false>(s_ent, s_rp, col, val, in, prev, out, row0, rows, V, alpha, beta);
-    }
-}
-
-// rows per block of the staged-CSR kernel: at most 4 passes of the 256 threads over RB * V items, as full as possible
-static int csm_rows_per_block(int V) {
-    int best = 1;
-    double best_eff = 0.0;
-    for (int rb = 1; rb <= kCsmMaxRows; ++rb) {
-        const int64_t items = (int64_t)rb * V;
-        const int64_t passes = ceil_div(items, 256);
-        if (passes > 4 && rb > 1) break;
-        const double eff = (double)items / (double)(passes * 256);
-        if (eff >= best_eff) { best_eff = eff; best = rb; }
-    }
-    return best;
 }
 
 // ---- block-plan registry: plans are created by the host side once per CSR operand and looked up by the
@@ -563,19 +545,26 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             return TGCN_OK;
         }
     }
-    const int csm_u = tuning_value(kTuneSpmmCsm);          // gathers in flight per thread of the staged-CSR kernel (0 = off)
-    if (vec && csm_u > 0 && (int64_t)N * (C / 4) < (int64_t)INT32_MAX) {
+    // staged-CSR kernel: value = blocks per SM it is compiled for (4, 5, 6, 8; 0 = off); 100 + b (the default, 108)
+    // = only for slabs that do not stay in L2 (>= 96 MB), where it measured 10 % faster than the other variants
+    int csm_b = tuning_value(kTuneSpmmCsm);
+    if (csm_b >= 100) csm_b = ((int64_t)N * C * 4 >= (int64_t)96 << 20) ? csm_b - 100 : 0;
+    if (vec && csm_b > 0 && C / 4 <= 256 && (int64_t)N * (C / 4) < ((int64_t)1 << 30)) {   // col * V stays in int32 (halo rows included)
         const int V = (int)(C / 4);
-        const int RB = csm_rows_per_block(V);
+        int TY = 256 / V;
+        if (TY > kCsmMaxRows) TY = kCsmMaxRows;
+        int RB = 4 * TY;                                   // four rows per thread: the staging cost is paid once per 4
+        if (RB > kCsmMaxRows) RB = kCsmMaxRows;
         const unsigned blocks = (unsigned)ceil_div(N, RB);
-#define TGCN_SPMM_CSM(UU)                                                                                          \
+        const dim3 bd((unsigned)V, (unsigned)TY);
+#define TGCN_SPMM_CSM(MB)                                                                                          \
         do {                                                                                                       \
-            if (prev) spmm_step_csm_kernel<true, UU><<<blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
-                                                                              (const float4*)prev, (float4*)out, V, RB, alpha, beta); \
-            else spmm_step_csm_kernel<false, UU><<<blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
-                                                                          (float4*)out, V, RB, alpha, beta);          \
+            if (prev) spmm_step_csm_kernel<true, MB><<<blocks, bd, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
+                                                                             (const float4*)prev, (float4*)out, V, RB, alpha, beta); \
+            else spmm_step_csm_kernel<false, MB><<<blocks, bd, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
+                                                                         (float4*)out, V, RB, alpha, beta);          \
         } while (0)
-        if (csm_u >= 12) TGCN_SPMM_CSM(12); else if (csm_u >= 8) TGCN_SPMM_CSM(8); else TGCN_SPMM_CSM(4);
+        if (csm_b >= 8) TGCN_SPMM_CSM(8); else if (csm_b >= 6) TGCN_SPMM_CSM(6); else if (csm_b >= 5) TGCN_SPMM_CSM(5); else TGCN_SPMM_CSM(4);
 #undef TGCN_SPMM_CSM
         TGCN_LAUNCH_CHECK("spmm_step");
         return TGCN_OK;

@@ -236,6 +236,11 @@ class PeerAllreduceSGD:
     def moms(self):
         return (self._early.moms if self._early else []) + self._main.moms
 
+    @property
+    def state(self):
+        """Device-side counters of the group exchanged at `step()` (element 0 = steps taken)."""
+        return self._main.state
+
     def _on_grad(self, _param):
         self._seen += 1
         if self._seen == len(self._early.params):      # every early gradient exists: exchange + update them now
