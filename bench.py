@@ -221,10 +221,12 @@ def run_b200(args):
     # whose allreduce runs under the layer-1 backward
     # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
     # --dp nccl: two-bucket NCCL allreduce overlapped with the layer-1 backward + torch's fused SGD
-    use_peer = args.dp in ("peer", "peer-overlap")
-    # the conv layers' gradients come last in the backward: with --dp peer-overlap the head's (large) exchange + update
-    # is launched from autograd hooks on a side stream under the conv backward, only the conv group remains at the end
-    late = [] if args.dp != "peer-overlap" else [p for n_, m in model.named_children() if n_ in ("tgcn1", "gcn2")
+    use_peer = args.dp in ("peer", "peer-overlap", "peer-serial")
+    # the conv layers' gradients come last in the backward: with peer-overlap the head's (large) exchange + update is
+    # launched from autograd hooks on a side stream under the conv backward, only the conv group remains at the end.
+    # Measured (profiles/r01/scaling_hcp360.txt): +2.6 % at 8 GPUs, -2 % at 2 GPUs (two more launches) => auto by world
+    overlap = args.dp == "peer-overlap" or (args.dp == "peer" and world >= 4)
+    late = [] if not overlap else [p for n_, m in model.named_children() if n_ in ("tgcn1", "gcn2")
                                                 for p in m.parameters()]
     if use_peer and world == 1:
         opt = PeerAllreduceSGD(model.parameters(), lr=0.01, momentum=0.5)     # world 1: one fused update launch
@@ -733,9 +735,10 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the separate roofline timing loop (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--rgg-n", type=int, default=1_000_000, help="vertices of the rgg1m workload")
-    ap.add_argument("--dp", default="peer", choices=["peer", "peer-overlap", "nccl"],
-                    help="gradient exchange for N > 1: peer = fused peer-memory allreduce+SGD after the backward; peer-overlap = "
-                         "the head group's exchange runs under the conv backward; nccl = bucketed NCCL + torch SGD")
+    ap.add_argument("--dp", default="peer", choices=["peer", "peer-overlap", "peer-serial", "nccl"],
+                    help="gradient exchange for N > 1: peer = fused peer-memory allreduce+SGD (overlap variant from 4 GPUs); "
+                         "peer-overlap = the head group's exchange runs under the conv backward; peer-serial = one exchange "
+                         "after the backward; nccl = bucketed NCCL + torch SGD")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
