@@ -7,7 +7,8 @@ lib = _lib.load()
 dev = torch.device("cuda")
 KEYS = (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM", b"SPMM_STAGED")
 VARIANTS = [("plain", {}), ("pipe4", {b"SPMM_PIPE": 4}), ("pipe8", {b"SPMM_PIPE": 8}),
-            ("csm4", {b"SPMM_CSM": 4}), ("csm6", {b"SPMM_CSM": 6}), ("csm8", {b"SPMM_CSM": 8})]
+            ("csm6", {b"SPMM_CSM": 6}), ("csm8", {b"SPMM_CSM": 8}), ("csm8p2", {b"SPMM_CSM": 28}), ("csm8p8", {b"SPMM_CSM": 88}),
+            ("csm8p6", {b"SPMM_CSM": 68})]
 
 
 def run(name, L, C, K=5, reps=5, has_prev=False):

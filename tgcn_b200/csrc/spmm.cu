@@ -545,15 +545,18 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             return TGCN_OK;
         }
     }
-    // staged-CSR kernel: value = blocks per SM it is compiled for (4, 5, 6, 8; 0 = off); 100 + b (the default, 108)
+    // staged-CSR kernel: units digit = blocks per SM it is compiled for (4, 5, 6, 8; 0 = off), tens digit = rows per
+    // thread (0 = 4); 100 + that (the default, 106)
     // = only for slabs that do not stay in L2 (>= 96 MB), where it measured 10 % faster than the other variants
     int csm_b = tuning_value(kTuneSpmmCsm);
     if (csm_b >= 100) csm_b = ((int64_t)N * C * 4 >= (int64_t)96 << 20) ? csm_b - 100 : 0;
+    const int csm_p = csm_b / 10 > 0 ? csm_b / 10 : 4;      // tens digit: rows per thread (default 4)
+    csm_b %= 10;
     if (vec && csm_b > 0 && C / 4 <= 256 && (int64_t)N * (C / 4) < ((int64_t)1 << 30)) {   // col * V stays in int32 (halo rows included)
         const int V = (int)(C / 4);
         int TY = 256 / V;
         if (TY > kCsmMaxRows) TY = kCsmMaxRows;
-        int RB = 4 * TY;                                   // four rows per thread: the staging cost is paid once per 4
+        int RB = csm_p * TY;                               // rows per thread: the staging cost is paid once per csm_p rows
         if (RB > kCsmMaxRows) RB = kCsmMaxRows;
         const unsigned blocks = (unsigned)ceil_div(N, RB);
         const dim3 bd((unsigned)V, (unsigned)TY);
