@@ -21,7 +21,8 @@ using namespace tc;
 constexpr int kT2Threads = 320;       // 8 transform warps + producer warp + MMA warp
 constexpr int kT2Transform = 8;       // transform / epilogue warps
 constexpr int kT2RawMax = 6;          // raw ring depth (run-time value R <= kT2RawMax, sized to fill shared memory)
-constexpr int kT2Op = 2;              // operand stage depth
+constexpr int kT2Op = 2;              // operand stage depth (bwd_w)
+constexpr int kT2OpF = 2;             // operand stage depth of the forward kernel (3 measured slower: fewer raw ring slots)
 constexpr uint32_t kT2TileBytes = 128 * 128;
 
 // Align the dynamic shared-memory window to 1024 B with pointer arithmetic on the __shared__ array itself,
@@ -61,6 +62,35 @@ __device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t o
     }
 }
 
+// Shared-memory vector access by 32-bit shared-window address (no generic-address arithmetic in the hot loops).
+template <int VEC>
+__device__ __forceinline__ void lds_vec_u32(uint32_t addr, float* v) {
+    if constexpr (VEC == 4) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+    } else if constexpr (VEC == 2) {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+    } else {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void split_store_u32(uint32_t hi, uint32_t lo, const float* x) {
+    float h[VEC], l[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = x[i] - h[i]; }
+    if constexpr (VEC == 4) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+    } else if constexpr (VEC == 2) {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(hi), "f"(h[0]), "f"(h[1]) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(lo), "f"(l[0]), "f"(l[1]) : "memory");
+    } else {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(hi), "f"(h[0]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lo), "f"(l[0]) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward:  out[m, g] = sum_j sum_d P_j[m, d] W'_j[d, g] + bias
 // unit = (tile of 128 pairs, order j): raw slot = [128 x D fp32 (contiguous in the slab) | weight image of j]
@@ -88,8 +118,8 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
     const uint32_t op_bytes = 2 * kT2TileBytes + wbytes;          // [A hi | A lo | W hi | W lo]
     const uint32_t raw_bytes = p.rawA_bytes + wbytes;             // [A raw | W image]
     uint8_t* op_base = smem;
-    uint8_t* raw_base = smem + kT2Op * op_bytes;
-    __shared__ __align__(8) uint64_t raw_full[kT2RawMax], raw_free[kT2RawMax], op_full[kT2Op], op_free[kT2Op], acc_full, acc_free;
+    uint8_t* raw_base = smem + kT2OpF * op_bytes;
+    __shared__ __align__(8) uint64_t raw_full[kT2RawMax], raw_free[kT2RawMax], op_full[kT2OpF], op_free[kT2OpF], acc_full, acc_free;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,12 +127,17 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
     const uint32_t ncols = tmem_cols_pow2((uint32_t)p.GP);
     if (tid == 0) {
         for (int i = 0; i < kT2RawMax; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kT2Transform); }
-        for (int i = 0; i < kT2Op; ++i) { mbar_init(&op_full[i], kT2Transform); mbar_init(&op_free[i], 1); }
+        for (int i = 0; i < kT2OpF; ++i) { mbar_init(&op_full[i], kT2Transform); mbar_init(&op_free[i], 1); }
         mbar_init(&acc_full, 1);
         mbar_init(&acc_free, kT2Transform);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
+    // zero the A operand tiles once: the fast transform path never writes the padding columns (d >= D)
+    for (int sidx = 0; sidx < kT2OpF; ++sidx)
+        for (uint32_t i = tid; i < 2 * kT2TileBytes / 16; i += kT2Threads)
+            reinterpret_cast<float4*>(op_base + sidx * op_bytes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -150,8 +185,8 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
                 if (ti >= 1) mbar_wait(&acc_free, (ti - 1) & 1);          // epilogue of the previous tile drained TMEM
                 tcgen05_fence_after();
                 for (int j = 0; j < p.K; ++j, ++g) {
-                    const uint32_t s = g % kT2Op;
-                    mbar_wait(&op_full[s], (g / kT2Op) & 1);
+                    const uint32_t s = g % kT2OpF;
+                    mbar_wait(&op_full[s], (g / kT2OpF) & 1);
                     tcgen05_fence_after();
                     uint8_t* op = op_base + s * op_bytes;
                     const uint64_t dah = make_desc_kmajor(smem_u32(op)), dal = make_desc_kmajor(smem_u32(op + kT2TileBytes));
@@ -174,13 +209,68 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
         const int sub = lane / LPR, c0 = (lane % LPR) * VEC;
         const bool cok = c0 < p.D;
         const int lg = warp & 3, ch = warp >> 2;              // TMEM lane group / column-chunk parity of this warp
+        // unit-invariant addresses of this thread's NI vectors: raw slot offset and swizzled operand offset
+        uint32_t src_off[NI], dst_off[NI];
+#pragma unroll
+        for (int e = 0; e < NI; ++e) {
+            const uint32_t row = (uint32_t)(warp * 16 + e * VEC + sub);
+            src_off[e] = (row * (uint32_t)p.D + (uint32_t)c0) * 4u;
+            dst_off[e] = sw128_offset(row, (uint32_t)c0);
+        }
+        const uint32_t raw_u32 = smem_u32(raw_base), op_u32 = smem_u32(op_base);
+        const int wpieces_f = (int)(wbytes / 16);
         uint32_t g = 0, ti = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
             const int m0 = tile * 128;
             const int rows = min(128, p.M - m0);
             const bool direct = (((uint32_t)rows * (uint32_t)p.D * 4u) & 15u) != 0;
+            if (!direct && p.dbg == 0) {
+                // fast path: branch-free, all shared loads of a unit issued back to back
+                for (int j = 0; j < p.K; ++j, ++g) {
+                    const uint32_t r = g % R, s = g % kT2OpF;
+                    const uint32_t slot_u32 = raw_u32 + r * raw_bytes;
+                    float buf[16];
+                    float4 wv[4];
+                    mbar_wait(&raw_full[r], (g / R) & 1);
+                    if (cok) {
+#pragma unroll
+                        for (int e = 0; e < NI; ++e) lds_vec_u32<VEC>(slot_u32 + src_off[e], &buf[e * VEC]);
+                    }
+                    const uint32_t wsrc_u32 = slot_u32 + p.rawA_bytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = tid + i * 256;
+                        if (idx < wpieces_f) {
+                            float t4[4];
+                            lds_vec_u32<4>(wsrc_u32 + (uint32_t)idx * 16u, t4);
+                            wv[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                        }
+                    }
+                    if (g >= kT2OpF) mbar_wait(&op_free[s], ((g / kT2OpF) - 1) & 1);
+                    const uint32_t opa = op_u32 + s * op_bytes;
+                    if (cok) {
+#pragma unroll
+                        for (int e = 0; e < NI; ++e)
+                            split_store_u32<VEC>(opa + dst_off[e], opa + kT2TileBytes + dst_off[e], &buf[e * VEC]);
+                    }
+                    const uint32_t wdst_u32 = opa + 2 * kT2TileBytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = tid + i * 256;
+                        if (idx < wpieces_f)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wdst_u32 + (uint32_t)idx * 16u),
+                                         "f"(wv[i].x), "f"(wv[i].y), "f"(wv[i].z), "f"(wv[i].w) : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&op_full[s]);
+                        mbar_arrive(&raw_free[r]);
+                    }
+                }
+            } else
             for (int j = 0; j < p.K; ++j, ++g) {
-                const uint32_t r = g % R, s = g % kT2Op;
+                const uint32_t r = g % R, s = g % kT2OpF;
                 const uint8_t* slot = raw_base + r * raw_bytes;
                 float buf[16];
                 mbar_wait(&raw_full[r], (g / R) & 1);
@@ -208,7 +298,7 @@ contract_fwd_tc2_kernel(const Fwd2Params p) {
                     const int idx = tid + i * 256;
                     if (idx < wpieces && !(p.dbg & 16)) wv[i] = wsrc[idx];
                 }
-                if (g >= kT2Op) mbar_wait(&op_free[s], ((g / kT2Op) - 1) & 1);
+                if (g >= kT2OpF) mbar_wait(&op_free[s], ((g / kT2OpF) - 1) & 1);
                 uint8_t* op = op_base + s * op_bytes;
                 if (!(p.dbg & 2)) {
 #pragma unroll
@@ -400,6 +490,25 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
         const int n_items = jc * RG;                               // (order, row group) pairs, dealt to the 8 warps
         const int GV = p.G >> 2;                                   // dOut float4 per row
         const int n_bitems = kBw2KT * GV;
+        // unit-invariant addresses of this thread's staged vectors (raw slot offset, swizzled operand offset)
+        uint32_t a_src[NSLOT], a_dst[NSLOT], b_src[2], b_dst[2];
+#pragma unroll
+        for (int e = 0; e < NSLOT; ++e) {
+            const int item = warp + kT2Transform * e;
+            const int jl = item / RG, rg = item - jl * RG;
+            const int k = rg * VEC + sub;
+            const int mn = jl * p.DPAD + c0;
+            a_src[e] = (uint32_t)jl * chunkA + ((uint32_t)k * (uint32_t)p.D + (uint32_t)c0) * 4u;
+            a_dst[e] = (uint32_t)(mn >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(mn & 31));
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int item = tid + 256 * e;
+            const int k = item / GV, gv = item - k * GV, gc = gv * 4;
+            b_src[e] = p.rawA_bytes + (uint32_t)k * rowG + (uint32_t)gv * 16u;
+            b_dst[e] = (uint32_t)(gc >> 5) * blk + sw128b32_offset((uint32_t)k, (uint32_t)(gc & 31));
+        }
+        const uint32_t raw_u32 = smem_u32(raw_base), op_u32 = smem_u32(op_base);
         uint32_t g = 0;
         for (int u = u_begin; u < u_end; ++u, ++g) {
             const uint32_t r = g % R, s = g % kT2Op;
@@ -409,6 +518,39 @@ contract_bwd_w_tc2_kernel(const BwdW2Params p) {
             const bool direct = rows < kBw2KT;
             float abuf[24];
             float4 bbuf[2];
+            if (!direct) {
+                // fast path: branch-free, every shared load of the unit issued back to back
+                const uint32_t slot_u32 = raw_u32 + r * raw_bytes;
+                float bb[2][4];
+                mbar_wait(&raw_full[r], (g / R) & 1);
+                if (cok) {
+#pragma unroll
+                    for (int e = 0; e < NSLOT; ++e)
+                        if (warp + kT2Transform * e < n_items) lds_vec_u32<VEC>(slot_u32 + a_src[e], &abuf[e * VEC]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (tid + 256 * e < n_bitems) lds_vec_u32<4>(slot_u32 + b_src[e], bb[e]);
+                if (g >= kT2Op) mbar_wait(&op_free[s], ((g / kT2Op) - 1) & 1);
+                const uint32_t ah32 = op_u32 + s * op_bytes, al32 = ah32 + a_part;
+                const uint32_t bh32 = ah32 + 2 * a_part, bl32 = bh32 + b_part;
+                if (cok) {
+#pragma unroll
+                    for (int e = 0; e < NSLOT; ++e)
+                        if (warp + kT2Transform * e < n_items)
+                            split_store_u32<VEC>(ah32 + a_dst[e], al32 + a_dst[e], &abuf[e * VEC]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (tid + 256 * e < n_bitems) split_store_u32<4>(bh32 + b_dst[e], bl32 + b_dst[e], bb[e]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&op_full[s]);
+                    mbar_arrive(&raw_free[r]);
+                }
+                continue;
+            }
             mbar_wait(&raw_full[r], (g / R) & 1);
 #pragma unroll
             for (int e = 0; e < NSLOT; ++e) {
@@ -540,7 +682,7 @@ int contract_fwd_tc2(const float* stack, const uint8_t* wimg, const float* bias,
     p.rawA_bytes = (uint32_t)round_up2(128 * D * 4, 1024);
     if (const char* e = getenv("TGCN_T2_PAD")) p.rawA_bytes += (uint32_t)atoi(e);
     const size_t wbytes = 2 * (size_t)GP * kRowBytes;
-    const size_t op_total = 1024 + kT2Op * (2 * (size_t)kT2TileBytes + wbytes);
+    const size_t op_total = 1024 + kT2OpF * (2 * (size_t)kT2TileBytes + wbytes);
     const size_t raw_slot = (size_t)p.rawA_bytes + wbytes;
     if (op_total + 2 * raw_slot > kT2SmemLimit) return TGCN_OK;
     int R = (int)((kT2SmemLimit - op_total) / raw_slot);
