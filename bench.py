@@ -23,6 +23,7 @@ import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
 METRIC = "tgcn_train_samples_per_s"
+ROWTILE_DEFAULT = 0      # rows per tile of the register-tiled SpMM on the streaming workloads (0: per-entry kernels)
 UNIT = "samples/s"
 
 WORKLOADS = {
@@ -217,6 +218,17 @@ def run_b200(args):
         model = wl.NetTGCN_MNIST(Lt, horizon=H, n_classes=cfg["classes"], engine=args.engine).to(dev)
     broadcast_parameters(model)
     N0 = Ls[0].shape[0]
+    rowtile_info = []
+    if args.rowtile:
+        # streaming layers only (the resident kernels keep the operand in shared memory and never call the SpMM)
+        for name in ("tgcn1", "gcn2"):
+            lay = getattr(model, name, None)
+            if lay is None:
+                continue
+            plan = lay._plan(dev)
+            K_, G_ = lay.weight.shape[0], lay.weight.shape[-1]
+            if not lay._use_resident(plan, lay.weight.numel() // (K_ * G_), G_, K_):
+                rowtile_info += [dict(i[2], layer=name) for i in plan.ensure_rowtile_plans(rows_per_tile=args.rowtile)]
     # the first layer's gradients are produced last: their (small) bucket is reduced after the others,
     # whose allreduce runs under the layer-1 backward
     # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
@@ -386,7 +398,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": cfg["desc"], "per_gpu_batch": Q, "global_batch": world * Q,
                        "N_padded": [int(L.shape[0]) for L in Ls], "nnz_L0": int(Ls[0].nnz), "K": 10, "H": H,
-                       "parallelism": "dp%d" % world, "engine": args.engine,
+                       "parallelism": "dp%d" % world, "engine": args.engine, "spmm_rowtile": rowtile_info or None,
                        "gradient_exchange": ("none" if world == 1 else
                                              ("peer-memory allreduce fused with SGD (NVLink P2P loads)" +
                                               ("; head group exchanged under the conv backward" if late else "")) if use_peer else
@@ -430,7 +442,7 @@ def run_rgg(args):
     K, H, Fin, G, Q = 8, 3, 64, 64, args.batch or 1
     D = H * Fin
     L, _ = wl.random_geometric(n=n, mean_degree=12.0, seed=0)
-    layer = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev)
+    layer = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev, rows_per_tile=args.rowtile)
     n_own = layer.n_own
     gen = torch.Generator().manual_seed(0)
     bound = 1.0 / (Fin * K) ** 0.5
@@ -501,7 +513,8 @@ def run_rgg(args):
         per = _time_graph(spmm_steps, 5, None) / (K - 1)
         nbytes = 2 * 4 * n_own * C + 8 * int(layer.col.numel()) + 4 * (n_own + 1)
         ach = nbytes / (per * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "spmm_step kernel (recursion step on this rank's rows, 2S+E bytes; slabs exceed L2)",
+        roof = {"bound": "hbm", "kernel": ("spmm_step_rtile_kernel" if layer.rowtile else "spmm_step_csm_kernel") +
+                                          " (recursion step on this rank's rows, 2S+E bytes; slabs exceed L2)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": int(nbytes),
                 "us_per_launch": per * 1e3, "peak_source": src}
     cpu = None
@@ -514,6 +527,7 @@ def run_rgg(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "rgg1m", "description": cfg["desc"], "vertices": n, "nnz": int(L.nnz), "K": K, "H": H,
                            "F": Fin, "G": G, "batch": Q, "parallelism": "rows/%d" % world, "halo_rows_rank0": int(layer.plan.n_halo),
+                           "spmm_rowtile": layer.rowtile[2] if layer.rowtile else None,
                            "l2": "working set exceeds L2 (768 MB slabs at 1 GPU)", "cuda_graph": False},
                 "e2e": {"value": Q / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4),
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -646,7 +660,8 @@ def measure_spmm_roofline(lib, model, Ls, Q, H, dev, flush_buf):
     per_launch_ms = _time_graph(steps, reps, flush_buf) / (K - 1)
     bytes_per_launch = algorithmic_step_bytes(N, C, plan.nnz, has_prev=False)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "spmm_step_pipe_kernel (layer-1 recursion step, 2S+E bytes)",
+    kname = "spmm_step_rtile_kernel" if getattr(plan, "_rowtiles", None) else "spmm_step_pipe_kernel"
+    return {"bound": "hbm", "kernel": kname + " (layer-1 recursion step, 2S+E bytes)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "bytes_per_launch": int(bytes_per_launch), "us_per_launch": per_launch_ms * 1e3, "peak_source": src}
 
@@ -739,6 +754,8 @@ def main():
                     help="gradient exchange for N > 1: peer = fused peer-memory allreduce+SGD (overlap variant from 4 GPUs); "
                          "peer-overlap = the head group's exchange runs under the conv backward; peer-serial = one exchange "
                          "after the backward; nccl = bucketed NCCL + torch SGD")
+    ap.add_argument("--rowtile", type=int, default=ROWTILE_DEFAULT, choices=[0, 4, 8],
+                    help="rows per tile of the register-tiled SpMM kernel for the streaming layers (0 = per-entry kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

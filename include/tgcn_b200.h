@@ -65,7 +65,8 @@ long long tgcn_launch_count(void);
  * plans (1), "RES_TC" = contraction of the resident forward kernel on tcgen05 with 3xTF32 operands and TMEM
  * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes), "RES_ENT" =
  * keep each thread's CSR entries in registers across the K steps of the resident forward (bit-identical; 0 default:
- * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us).  The SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
+ * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us), "SPMM_RTILE" = use
+ * registered row-tile plans (1; 2 = only for slabs that do not stay in L2; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
 int tgcn_set_tuning(const char* key, int value);
 
 /* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */
@@ -82,6 +83,21 @@ int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host
 int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
                          const uint16_t* lcol_dev, int RB, int maxd);
 int tgcn_plan_destroy(int64_t handle);
+
+/* ---- row-tile plans: register-tiled SpMM ("SPMM_RTILE" tuning key, on whenever a plan is registered) ---- */
+/* A thread of the row-tile kernel owns one float4 column of R consecutive rows (R = 4 or 8) and loads every DISTINCT
+ * source row of the tile once, applying it to all R rows with a dense coefficient vector -- 2-2.75x fewer gathers than
+ * one per CSR entry on graphs whose row order has locality (coarsening order, Morton order).  Same mathematical
+ * operation as the reference's sparse product (gcn_matmul.py:154, gcn.py:147); the summation order per output element
+ * is ascending source row, so results agree with the other SpMM kernels to fp32 rounding, not bit for bit.
+ * tgcn_rowtile_plan_host builds the plan on the host (src_host == w_host == NULL: size query; returns the number of
+ * (tile, source) pairs); upload the arrays (w_dev 16-byte aligned) and register them keyed by the device address of
+ * the CSR `col` array.  The arrays stay owned by the caller and must outlive the plan. */
+int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N, int R,
+                               int32_t* tile_ptr_host, int32_t* src_host, float* w_host);
+int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int R, const int32_t* tile_ptr_dev,
+                                 const int32_t* src_dev, const float* w_dev);
+int tgcn_rowtile_plan_destroy(int64_t handle);
 
 /* ---- layout ------------------------------------------------------------------------------ */
 /* x[Q,N,D] -> slab[N,Q,D]   (replaces X.permute(1,3,2,0).reshape(N,-1), gcn_matmul.py:152-153) */

@@ -223,3 +223,87 @@ def test_row_block_staged_spmm_is_bit_identical(rb, cap, C):
         assert torch.equal(run(plain, False), run(staged, False))
     finally:
         lib.tgcn_set_tuning(b"SPMM_STAGED", -1)
+
+
+@pytest.mark.parametrize("R", [4, 8])
+@pytest.mark.parametrize("C", [8, 72, 192, 240, 1024])      # V = 2, 18, 48, 60 (warps straddle tiles), 256 (one tile per block)
+def test_register_tiled_spmm_matches_plain_kernel(R, C):
+    """tgcn_rowtile_plan_create + the register-tiled SpMM kernel (every distinct source row of a tile of R rows
+    loaded once and applied to all R rows) against the plain kernel and an fp64 product on the same operands, with
+    and without `prev`, `prev` aliasing `out`, N not a multiple of R, empty rows, a non-symmetric operand.  The
+    summation order differs from the plain kernel's (one ascending chain instead of two), hence a tolerance: 1e-5 of
+    the largest output against the plain kernel, 1e-4 (north_star) against fp64."""
+    from tgcn_b200 import _lib
+    from tgcn_b200.csr import build_csr
+    from conftest import csr_from, load_golden
+    import scipy.sparse as sp
+    lib = _lib.load()
+    L = csr_from(load_golden("graph_grid28_k8_seed0.npz"), "L_0").tolil()     # coarsening order: locality + empty rows
+    L[5, 17] = 0.3                                                           # break the symmetry: L^T gets its own plan
+    L = L.tocsr()[:-3, :-3]                                                  # N % 8 != 0
+    n = L.shape[0]
+    assert n % 8 != 0
+    rng = np.random.default_rng(R + C)
+    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    prev = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(plan, with_prev, transpose=False, alias=False):
+        out = prev.clone() if alias else torch.full((n, C), float("nan"), device="cuda")
+        rp, c, v = (plan.rowptr_t, plan.col_t, plan.val_t) if transpose else (plan.rowptr, plan.col, plan.val)
+        pv = out if alias else (prev if with_prev else None)
+        before = lib.tgcn_launch_count()
+        rc = lib.tgcn_spmm_step(rp.data_ptr(), c.data_ptr(), v.data_ptr(), n, x.data_ptr(),
+                                None if pv is None else pv.data_ptr(), out.data_ptr(), C, 2.0, -1.0, st)
+        assert rc == 0, _lib.last_error()
+        assert lib.tgcn_launch_count() == before + 1
+        return out
+    plain = build_csr(L, torch.device("cuda"))
+    tiled = build_csr(L, torch.device("cuda"))
+    info = tiled.ensure_rowtile_plans(rows_per_tile=R, min_gain=0.0)
+    assert len(info) == 2 and info[0][2]["gain"] > 1.2 and not tiled.symmetric
+    Ld = sp.csr_matrix(L, dtype=np.float64)
+    x64, p64 = x.double().cpu().numpy(), prev.double().cpu().numpy()
+    for transpose in (False, True):
+        M = Ld.T if transpose else Ld
+        for with_prev, alias in ((False, False), (True, False), (True, True)):
+            base = run(plain, with_prev, transpose, alias)
+            got = run(tiled, with_prev, transpose, alias)
+            ref = 2.0 * (M @ x64) - (p64 if with_prev else 0.0)
+            scale = float(np.abs(ref).max())
+            assert not torch.equal(got, torch.full_like(got, float("nan")))
+            assert float((got - base).abs().max()) <= 1e-5 * scale
+            assert float(np.abs(got.double().cpu().numpy() - ref).max()) <= 1e-4 * scale
+    # the tuning key switches the register-tiled path off without touching the plan: bit-identical to plain again
+    try:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", 0)
+        assert torch.equal(run(plain, True), run(tiled, True))
+    finally:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
+
+
+def test_register_tiled_spmm_through_the_layer():
+    """A streaming-engine layer whose operand has a row-tile plan: forward, dW, db and dx within 1e-4 of the oracle."""
+    from oracle import layers_np
+    from tgcn_b200.nn.gcn import TGCNCheb_H
+    from conftest import csr_from, load_golden
+    L = csr_from(load_golden("graph_grid28_k8_seed0.npz"), "L_0")
+    n = L.shape[0]
+    Ld = np.asarray(L.todense(), dtype=np.float32)
+    Q, H, G, K = 3, 4, 8, 5
+    torch.manual_seed(0)
+    lay = TGCNCheb_H(torch.tensor(Ld), 1, G, K, H, engine="ffma").cuda()
+    x = torch.randn(Q, n, H, device="cuda", requires_grad=True)
+    info = lay._plan(x.device).ensure_rowtile_plans(rows_per_tile=8, min_gain=0.0)
+    assert info and info[0][2]["gain"] > 1.2
+    out = lay(x)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    W, b = lay.weight.detach().cpu().numpy(), lay.bias.detach().cpu().numpy()
+    ref = layers_np.layer_forward(Ld, x.detach().cpu().numpy(), W, b, kind="tgcn_h")
+    dW, db, dx = layers_np.layer_backward(Ld, x.detach().cpu().numpy(), W, dout.cpu().numpy(), b.shape, kind="tgcn_h")
+    rel = lambda a, r: float(np.abs(a - r).max() / np.abs(r).max())
+    assert rel(out.detach().cpu().numpy(), ref) < 1e-4
+    assert rel(lay.weight.grad.cpu().numpy(), dW) < 1e-4
+    assert rel(lay.bias.grad.cpu().numpy(), db) < 1e-4
+    assert rel(x.grad.cpu().numpy(), dx) < 1e-4

@@ -1,0 +1,76 @@
+"""Host-side row-tile plan of the register-tiled SpMM (tgcn_rowtile_plan_host): a pure CPU function of the C-ABI.
+The plan is replayed in numpy exactly as spmm_step_rtile_kernel walks it (per tile: distinct source rows in
+ascending order, a dense R-vector of coefficients each) and compared with the sparse product it must equal
+(gcn_matmul.py:154)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tgcn_b200 import _lib
+
+
+def _plan(m, R):
+    lib = _lib.load()
+    m = m.tocsr(); m.sort_indices()
+    rp = m.indptr.astype(np.int32); c = m.indices.astype(np.int32); v = m.data.astype(np.float32)
+    n = m.shape[0]
+    nt = (n + R - 1) // R
+    tile_ptr = np.full(nt + 1, -1, np.int32)
+    total = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, None, None)
+    src = np.full(max(total, 1), -1, np.int32)
+    w = np.full((max(total, 1), R), np.nan, np.float32)
+    total2 = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data,
+                                        src.ctypes.data, w.ctypes.data)
+    assert total == total2 == tile_ptr[nt]
+    return rp, c, v, tile_ptr, src[:total], w[:total]
+
+
+def _replay(tile_ptr, src, w, x, n, R):
+    out = np.zeros((n, x.shape[1]), np.float64)
+    for t in range(len(tile_ptr) - 1):
+        for s in range(tile_ptr[t], tile_ptr[t + 1]):
+            for q in range(R):
+                row = t * R + q
+                if row < n:
+                    out[row] += np.float64(w[s, q]) * x[src[s]]
+    return out
+
+
+@pytest.mark.parametrize("R", [4, 8])
+@pytest.mark.parametrize("n", [1, 7, 64, 203])
+def test_plan_replay_equals_sparse_product(R, n):
+    rng = np.random.default_rng(n * 10 + R)
+    m = sp.random(n, n, density=min(1.0, 6.0 / n), random_state=n + R, format="lil", dtype=np.float32)
+    if n > 10:
+        m[3, :] = 0                      # an empty row
+        m[5, ::2] = 0.5                  # a long row
+    m = m.tocsr()
+    rp, c, v, tile_ptr, src, w = _plan(m, R)
+    x = rng.standard_normal((n, 5))
+    ref = sp.csr_matrix((v.astype(np.float64), c, rp), shape=(n, n)) @ x
+    np.testing.assert_allclose(_replay(tile_ptr, src, w, x, n, R), ref, rtol=1e-12, atol=1e-12)
+    # structure: sources strictly ascending inside a tile, every stored coefficient is a CSR value or 0,
+    # one (tile, source) pair per distinct column of the tile, padded rows of the last tile carry zeros
+    for t in range(len(tile_ptr) - 1):
+        s0, s1 = tile_ptr[t], tile_ptr[t + 1]
+        assert np.all(np.diff(src[s0:s1]) > 0)
+        r0, r1 = t * R, min(n, t * R + R)
+        assert set(src[s0:s1].tolist()) == set(c[rp[r0]:rp[r1]].tolist())
+        assert np.all(w[s0:s1, r1 - r0:] == 0)
+    assert np.count_nonzero(w) == np.count_nonzero(v)
+
+
+def test_plan_counts_shared_sources_once_and_rejects_bad_arguments():
+    lib = _lib.load()
+    # 8 rows that all read sources {0, 1}: one tile of 8 has 2 sources, two tiles of 4 have 2 each
+    m = sp.csr_matrix(np.tile(np.array([[1.0, 2.0] + [0.0] * 6], np.float32), (8, 1)))
+    for R, want in ((8, 2), (4, 4)):
+        rp, c, v, tile_ptr, src, w = _plan(m, R)
+        assert len(src) == want and np.all(w[:, :] == np.where(src[:, None] == 0, 1.0, 2.0))
+    rp = m.indptr.astype(np.int32); c = m.indices.astype(np.int32); v = m.data.astype(np.float32)
+    tp = np.zeros(9, np.int32)
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 3, tp.ctypes.data, None, None) == -1
+    assert lib.tgcn_rowtile_plan_host(None, c.ctypes.data, v.ctypes.data, 8, 8, tp.ctypes.data, None, None) == -1
+    src = np.zeros(16, np.int32)
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, tp.ctypes.data, src.ctypes.data, None) == -1
+    assert lib.tgcn_rowtile_plan_destroy(12345) != 0

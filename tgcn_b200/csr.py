@@ -14,7 +14,7 @@ class LaplacianCSR:
     """int32 CSR of L and of L^T resident on one CUDA device."""
 
     __slots__ = ("n", "nnz", "rowptr", "col", "val", "rowptr_t", "col_t", "val_t", "symmetric", "device",
-                 "_host", "_packed", "_lock", "_blocks")
+                 "_host", "_packed", "_lock", "_blocks", "_rowtiles")
 
     def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, symmetric, device):
         self.n, self.nnz = n, int(col.numel())
@@ -26,6 +26,7 @@ class LaplacianCSR:
         self._packed = {}
         self._lock = threading.Lock()
         self._blocks = None        # row-block plans of the streaming SpMM: list of (handle, tensors kept alive, stats)
+        self._rowtiles = None      # row-tile plans (register-tiled SpMM): same shape of list
 
     def _host_arrays(self):
         if self._host is None:
@@ -70,6 +71,27 @@ class LaplacianCSR:
             self._blocks = made
         return self._blocks
 
+    def ensure_rowtile_plans(self, rows_per_tile=8, min_gain=1.5):
+        """Row-tile plans for the register-tiled SpMM kernel (include/tgcn_b200.h, tgcn_rowtile_plan_create): built
+        once per device for L (and L^T when it differs) and registered with the library when the row order has enough
+        locality (see `make_rowtile_plan`).  Idempotent."""
+        if self._rowtiles is not None:
+            return self._rowtiles
+        with self._lock:
+            if self._rowtiles is not None:
+                return self._rowtiles
+            host = self._host_arrays()
+            made = []
+            variants = [(host[0], host[1], host[2], self.col)]
+            if not self.symmetric:
+                variants.append((host[3], host[4], host[5], self.col_t))
+            for rp, c, v, col_dev in variants:
+                one = make_rowtile_plan(rp, c, v, self.n, rows_per_tile, col_dev, min_gain)
+                if one is not None:
+                    made.append(one)
+            self._rowtiles = made
+        return self._rowtiles
+
     def __del__(self):
         try:
             if self._blocks:
@@ -77,6 +99,11 @@ class LaplacianCSR:
                 lib = _lib.load()
                 for h, _, _ in self._blocks:
                     lib.tgcn_plan_destroy(h)
+            if self._rowtiles:
+                from . import _lib
+                lib = _lib.load()
+                for h, _, _ in self._rowtiles:
+                    lib.tgcn_rowtile_plan_destroy(h)
         except Exception:
             pass
 
@@ -108,6 +135,38 @@ class LaplacianCSR:
             hit = (torch.from_numpy(rowinfo).to(self.device), torch.from_numpy(entries).to(self.device), E)
             self._packed[key] = hit
         return hit
+
+
+def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5):
+    """Build (host, tgcn_rowtile_plan_host) and register (tgcn_rowtile_plan_create) the row-tile plan of the CSR
+    operand `rowptr/col/val` (int32/int32/float32 numpy, `n` rows) whose column array lives on the device as
+    `col_dev`.  Returns (handle, device arrays to keep alive, stats), or None when the row order has too little
+    locality: CSR entries / distinct (tile, source row) pairs < min_gain -- below that the kernel would do as many
+    gathers as the per-entry kernels and R times their multiply-adds."""
+    from . import _lib
+    lib = _lib.load()
+    R = int(rows_per_tile)
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    c = np.ascontiguousarray(col, dtype=np.int32)
+    v = np.ascontiguousarray(val, dtype=np.float32)
+    if n < 1 or c.size == 0:
+        return None
+    tile_ptr = np.zeros((n + R - 1) // R + 1, dtype=np.int32)
+    total = int(lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, None, None))
+    if total <= 0:
+        raise RuntimeError("tgcn_rowtile_plan_host rejected the CSR operand (rows_per_tile=%d)" % R)
+    if c.size / total < min_gain:
+        return None
+    src = np.zeros(total, dtype=np.int32)
+    w = np.zeros((total, R), dtype=np.float32)
+    lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, src.ctypes.data,
+                               w.ctypes.data)
+    dev_arrays = tuple(torch.from_numpy(a).to(col_dev.device) for a in (tile_ptr, src, w))
+    h = int(lib.tgcn_rowtile_plan_create(col_dev.data_ptr(), n, R, dev_arrays[0].data_ptr(), dev_arrays[1].data_ptr(),
+                                         dev_arrays[2].data_ptr()))
+    if h < 0:
+        raise RuntimeError("tgcn_rowtile_plan_create failed: %s" % _lib.last_error())
+    return h, dev_arrays, {"gain": c.size / total, "sources": total, "rows_per_tile": R}
 
 
 def _to_scipy_like(L):

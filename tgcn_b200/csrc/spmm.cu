@@ -489,6 +489,114 @@ spmm_step_csm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
     }
 }
 
+// ---- register-tiled row-tile kernel (SPMM_RTILE) ---------------------------------------------------------------
+// ncu on the staged-CSR kernel shows the L1 data pipe at 92 % of its wavefront rate: every (row, entry) pair costs one
+// LDG.128 per float4 column no matter where the line comes from, so no LDG- or LDS-based gather can go faster.  This
+// kernel cuts the NUMBER of gathers: a thread owns one float4 column of R consecutive rows (4R accumulators in
+// registers).  The host plan (tgcn_rowtile_plan_host) lists, per tile of R rows, the DISTINCT source rows in ascending
+// order, each with a dense R-vector of coefficients (0 where a row of the tile has no such entry).  A source row is
+// loaded ONCE per tile and applied to all R rows: on the strip+Morton-ordered 1M-vertex geometric graph a tile of 8
+// rows has 35 distinct sources for 96 entries (2.75x fewer gathers), on the cortical mesh 2.0x.  The accumulators are
+// paired over ROWS -- {row 2p, row 2p+1} of one component in one 64-bit register -- so the coefficient pairs come
+// straight from memory as the first operand of fma.rn.f32x2 and only the 4 components of x need a duplicating move.
+// Summation order per output element: ascending source row, one chain (the other kernels alternate two chains), so
+// results agree with them to fp32 rounding (not bit-identical); a zero coefficient multiplies the source value, so a
+// non-finite activation reaches every row of a tile that shares the source (finite inputs: exact zeros, no effect).
+template <int R>
+__device__ __forceinline__ void rtile_apply(unsigned long long (&a)[4][R / 2], const float4& x,
+                                            const unsigned long long (&wp)[R / 2]) {
+    unsigned long long xx[4];
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx[0]) : "f"(x.x));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx[1]) : "f"(x.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx[2]) : "f"(x.z));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx[3]) : "f"(x.w));
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p)
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[c][p]) : "l"(wp[p]), "l"(xx[c]));
+}
+
+template <int R>
+__device__ __forceinline__ void rtile_load_w(const float* __restrict__ w, int64_t s, unsigned long long (&wp)[R / 2]) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(w + s * R);
+#pragma unroll
+    for (int i = 0; i < R / 4; ++i) {
+        const ulonglong2 v = __ldg(p + i);
+        wp[2 * i] = v.x;
+        wp[2 * i + 1] = v.y;
+    }
+}
+
+template <bool kHasPrev, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
+                       int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
+                       float alpha, float beta) {
+    const int tx = threadIdx.x;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y;
+    if (t >= ntiles) return;
+    int s = __ldg(tile_ptr + t);
+    const int s1 = __ldg(tile_ptr + t + 1);
+    unsigned long long a[4][R / 2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p) a[c][p] = 0ull;
+    const float4* inv = in + tx;
+    // two sources in flight per thread: both gathers and both coefficient vectors are issued before the first FFMA2
+    for (; s + 2 <= s1; s += 2) {
+        const int c0 = __ldg(src + s), c1 = __ldg(src + s + 1);
+        unsigned long long w0[R / 2], w1[R / 2];
+        rtile_load_w<R>(w, s, w0);
+        rtile_load_w<R>(w, s + 1, w1);
+        const float4 x0 = __ldg(inv + (int64_t)c0 * V);
+        const float4 x1 = __ldg(inv + (int64_t)c1 * V);
+        rtile_apply<R>(a, x0, w0);
+        rtile_apply<R>(a, x1, w1);
+    }
+    if (s < s1) {
+        const int c0 = __ldg(src + s);
+        unsigned long long w0[R / 2];
+        rtile_load_w<R>(w, s, w0);
+        rtile_apply<R>(a, __ldg(inv + (int64_t)c0 * V), w0);
+    }
+    const int row0 = t * R;
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) {
+        float lo[4], hi[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) asm("mov.b64 {%0, %1}, %2;" : "=f"(lo[c]), "=f"(hi[c]) : "l"(a[c][p]));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = row0 + 2 * p + h;
+            if (row >= N) break;
+            const float* v = h ? hi : lo;
+            const int64_t idx = (int64_t)row * V + tx;
+            float4 r4 = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
+            if (kHasPrev) {
+                const float4 pv = prev[idx];
+                r4.x = fmaf(beta, pv.x, r4.x);
+                r4.y = fmaf(beta, pv.y, r4.y);
+                r4.z = fmaf(beta, pv.z, r4.z);
+                r4.w = fmaf(beta, pv.w, r4.w);
+            }
+            out[idx] = r4;
+        }
+    }
+}
+
+struct RowTilePlan { const void* key; const int* tile_ptr; const int* src; const float* w; int R, N; bool live; };
+static std::mutex g_rt_mu;
+static std::vector<RowTilePlan> g_rt_plans;
+
+static bool find_rowtile_plan(const void* col, int N, RowTilePlan* out) {
+    std::lock_guard<std::mutex> lk(g_rt_mu);
+    for (const RowTilePlan& rp : g_rt_plans)
+        if (rp.live && rp.key == col && rp.N == N) { *out = rp; return true; }
+    return false;
+}
+
 // ---- block-plan registry: plans are created by the host side once per CSR operand and looked up by the
 // device address of its `col` array (the plan's arrays stay owned by the caller)
 struct BlockPlan { const void* key; const int* blk_ptr; const int* blk_rows; const unsigned short* lcol; int RB, maxd, N; bool live; };
@@ -544,6 +652,29 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
         }
+    }
+    // register-tiled row-tile kernel: whenever a row-tile plan is registered for this operand ("SPMM_RTILE": 0 = off,
+    // 1 = on, 2 = on only for slabs that do not stay in L2)
+    RowTilePlan rt;
+    const int rt_mode = tuning_value(kTuneSpmmRtile);
+    if (vec && rt_mode != 0 && C / 4 <= 256 && (rt_mode != 2 || (int64_t)N * C * 4 >= (int64_t)96 << 20) &&
+        find_rowtile_plan(col, N, &rt)) {
+        const int V = (int)(C / 4);
+        const int TY = 256 / V;
+        const int ntiles = (int)ceil_div(N, rt.R);
+        const unsigned blocks = (unsigned)ceil_div(ntiles, TY);
+        const dim3 bd((unsigned)V, (unsigned)TY);
+#define TGCN_SPMM_RT(RR, MB)                                                                                        \
+        do {                                                                                                        \
+            if (prev) spmm_step_rtile_kernel<true, RR, MB><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
+                                                                                  (const float4*)prev, (float4*)out, V, ntiles, alpha, beta); \
+            else spmm_step_rtile_kernel<false, RR, MB><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
+                                                                              (float4*)out, V, ntiles, alpha, beta); \
+        } while (0)
+        if (rt.R == 8) TGCN_SPMM_RT(8, 3); else TGCN_SPMM_RT(4, 4);
+#undef TGCN_SPMM_RT
+        TGCN_LAUNCH_CHECK("spmm_step");
+        return TGCN_OK;
     }
     // staged-CSR kernel: units digit = blocks per SM it is compiled for (4, 5, 6, 8; 0 = off), tens digit = rows per
     // thread (0 = 4); 100 + that (the default, 106)
@@ -748,6 +879,71 @@ extern "C" int tgcn_plan_destroy(int64_t handle) {
     if (handle < 0 || handle >= (int64_t)g_plans.size() || !g_plans[handle].live)
         return set_error(TGCN_ERR_INVALID, "tgcn_plan_destroy: unknown handle %lld", (long long)handle);
     g_plans[handle].live = false;
+    return TGCN_OK;
+}
+
+// Host-side row-tile plan for spmm_step_rtile_kernel: per tile of R consecutive rows (R = 4 or 8) the distinct source
+// rows in ascending order, each with its R coefficients (row-major inside the tile, 0 where absent; duplicate (row,
+// col) entries are summed in CSR order).  tile_ptr_host[ceil(N/R)+1]; src_host / w_host: capacity = nnz sources
+// (w: nnz*R floats); both NULL: size query.  Returns the total number of (tile, source) pairs, -1 on bad arguments.
+extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
+                                          int R, int32_t* tile_ptr_host, int32_t* src_host, float* w_host) {
+    if (N < 0 || (R != 4 && R != 8) || !rowptr_host || (rowptr_host[N] > 0 && (!col_host || !val_host))) return -1;
+    if ((src_host == nullptr) != (w_host == nullptr)) return -1;
+    const int nt = (int)ceil_div(N, R);
+    int64_t total = 0;
+    std::vector<std::pair<int32_t, int32_t>> ent;     // (col, CSR position) of the tile's entries
+    for (int t = 0; t < nt; ++t) {
+        const int r0 = t * R, r1 = (int)min64((int64_t)N, (int64_t)r0 + R);
+        const int e0 = rowptr_host[r0], e1 = rowptr_host[r1];
+        ent.clear();
+        for (int e = e0; e < e1; ++e) ent.push_back({col_host[e], e});
+        std::sort(ent.begin(), ent.end());
+        if (tile_ptr_host) tile_ptr_host[t] = (int32_t)total;
+        int r = r0;                                    // row lookup for CSR positions: positions ascend within a source
+        for (size_t i = 0; i < ent.size();) {
+            size_t j = i;
+            while (j < ent.size() && ent[j].first == ent[i].first) ++j;
+            if (src_host) {
+                src_host[total] = ent[i].first;
+                float* wv = w_host + total * R;
+                for (int q = 0; q < R; ++q) wv[q] = 0.f;
+                r = r0;
+                for (size_t k = i; k < j; ++k) {
+                    const int e = ent[k].second;
+                    while (rowptr_host[r + 1] <= e) ++r;
+                    wv[r - r0] += val_host[e];
+                }
+            }
+            ++total;
+            i = j;
+        }
+    }
+    if (tile_ptr_host) tile_ptr_host[nt] = (int32_t)total;
+    return total;
+}
+
+// Register / drop a row-tile plan for the CSR operand whose column array lives at device address `col_dev`
+// (device arrays owned by the caller; they must outlive the plan).  Returns a handle >= 0.
+extern "C" int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int R, const int32_t* tile_ptr_dev,
+                                            const int32_t* src_dev, const float* w_dev) {
+    if (!col_dev || !tile_ptr_dev || !src_dev || !w_dev || (R != 4 && R != 8) || N < 1 || !aligned16(w_dev)) {
+        set_error(TGCN_ERR_INVALID, "tgcn_rowtile_plan_create: bad arguments");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lk(g_rt_mu);
+    const RowTilePlan np{col_dev, tile_ptr_dev, src_dev, w_dev, R, N, true};
+    for (size_t i = 0; i < g_rt_plans.size(); ++i)
+        if (!g_rt_plans[i].live) { g_rt_plans[i] = np; return (int64_t)i; }
+    g_rt_plans.push_back(np);
+    return (int64_t)g_rt_plans.size() - 1;
+}
+
+extern "C" int tgcn_rowtile_plan_destroy(int64_t handle) {
+    std::lock_guard<std::mutex> lk(g_rt_mu);
+    if (handle < 0 || handle >= (int64_t)g_rt_plans.size() || !g_rt_plans[handle].live)
+        return set_error(TGCN_ERR_INVALID, "tgcn_rowtile_plan_destroy: unknown handle %lld", (long long)handle);
+    g_rt_plans[handle].live = false;
     return TGCN_OK;
 }
 

@@ -377,7 +377,10 @@ class RowPartitionedLayer:
     layer because the local CSR keeps each row's entry order.  Input gradients are not produced (first-layer
     use, as in the reference models where the input does not require grad)."""
 
-    def __init__(self, L_csr, K, D, G, rank=0, world=1, device=None, recursion=0, engine=0, group=None):
+    def __init__(self, L_csr, K, D, G, rank=0, world=1, device=None, recursion=0, engine=0, group=None,
+                 rows_per_tile=0):
+        """rows_per_tile = 4 or 8: register the row-tile plan of this rank's rows (register-tiled SpMM kernel,
+        include/tgcn_b200.h `tgcn_rowtile_plan_create`) when the row order has locality; 0: per-entry kernels."""
         from . import _lib
         self.lib = _lib.load()
         self.K, self.D, self.G = K, D, G
@@ -397,6 +400,17 @@ class RowPartitionedLayer:
         self.val = torch.tensor(pl.val, device=dev)
         self.send_idx_dev = [None if (i is None or len(i) == 0) else torch.as_tensor(i, device=dev) for i in pl.send_idx]
         self._bufs = {}
+        self.rowtile = None
+        if rows_per_tile:
+            from .csr import make_rowtile_plan
+            self.rowtile = make_rowtile_plan(pl.rowptr, pl.col, pl.val, self.n_own, rows_per_tile, self.col)
+
+    def __del__(self):
+        try:
+            if self.rowtile is not None:
+                self.lib.tgcn_rowtile_plan_destroy(self.rowtile[0])
+        except Exception:
+            pass
 
     def _buffers(self, Q):
         b = self._bufs.get(Q)
