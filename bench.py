@@ -23,7 +23,7 @@ import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
 METRIC = "tgcn_train_samples_per_s"
-ROWTILE_DEFAULT = 0      # rows per tile of the register-tiled SpMM on the streaming workloads (0: per-entry kernels)
+ROWTILE_DEFAULT = 4      # rows per tile of the register-tiled SpMM on the streaming workloads (0: per-entry kernels)
 UNIT = "samples/s"
 
 WORKLOADS = {

@@ -66,7 +66,7 @@ long long tgcn_launch_count(void);
  * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes), "RES_ENT" =
  * keep each thread's CSR entries in registers across the K steps of the resident forward (bit-identical; 0 default:
  * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us), "SPMM_RTILE" = use
- * registered row-tile plans (1; 2 = only for slabs that do not stay in L2; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
+ * registered row-tile plans (1; 4/5/6/8 = the build for that many blocks per SM; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
 int tgcn_set_tuning(const char* key, int value);
 
 /* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */
@@ -92,10 +92,11 @@ int tgcn_plan_destroy(int64_t handle);
  * is ascending source row, so results agree with the other SpMM kernels to fp32 rounding, not bit for bit.
  * tgcn_rowtile_plan_host builds the plan on the host (src_host == w_host == NULL: size query; returns the number of
  * (tile, source) pairs); upload the arrays (w_dev 16-byte aligned) and register them keyed by the device address of
- * the CSR `col` array.  The arrays stay owned by the caller and must outlive the plan. */
+ * the CSR `col` array; n_src_rows = number of rows of the gathered operand (every source id < n_src_rows: N for a
+ * square operand, N + halo rows for a row partition).  The arrays stay owned by the caller and must outlive the plan. */
 int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N, int R,
                                int32_t* tile_ptr_host, int32_t* src_host, float* w_host);
-int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int R, const int32_t* tile_ptr_dev,
+int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int n_src_rows, int R, const int32_t* tile_ptr_dev,
                                  const int32_t* src_dev, const float* w_dev);
 int tgcn_rowtile_plan_destroy(int64_t handle);
 

@@ -6,6 +6,7 @@ from tgcn_b200 import _lib, workloads as wl
 from tgcn_b200.csr import build_csr, make_rowtile_plan
 lib = _lib.load()
 dev = torch.device("cuda")
+MODES = (4, 5, 6, 8)
 
 
 def run(name, L, C, K=4, reps=3, has_prev=False):
@@ -23,7 +24,13 @@ def run(name, L, C, K=4, reps=3, has_prev=False):
     stack = torch.randn(K, N, C, device=dev)
     byt = 2 * 4 * N * C + 8 * base.nnz + 4 * (N + 1)
     outs = {}
-    for vname, plan in ops.items():
+    runs = [("default", ops["default"], 1)]
+    for m in MODES:
+        runs += [("rtile4/b%d" % m, ops["rtile4"], m)]
+    runs += [("rtile8/b3", ops["rtile8"], 1), ("rtile8/b4", ops["rtile8"], 4)]
+    for vname, plan, mode in runs:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
+
         def steps():
             st = torch.cuda.current_stream().cuda_stream
             for k in range(1, K):

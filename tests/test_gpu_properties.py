@@ -307,3 +307,40 @@ def test_register_tiled_spmm_through_the_layer():
     assert rel(lay.weight.grad.cpu().numpy(), dW) < 1e-4
     assert rel(lay.bias.grad.cpu().numpy(), db) < 1e-4
     assert rel(x.grad.cpu().numpy(), dx) < 1e-4
+
+
+@pytest.mark.parametrize("mode", [1, 4, 5, 6, 8])          # SPMM_RTILE: the builds for 4/5/6/8 blocks per SM
+@pytest.mark.parametrize("R", [4, 8])
+def test_register_tiled_spmm_long_plan_runs_walk_global_memory(R, mode):
+    """Blocks whose tiles hold more (tile, source) pairs than the shared-memory stage (768) walk the plan in global
+    memory; a stretch of short rows IS staged.  Rows of 0, 1, 2, 3, 5 and ~150 entries, every occupancy build."""
+    from tgcn_b200 import _lib
+    from tgcn_b200.csr import build_csr
+    import scipy.sparse as sp
+    lib = _lib.load()
+    rng = np.random.default_rng(R)
+    n, C = 301, 72
+    A = sp.random(n, n, density=0.5, random_state=2, format="lil", dtype=np.float32)
+    for r, k in ((0, 0), (1, 1), (2, 2), (3, 3), (4, 5), (300, 0)):
+        A[r, :] = 0
+        A[r, :k] = 0.5
+    for r in range(112, 300):                # V = 18: blocks of 14 tiles = 56 (R=4) / 112 (R=8) rows; these are staged
+        A[r, :] = 0
+        A[r, r % 7:r % 7 + 6] = 0.25
+    A = A.tocsr()
+    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    prev = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    tiled = build_csr(A, torch.device("cuda"))
+    info = tiled.ensure_rowtile_plans(rows_per_tile=R, min_gain=0.0)
+    assert info
+    out = torch.full((n, C), float("nan"), device="cuda")
+    try:
+        assert lib.tgcn_set_tuning(b"SPMM_RTILE", mode) == 0
+        rc = lib.tgcn_spmm_step(tiled.rowptr.data_ptr(), tiled.col.data_ptr(), tiled.val.data_ptr(), n, x.data_ptr(),
+                                prev.data_ptr(), out.data_ptr(), C, 2.0, -1.0, st)
+        assert rc == 0, _lib.last_error()
+    finally:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
+    ref = 2.0 * (sp.csr_matrix(A, dtype=np.float64) @ x.double().cpu().numpy()) - prev.double().cpu().numpy()
+    assert float(np.abs(out.double().cpu().numpy() - ref).max()) <= 1e-5 * float(np.abs(ref).max())

@@ -162,8 +162,8 @@ def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5)
     lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, src.ctypes.data,
                                w.ctypes.data)
     dev_arrays = tuple(torch.from_numpy(a).to(col_dev.device) for a in (tile_ptr, src, w))
-    h = int(lib.tgcn_rowtile_plan_create(col_dev.data_ptr(), n, R, dev_arrays[0].data_ptr(), dev_arrays[1].data_ptr(),
-                                         dev_arrays[2].data_ptr()))
+    h = int(lib.tgcn_rowtile_plan_create(col_dev.data_ptr(), n, int(src.max()) + 1, R, dev_arrays[0].data_ptr(),
+                                         dev_arrays[1].data_ptr(), dev_arrays[2].data_ptr()))
     if h < 0:
         raise RuntimeError("tgcn_rowtile_plan_create failed: %s" % _lib.last_error())
     return h, dev_arrays, {"gain": c.size / total, "sources": total, "rows_per_tile": R}

@@ -518,50 +518,87 @@ __device__ __forceinline__ void rtile_apply(unsigned long long (&a)[4][R / 2], c
 }
 
 template <int R>
-__device__ __forceinline__ void rtile_load_w(const float* __restrict__ w, int64_t s, unsigned long long (&wp)[R / 2]) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(w + s * R);
+__device__ __forceinline__ void rtile_load_w(const float* w, int64_t s, unsigned long long (&wp)[R / 2]) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(w + s * R);   // shared or global (generic 16-byte loads)
 #pragma unroll
     for (int i = 0; i < R / 4; ++i) {
-        const ulonglong2 v = __ldg(p + i);
+        const ulonglong2 v = p[i];
         wp[2 * i] = v.x;
         wp[2 * i + 1] = v.y;
     }
 }
+
+// A block owns TY consecutive tiles, whose plan entries are ONE contiguous run of src[] / w[]: the run is copied into
+// shared memory by coalesced loads first (source ids pre-multiplied by the row pitch), so the dependent chain of a
+// source is LDS -> LDG.128 instead of LDG -> LDG -> LDG.128 (the first version, which walked the plan in global
+// memory, was latency-bound at 565 us on the 1M-vertex graph).  Runs longer than the stage are walked in global memory.
+constexpr int kRtCap = 768;        // staged (tile, source) pairs per block: 3 KB of ids + 768*R*4 bytes of coefficients
+constexpr int kRtMaxTiles = 32;
 
 template <bool kHasPrev, int R, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
                        int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
                        float alpha, float beta) {
-    const int tx = threadIdx.x;
-    const int t = blockIdx.x * blockDim.y + threadIdx.y;
-    if (t >= ntiles) return;
-    int s = __ldg(tile_ptr + t);
-    const int s1 = __ldg(tile_ptr + t + 1);
+    __shared__ __align__(16) float s_w[kRtCap * R];
+    __shared__ int s_src[kRtCap];
+    __shared__ int s_tp[kRtMaxTiles + 1];
+    constexpr int U = R == 4 ? 4 : 2;          // sources in flight per thread
+    const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+    const int tid = ty * V + tx, nthr = V * TY;
+    const int t0 = blockIdx.x * TY;
+    const int nt = min(TY, ntiles - t0);
+    for (int i = tid; i <= nt; i += nthr) s_tp[i] = __ldg(tile_ptr + t0 + i);
+    __syncthreads();
+    const int s_lo = s_tp[0], n_src = s_tp[nt] - s_lo;
+    const bool staged = n_src <= kRtCap;
+    if (staged) {
+        for (int i = tid; i < n_src; i += nthr) s_src[i] = __ldg(src + s_lo + i) * V;
+        const float4* wg = reinterpret_cast<const float4*>(w + (int64_t)s_lo * R);
+        float4* ws = reinterpret_cast<float4*>(s_w);
+        for (int i = tid; i < n_src * (R / 4); i += nthr) ws[i] = __ldg(wg + i);
+    }
+    __syncthreads();
+    if (ty >= nt) return;
     unsigned long long a[4][R / 2];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int p = 0; p < R / 2; ++p) a[c][p] = 0ull;
     const float4* inv = in + tx;
-    // two sources in flight per thread: both gathers and both coefficient vectors are issued before the first FFMA2
-    for (; s + 2 <= s1; s += 2) {
-        const int c0 = __ldg(src + s), c1 = __ldg(src + s + 1);
-        unsigned long long w0[R / 2], w1[R / 2];
-        rtile_load_w<R>(w, s, w0);
-        rtile_load_w<R>(w, s + 1, w1);
-        const float4 x0 = __ldg(inv + (int64_t)c0 * V);
-        const float4 x1 = __ldg(inv + (int64_t)c1 * V);
-        rtile_apply<R>(a, x0, w0);
-        rtile_apply<R>(a, x1, w1);
+    const int cnt = s_tp[ty + 1] - s_tp[ty];
+    if (staged) {
+        const int* sp = s_src + (s_tp[ty] - s_lo);
+        const float* wp = s_w + (size_t)(s_tp[ty] - s_lo) * R;
+        int j = 0;
+        for (; j + U <= cnt; j += U) {
+            int c[U];
+            unsigned long long wv[U][R / 2];
+            float4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = sp[j + u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = __ldg(inv + c[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) rtile_load_w<R>(wp, j + u, wv[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) rtile_apply<R>(a, x[u], wv[u]);
+        }
+        for (; j < cnt; ++j) {
+            unsigned long long wv[R / 2];
+            const float4 x = __ldg(inv + sp[j]);
+            rtile_load_w<R>(wp, j, wv);
+            rtile_apply<R>(a, x, wv);
+        }
+    } else {
+        for (int s = s_tp[ty]; s < s_tp[ty] + cnt; ++s) {
+            unsigned long long wv[R / 2];
+            const float4 x = __ldg(inv + (int64_t)__ldg(src + s) * V);
+            rtile_load_w<R>(w, s, wv);
+            rtile_apply<R>(a, x, wv);
+        }
     }
-    if (s < s1) {
-        const int c0 = __ldg(src + s);
-        unsigned long long w0[R / 2];
-        rtile_load_w<R>(w, s, w0);
-        rtile_apply<R>(a, __ldg(inv + (int64_t)c0 * V), w0);
-    }
-    const int row0 = t * R;
+    const int row0 = (t0 + ty) * R;
 #pragma unroll
     for (int p = 0; p < R / 2; ++p) {
         float lo[4], hi[4];
@@ -586,7 +623,7 @@ spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__
     }
 }
 
-struct RowTilePlan { const void* key; const int* tile_ptr; const int* src; const float* w; int R, N; bool live; };
+struct RowTilePlan { const void* key; const int* tile_ptr; const int* src; const float* w; int R, N, n_src_rows; bool live; };
 static std::mutex g_rt_mu;
 static std::vector<RowTilePlan> g_rt_plans;
 
@@ -654,13 +691,14 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         }
     }
     // register-tiled row-tile kernel: whenever a row-tile plan is registered for this operand ("SPMM_RTILE": 0 = off,
-    // 1 = on, 2 = on only for slabs that do not stay in L2)
+    // 1 = on with the default occupancy, 4/5/6/8 = compiled for that many blocks per SM)
     RowTilePlan rt;
     const int rt_mode = tuning_value(kTuneSpmmRtile);
-    if (vec && rt_mode != 0 && C / 4 <= 256 && (rt_mode != 2 || (int64_t)N * C * 4 >= (int64_t)96 << 20) &&
-        find_rowtile_plan(col, N, &rt)) {
+    if (vec && rt_mode != 0 && C / 4 <= 256 && find_rowtile_plan(col, N, &rt) &&
+        (int64_t)rt.n_src_rows * (C / 4) < ((int64_t)1 << 31)) {             // src * V stays in int32
         const int V = (int)(C / 4);
-        const int TY = 256 / V;
+        int TY = 256 / V;
+        if (TY > kRtMaxTiles) TY = kRtMaxTiles;
         const int ntiles = (int)ceil_div(N, rt.R);
         const unsigned blocks = (unsigned)ceil_div(ntiles, TY);
         const dim3 bd((unsigned)V, (unsigned)TY);
@@ -671,7 +709,12 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             else spmm_step_rtile_kernel<false, RR, MB><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
                                                                               (float4*)out, V, ntiles, alpha, beta); \
         } while (0)
-        if (rt.R == 8) TGCN_SPMM_RT(8, 3); else TGCN_SPMM_RT(4, 4);
+        if (rt.R == 8) {
+            if (rt_mode >= 4 && rt_mode != 8) TGCN_SPMM_RT(8, 4); else TGCN_SPMM_RT(8, 3);
+        } else {
+            if (rt_mode >= 8) TGCN_SPMM_RT(4, 8); else if (rt_mode == 6) TGCN_SPMM_RT(4, 6);
+            else if (rt_mode == 5) TGCN_SPMM_RT(4, 5); else TGCN_SPMM_RT(4, 4);
+        }
 #undef TGCN_SPMM_RT
         TGCN_LAUNCH_CHECK("spmm_step");
         return TGCN_OK;
@@ -924,15 +967,16 @@ extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int3
 }
 
 // Register / drop a row-tile plan for the CSR operand whose column array lives at device address `col_dev`
-// (device arrays owned by the caller; they must outlive the plan).  Returns a handle >= 0.
-extern "C" int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int R, const int32_t* tile_ptr_dev,
+// (device arrays owned by the caller; they must outlive the plan); n_src_rows = rows of the gathered operand
+// (every source id is < n_src_rows; N for a square operand, more with halo rows).  Returns a handle >= 0.
+extern "C" int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int n_src_rows, int R, const int32_t* tile_ptr_dev,
                                             const int32_t* src_dev, const float* w_dev) {
-    if (!col_dev || !tile_ptr_dev || !src_dev || !w_dev || (R != 4 && R != 8) || N < 1 || !aligned16(w_dev)) {
+    if (!col_dev || !tile_ptr_dev || !src_dev || !w_dev || (R != 4 && R != 8) || N < 1 || n_src_rows < 1 || !aligned16(w_dev)) {
         set_error(TGCN_ERR_INVALID, "tgcn_rowtile_plan_create: bad arguments");
         return -1;
     }
     std::lock_guard<std::mutex> lk(g_rt_mu);
-    const RowTilePlan np{col_dev, tile_ptr_dev, src_dev, w_dev, R, N, true};
+    const RowTilePlan np{col_dev, tile_ptr_dev, src_dev, w_dev, R, N, n_src_rows, true};
     for (size_t i = 0; i < g_rt_plans.size(); ++i)
         if (!g_rt_plans[i].live) { g_rt_plans[i] = np; return (int64_t)i; }
     g_rt_plans.push_back(np);

@@ -12,6 +12,11 @@ from .. import _lib
 # plans are only built on request (TGCN_SPMM_STAGED=1).
 import os as _os
 _STAGED_SPMM = _os.environ.get("TGCN_SPMM_STAGED", "0") not in ("", "0")
+# Register-tiled SpMM (csr.LaplacianCSR.ensure_rowtile_plans): TGCN_SPMM_ROWTILE=4|8 builds row-tile plans for every
+# streaming layer whose row order has locality (measured: 1M-vertex geometric graph 636 -> 535 us per recursion step,
+# cortical mesh 31 -> 28 us).  Opt-in because its summation order differs from the per-entry kernels' (results agree
+# to fp32 rounding, ~1e-7 relative, not bit for bit); bench.py switches it on for the streaming workloads.
+_ROWTILE_SPMM = int(_os.environ.get("TGCN_SPMM_ROWTILE", "0") or 0)
 
 
 def _ptr(t):
@@ -67,6 +72,8 @@ class ChebLayerFunction(torch.autograd.Function):
         b = None if bias is None else bias.contiguous()
         if _STAGED_SPMM:
             plan.ensure_block_plans()    # row-block staging of the SpMM when the row order has locality
+        if _ROWTILE_SPMM:
+            plan.ensure_rowtile_plans(rows_per_tile=_ROWTILE_SPMM)
         out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
         stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
         fw_bytes = int(lib.tgcn_layer_fwd_workspace(Q, N, D, G, K))
@@ -254,6 +261,8 @@ def cheb_basis(x, plan, K, recursion=_lib.RECURSION_REFERENCE, reference_layout=
     x = x.contiguous()
     if _STAGED_SPMM:
         plan.ensure_block_plans()
+    if _ROWTILE_SPMM:
+        plan.ensure_rowtile_plans(rows_per_tile=_ROWTILE_SPMM)
     stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
     with _DeviceGuard(dev):
         rc = lib.tgcn_cheb_basis(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(stack), Q, D, K,
