@@ -219,14 +219,12 @@ def run_b200(args):
     broadcast_parameters(model)
     N0 = Ls[0].shape[0]
     rowtile_info = []
-    if args.rowtile:
+    if args.rowtile and args.workload == "mesh32k":
         # streaming layers only (the resident kernels keep the operand in shared memory and never call the SpMM)
         for name in ("tgcn1", "gcn2"):
-            lay = getattr(model, name, None)
-            if lay is None:
-                continue
-            plan = lay._plan(dev)
+            lay = getattr(model, name)
             K_, G_ = lay.weight.shape[0], lay.weight.shape[-1]
+            plan = lay._plan(dev)
             if not lay._use_resident(plan, lay.weight.numel() // (K_ * G_), G_, K_):
                 rowtile_info += [dict(i[2], layer=name) for i in plan.ensure_rowtile_plans(rows_per_tile=args.rowtile)]
     # the first layer's gradients are produced last: their (small) bucket is reduced after the others,

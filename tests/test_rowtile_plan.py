@@ -74,3 +74,30 @@ def test_plan_counts_shared_sources_once_and_rejects_bad_arguments():
     src = np.zeros(16, np.int32)
     assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, tp.ctypes.data, src.ctypes.data, None) == -1
     assert lib.tgcn_rowtile_plan_destroy(12345) != 0
+
+
+def test_make_rowtile_plan_registers_and_filters_by_locality():
+    """csr.make_rowtile_plan: host plan + registration keyed by the `col` array (a CPU tensor stands in for the device
+    array here -- nothing is launched); operands without locality are refused by min_gain."""
+    import torch
+    from tgcn_b200.csr import make_rowtile_plan
+    lib = _lib.load()
+    # a banded matrix in natural order: neighbouring rows share sources
+    n = 64
+    band = sp.diags([1.0, 2.0, 3.0, 2.0, 1.0], [-2, -1, 0, 1, 2], shape=(n, n), format="csr", dtype=np.float32)
+    col_t = torch.from_numpy(band.indices.astype(np.int32))
+    made = make_rowtile_plan(band.indptr, band.indices, band.data, n, 8, col_t, min_gain=1.5)
+    assert made is not None
+    h, arrays, stats = made
+    assert stats["rows_per_tile"] == 8 and stats["sources"] == int(arrays[0][-1]) and stats["gain"] > 2.5
+    assert arrays[2].shape == (stats["sources"], 8) and int(arrays[1].max()) < n
+    assert lib.tgcn_rowtile_plan_destroy(h) == 0
+    assert lib.tgcn_rowtile_plan_destroy(h) != 0                      # already dropped
+    # a random permutation destroys the locality: one source per entry, gain ~1 -> no plan
+    rng = np.random.default_rng(0)
+    p = rng.permutation(n)
+    scattered = sp.csr_matrix(sp.random(n, n, density=0.02, random_state=1, dtype=np.float32))[p][:, p].tocsr()
+    col_s = torch.from_numpy(scattered.indices.astype(np.int32))
+    assert make_rowtile_plan(scattered.indptr, scattered.indices, scattered.data, n, 4, col_s, min_gain=1.5) is None
+    # empty operand
+    assert make_rowtile_plan(np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), 4, 4, col_s) is None
