@@ -226,7 +226,7 @@ def run_b200(args):
             K_, G_ = lay.weight.shape[0], lay.weight.shape[-1]
             plan = lay._plan(dev)
             if not lay._use_resident(plan, lay.weight.numel() // (K_ * G_), G_, K_):
-                rowtile_info += [dict(i[2], layer=name) for i in plan.ensure_rowtile_plans(rows_per_tile=args.rowtile)]
+                rowtile_info += [dict(i[2], layer=name) for i in plan.ensure_rowtile_plans(rows_per_tile=args.rowtile, pad=args.rowtile_pad)]
     # the first layer's gradients are produced last: their (small) bucket is reduced after the others,
     # whose allreduce runs under the layer-1 backward
     # N > 1 (default): gradient allreduce fused with the SGD update over NVLink peer memory (csrc/peer.cu);
@@ -440,7 +440,8 @@ def run_rgg(args):
     K, H, Fin, G, Q = 8, 3, 64, 64, args.batch or 1
     D = H * Fin
     L, _ = wl.random_geometric(n=n, mean_degree=12.0, seed=0)
-    layer = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev, rows_per_tile=args.rowtile)
+    layer = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev, rows_per_tile=args.rowtile,
+                                rowtile_pad=args.rowtile_pad)
     n_own = layer.n_own
     gen = torch.Generator().manual_seed(0)
     bound = 1.0 / (Fin * K) ** 0.5
@@ -754,6 +755,8 @@ def main():
                          "after the backward; nccl = bucketed NCCL + torch SGD")
     ap.add_argument("--rowtile", type=int, default=ROWTILE_DEFAULT, choices=[0, 4, 8],
                     help="rows per tile of the register-tiled SpMM kernel for the streaming layers (0 = per-entry kernels)")
+    ap.add_argument("--rowtile-pad", type=int, default=1,
+                    help="pad every row tile's plan to a multiple of this many entries (1 = none, the measured configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,6 +21,10 @@ def run(name, L, C, K=4, reps=3, has_prev=False):
         p._rowtiles = [made]
         ops["rtile%d" % R] = p
         print("%s: row-tile plan R=%d built in %.1f s, gain %.2f, %d sources" % (name, R, time.time() - t0, made[2]["gain"], made[2]["sources"]), flush=True)
+    for R, pad in ((4, 8), (4, 4), (8, 4)):             # padded plans: no one-at-a-time tail loop in the kernel
+        p = build_csr(L, dev)
+        p._rowtiles = [make_rowtile_plan(host[0], host[1], host[2], N, R, p.col, min_gain=0.0, pad=pad)]
+        ops["rtile%dp%d" % (R, pad)] = p
     stack = torch.randn(K, N, C, device=dev)
     byt = 2 * 4 * N * C + 8 * base.nnz + 4 * (N + 1)
     outs = {}
@@ -28,6 +32,7 @@ def run(name, L, C, K=4, reps=3, has_prev=False):
     for m in MODES:
         runs += [("rtile4/b%d" % m, ops["rtile4"], m)]
     runs += [("rtile8/b3", ops["rtile8"], 1), ("rtile8/b4", ops["rtile8"], 4)]
+    runs += [(k, v, 1) for k, v in ops.items() if "p" in k]
     for vname, plan, mode in runs:
         lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
 

@@ -9,17 +9,17 @@ import scipy.sparse as sp
 from tgcn_b200 import _lib
 
 
-def _plan(m, R):
+def _plan(m, R, pad=1):
     lib = _lib.load()
     m = m.tocsr(); m.sort_indices()
     rp = m.indptr.astype(np.int32); c = m.indices.astype(np.int32); v = m.data.astype(np.float32)
     n = m.shape[0]
     nt = (n + R - 1) // R
     tile_ptr = np.full(nt + 1, -1, np.int32)
-    total = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, None, None)
+    total = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, pad, tile_ptr.ctypes.data, None, None)
     src = np.full(max(total, 1), -1, np.int32)
     w = np.full((max(total, 1), R), np.nan, np.float32)
-    total2 = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data,
+    total2 = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, pad, tile_ptr.ctypes.data,
                                         src.ctypes.data, w.ctypes.data)
     assert total == total2 == tile_ptr[nt]
     return rp, c, v, tile_ptr, src[:total], w[:total]
@@ -60,6 +60,28 @@ def test_plan_replay_equals_sparse_product(R, n):
     assert np.count_nonzero(w) == np.count_nonzero(v)
 
 
+@pytest.mark.parametrize("R", [4, 8])
+@pytest.mark.parametrize("pad", [2, 4, 8])
+def test_padded_plan_is_the_unpadded_plan_plus_zero_coefficient_repeats(R, pad):
+    n = 203
+    rng = np.random.default_rng(pad)
+    m = sp.random(n, n, density=0.03, random_state=7, format="lil", dtype=np.float32)
+    m[8:16, :] = 0                                   # an empty tile (R = 8) / two empty tiles (R = 4): stays empty
+    m = m.tocsr()
+    rp, c, v, tp0, src0, w0 = _plan(m, R, 1)
+    _, _, _, tp, src, w = _plan(m, R, pad)
+    for t in range(len(tp) - 1):
+        k = tp0[t + 1] - tp0[t]
+        s0, s1 = tp[t], tp[t + 1]
+        assert s1 - s0 == (k + pad - 1) // pad * pad
+        assert np.array_equal(src[s0:s0 + k], src0[tp0[t]:tp0[t + 1]]) and np.array_equal(w[s0:s0 + k], w0[tp0[t]:tp0[t + 1]])
+        if k:
+            assert np.all(src[s0 + k:s1] == src[s0 + k - 1]) and np.all(w[s0 + k:s1] == 0)
+    x = rng.standard_normal((n, 3))
+    ref = sp.csr_matrix((v.astype(np.float64), c, rp), shape=(n, n)) @ x
+    np.testing.assert_allclose(_replay(tp, src, w, x, n, R), ref, rtol=1e-12, atol=1e-12)
+
+
 def test_plan_counts_shared_sources_once_and_rejects_bad_arguments():
     lib = _lib.load()
     # 8 rows that all read sources {0, 1}: one tile of 8 has 2 sources, two tiles of 4 have 2 each
@@ -69,10 +91,12 @@ def test_plan_counts_shared_sources_once_and_rejects_bad_arguments():
         assert len(src) == want and np.all(w[:, :] == np.where(src[:, None] == 0, 1.0, 2.0))
     rp = m.indptr.astype(np.int32); c = m.indices.astype(np.int32); v = m.data.astype(np.float32)
     tp = np.zeros(9, np.int32)
-    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 3, tp.ctypes.data, None, None) == -1
-    assert lib.tgcn_rowtile_plan_host(None, c.ctypes.data, v.ctypes.data, 8, 8, tp.ctypes.data, None, None) == -1
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 3, 1, tp.ctypes.data, None, None) == -1
+    assert lib.tgcn_rowtile_plan_host(None, c.ctypes.data, v.ctypes.data, 8, 8, 1, tp.ctypes.data, None, None) == -1
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, 0, tp.ctypes.data, None, None) == -1
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, 17, tp.ctypes.data, None, None) == -1
     src = np.zeros(16, np.int32)
-    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, tp.ctypes.data, src.ctypes.data, None) == -1
+    assert lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, 8, 8, 1, tp.ctypes.data, src.ctypes.data, None) == -1
     assert lib.tgcn_rowtile_plan_destroy(12345) != 0
 
 
@@ -89,7 +113,10 @@ def test_make_rowtile_plan_registers_and_filters_by_locality():
     made = make_rowtile_plan(band.indptr, band.indices, band.data, n, 8, col_t, min_gain=1.5)
     assert made is not None
     h, arrays, stats = made
-    assert stats["rows_per_tile"] == 8 and stats["sources"] == int(arrays[0][-1]) and stats["gain"] > 2.5
+    assert stats["rows_per_tile"] == 8 and stats["sources"] == stats["entries"] == int(arrays[0][-1]) and stats["gain"] > 2.5
+    padded = make_rowtile_plan(band.indptr, band.indices, band.data, n, 8, col_t, min_gain=1.5, pad=8)
+    assert padded[2]["sources"] == stats["sources"] and padded[2]["entries"] % 8 == 0 and padded[2]["entries"] == int(padded[1][0][-1])
+    assert padded[2]["gain"] == stats["gain"] and lib.tgcn_rowtile_plan_destroy(padded[0]) == 0
     assert arrays[2].shape == (stats["sources"], 8) and int(arrays[1].max()) < n
     assert lib.tgcn_rowtile_plan_destroy(h) == 0
     assert lib.tgcn_rowtile_plan_destroy(h) != 0                      # already dropped

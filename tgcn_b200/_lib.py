@@ -30,7 +30,7 @@ SIGNATURES = {
     "tgcn_block_plan_host": (_l, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "tgcn_plan_create": (_l, [_p, _i, _p, _p, _p, _i, _i]),
     "tgcn_plan_destroy": (_i, [_l]),
-    "tgcn_rowtile_plan_host": (_l, [_p, _p, _p, _i, _i, _p, _p, _p]),
+    "tgcn_rowtile_plan_host": (_l, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "tgcn_rowtile_plan_create": (_l, [_p, _i, _i, _i, _p, _p, _p]),
     "tgcn_rowtile_plan_destroy": (_i, [_l]),
     "tgcn_to_slab": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -71,7 +71,7 @@ class LaplacianCSR:
             self._blocks = made
         return self._blocks
 
-    def ensure_rowtile_plans(self, rows_per_tile=8, min_gain=1.5):
+    def ensure_rowtile_plans(self, rows_per_tile=8, min_gain=1.5, pad=1):
         """Row-tile plans for the register-tiled SpMM kernel (include/tgcn_b200.h, tgcn_rowtile_plan_create): built
         once per device for L (and L^T when it differs) and registered with the library when the row order has enough
         locality (see `make_rowtile_plan`).  Idempotent."""
@@ -86,7 +86,7 @@ class LaplacianCSR:
             if not self.symmetric:
                 variants.append((host[3], host[4], host[5], self.col_t))
             for rp, c, v, col_dev in variants:
-                one = make_rowtile_plan(rp, c, v, self.n, rows_per_tile, col_dev, min_gain)
+                one = make_rowtile_plan(rp, c, v, self.n, rows_per_tile, col_dev, min_gain, pad)
                 if one is not None:
                     made.append(one)
             self._rowtiles = made
@@ -137,12 +137,15 @@ class LaplacianCSR:
         return hit
 
 
-def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5):
+def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5, pad=1):
     """Build (host, tgcn_rowtile_plan_host) and register (tgcn_rowtile_plan_create) the row-tile plan of the CSR
     operand `rowptr/col/val` (int32/int32/float32 numpy, `n` rows) whose column array lives on the device as
     `col_dev`.  Returns (handle, device arrays to keep alive, stats), or None when the row order has too little
     locality: CSR entries / distinct (tile, source row) pairs < min_gain -- below that the kernel would do as many
-    gathers as the per-entry kernels and R times their multiply-adds."""
+    gathers as the per-entry kernels and R times their multiply-adds.  pad > 1 pads every tile to a multiple of `pad`
+    entries (zero coefficients) so the kernel never runs its one-at-a-time tail loop; the measured configuration is
+    pad=1 (the ncu source view of the round-1 capture puts ~40 % of the gather latency in that tail: pad=8 is the
+    first thing to measure next).  The gain is computed on the unpadded count."""
     from . import _lib
     lib = _lib.load()
     R = int(rows_per_tile)
@@ -152,21 +155,26 @@ def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5)
     if n < 1 or c.size == 0:
         return None
     tile_ptr = np.zeros((n + R - 1) // R + 1, dtype=np.int32)
-    total = int(lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, None, None))
-    if total <= 0:
+    distinct = int(lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, 1, tile_ptr.ctypes.data, None, None))
+    if distinct <= 0:
         raise RuntimeError("tgcn_rowtile_plan_host rejected the CSR operand (rows_per_tile=%d)" % R)
-    if c.size / total < min_gain:
+    if c.size / distinct < min_gain:
         return None
+    pad = int(pad)
+    total = distinct if pad == 1 else int(lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, pad,
+                                                                     tile_ptr.ctypes.data, None, None))
+    if total <= 0:
+        raise RuntimeError("tgcn_rowtile_plan_host rejected pad=%d" % pad)
     src = np.zeros(total, dtype=np.int32)
     w = np.zeros((total, R), dtype=np.float32)
-    lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, tile_ptr.ctypes.data, src.ctypes.data,
+    lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, n, R, pad, tile_ptr.ctypes.data, src.ctypes.data,
                                w.ctypes.data)
     dev_arrays = tuple(torch.from_numpy(a).to(col_dev.device) for a in (tile_ptr, src, w))
     h = int(lib.tgcn_rowtile_plan_create(col_dev.data_ptr(), n, int(src.max()) + 1, R, dev_arrays[0].data_ptr(),
                                          dev_arrays[1].data_ptr(), dev_arrays[2].data_ptr()))
     if h < 0:
         raise RuntimeError("tgcn_rowtile_plan_create failed: %s" % _lib.last_error())
-    return h, dev_arrays, {"gain": c.size / total, "sources": total, "rows_per_tile": R}
+    return h, dev_arrays, {"gain": c.size / distinct, "sources": distinct, "rows_per_tile": R, "pad": pad, "entries": total}
 
 
 def _to_scipy_like(L):

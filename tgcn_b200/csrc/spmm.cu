@@ -928,10 +928,12 @@ extern "C" int tgcn_plan_destroy(int64_t handle) {
 // Host-side row-tile plan for spmm_step_rtile_kernel: per tile of R consecutive rows (R = 4 or 8) the distinct source
 // rows in ascending order, each with its R coefficients (row-major inside the tile, 0 where absent; duplicate (row,
 // col) entries are summed in CSR order).  tile_ptr_host[ceil(N/R)+1]; src_host / w_host: capacity = nnz sources
-// (w: nnz*R floats); both NULL: size query.  Returns the total number of (tile, source) pairs, -1 on bad arguments.
+// (w: nnz*R floats) without padding -- use the size query; both NULL: size query.  pad >= 1: every non-empty tile's
+// run is padded to a multiple of `pad` entries with zero-coefficient repeats of its last source (1 = no padding).
+// Returns the total number of (tile, source) pairs including the padding, -1 on bad arguments.
 extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
-                                          int R, int32_t* tile_ptr_host, int32_t* src_host, float* w_host) {
-    if (N < 0 || (R != 4 && R != 8) || !rowptr_host || (rowptr_host[N] > 0 && (!col_host || !val_host))) return -1;
+                                          int R, int pad, int32_t* tile_ptr_host, int32_t* src_host, float* w_host) {
+    if (N < 0 || (R != 4 && R != 8) || pad < 1 || pad > 16 || !rowptr_host || (rowptr_host[N] > 0 && (!col_host || !val_host))) return -1;
     if ((src_host == nullptr) != (w_host == nullptr)) return -1;
     const int nt = (int)ceil_div(N, R);
     int64_t total = 0;
@@ -943,6 +945,7 @@ extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int3
         for (int e = e0; e < e1; ++e) ent.push_back({col_host[e], e});
         std::sort(ent.begin(), ent.end());
         if (tile_ptr_host) tile_ptr_host[t] = (int32_t)total;
+        const int64_t tile_start = total;
         int r = r0;                                    // row lookup for CSR positions: positions ascend within a source
         for (size_t i = 0; i < ent.size();) {
             size_t j = i;
@@ -961,6 +964,15 @@ extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int3
             ++total;
             i = j;
         }
+        // pad the tile's run to a multiple of `pad` with zero-coefficient repeats of its last source (an L1 hit for the
+        // kernel), so that a kernel that keeps `pad` gathers in flight never runs its one-at-a-time tail loop
+        if (!ent.empty())
+            for (; (total - tile_start) % pad != 0; ++total) {
+                if (src_host) {
+                    src_host[total] = ent.back().first;
+                    for (int q = 0; q < R; ++q) w_host[total * R + q] = 0.f;
+                }
+            }
     }
     if (tile_ptr_host) tile_ptr_host[nt] = (int32_t)total;
     return total;

@@ -378,9 +378,10 @@ class RowPartitionedLayer:
     use, as in the reference models where the input does not require grad)."""
 
     def __init__(self, L_csr, K, D, G, rank=0, world=1, device=None, recursion=0, engine=0, group=None,
-                 rows_per_tile=0):
+                 rows_per_tile=0, rowtile_pad=1):
         """rows_per_tile = 4 or 8: register the row-tile plan of this rank's rows (register-tiled SpMM kernel,
-        include/tgcn_b200.h `tgcn_rowtile_plan_create`) when the row order has locality; 0: per-entry kernels."""
+        include/tgcn_b200.h `tgcn_rowtile_plan_create`) when the row order has locality; 0: per-entry kernels.
+        rowtile_pad: see csr.make_rowtile_plan."""
         from . import _lib
         self.lib = _lib.load()
         self.K, self.D, self.G = K, D, G
@@ -403,7 +404,7 @@ class RowPartitionedLayer:
         self.rowtile = None
         if rows_per_tile:
             from .csr import make_rowtile_plan
-            self.rowtile = make_rowtile_plan(pl.rowptr, pl.col, pl.val, self.n_own, rows_per_tile, self.col)
+            self.rowtile = make_rowtile_plan(pl.rowptr, pl.col, pl.val, self.n_own, rows_per_tile, self.col, pad=rowtile_pad)
 
     def __del__(self):
         try:
