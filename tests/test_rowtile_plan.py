@@ -128,3 +128,33 @@ def test_make_rowtile_plan_registers_and_filters_by_locality():
     assert make_rowtile_plan(scattered.indptr, scattered.indices, scattered.data, n, 4, col_s, min_gain=1.5) is None
     # empty operand
     assert make_rowtile_plan(np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), 4, 4, col_s) is None
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_plan_of_a_row_partition_replays_to_the_global_product(world):
+    """Config 4: every rank builds the row-tile plan of ITS rows over the extended (own + halo) column space
+    (tgcn_b200.parallel.RowPartition); replayed on the extended slab it gives the global product's rows."""
+    from tgcn_b200.parallel import RowPartition
+    from tgcn_b200 import workloads as wl
+    L, _ = wl.random_geometric(n=3001, mean_degree=10.0, seed=3)
+    L = sp.csr_matrix(L)
+    n = L.shape[0]
+    rng = np.random.default_rng(world)
+    x = rng.standard_normal((n, 4))
+    ref = sp.csr_matrix(L, dtype=np.float64) @ x
+    lib = _lib.load()
+    for rank in range(world):
+        part = RowPartition(L, rank, world)
+        x_ext = np.concatenate([x[part.lo:part.hi], x[part.halo_ids]])          # owned rows, then halo rows by global id
+        R = 4
+        nt = (part.n_own + R - 1) // R
+        tp = np.zeros(nt + 1, np.int32)
+        rp, c, v = part.rowptr, part.col, part.val
+        total = lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, part.n_own, R, 1, tp.ctypes.data, None, None)
+        src = np.zeros(total, np.int32); w = np.zeros((total, R), np.float32)
+        lib.tgcn_rowtile_plan_host(rp.ctypes.data, c.ctypes.data, v.ctypes.data, part.n_own, R, 1, tp.ctypes.data, src.ctypes.data,
+                                   w.ctypes.data)
+        assert src.max() < part.n_own + part.n_halo and (world == 1 or src.max() >= part.n_own)   # halo rows are gathered
+        got = _replay(tp, src, w, x_ext, part.n_own, R)
+        np.testing.assert_allclose(got, ref[part.lo:part.hi], rtol=1e-6, atol=1e-7)    # fp32 coefficients vs fp64 product of fp32 values
+        assert total < c.size / 1.3                                                      # the strip+Morton order shares sources
