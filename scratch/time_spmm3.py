@@ -33,6 +33,7 @@ def run(name, L, C, K=4, reps=3, has_prev=False):
         runs += [("rtile4/b%d" % m, ops["rtile4"], m)]
     runs += [("rtile8/b3", ops["rtile8"], 1), ("rtile8/b4", ops["rtile8"], 4)]
     runs += [(k, v, 1) for k, v in ops.items() if "p" in k]
+    runs += [("rtile4/remap", ops["rtile4"], 16), ("rtile8/remap", ops["rtile8"], 16), ("rtile4p8/remap", ops["rtile4p8"], 16)]
     for vname, plan, mode in runs:
         lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
 

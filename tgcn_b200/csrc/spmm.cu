@@ -535,7 +535,10 @@ __device__ __forceinline__ void rtile_load_w(const float* w, int64_t s, unsigned
 constexpr int kRtCap = 768;        // staged (tile, source) pairs per block: 3 KB of ids + 768*R*4 bytes of coefficients
 constexpr int kRtMaxTiles = 32;
 
-template <bool kHasPrev, int R, int MINB>
+// kRemap (experimental, "SPMM_RTILE" = 16, unmeasured): block b works on tile group (b mod 148) * per + b / 148, so the
+// blocks that are resident on one SM together, and the ones that follow them there, own ADJACENT tile groups and find
+// each other's source rows in that SM's L1 (ncu: 2.6 GB of L2 -> L1 fills for a 768 MB slab with the identity mapping).
+template <bool kHasPrev, int R, int MINB, bool kRemap = false>
 __global__ void __launch_bounds__(256, MINB)
 spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
                        int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
@@ -546,7 +549,15 @@ spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__
     constexpr int U = R == 4 ? 4 : 2;          // sources in flight per thread
     const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
     const int tid = ty * V + tx, nthr = V * TY;
-    const int t0 = blockIdx.x * TY;
+    int t0;
+    if constexpr (kRemap) {
+        int group = (int)blockIdx.x;
+        const int per = (int)gridDim.x / kNumSMs;          // a bijection on [0, per * 148); the remainder keeps its index
+        if (group < per * kNumSMs) group = (group % kNumSMs) * per + group / kNumSMs;
+        t0 = group * TY;
+    } else {
+        t0 = blockIdx.x * TY;
+    }
     const int nt = min(TY, ntiles - t0);
     for (int i = tid; i <= nt; i += nthr) s_tp[i] = __ldg(tile_ptr + t0 + i);
     __syncthreads();
@@ -691,7 +702,8 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         }
     }
     // register-tiled row-tile kernel: whenever a row-tile plan is registered for this operand ("SPMM_RTILE": 0 = off,
-    // 1 = on with the default occupancy, 4/5/6/8 = compiled for that many blocks per SM)
+    // 1 = on with the default occupancy, 4/5/6/8 = compiled for that many blocks per SM, 16 = default occupancy with the
+    // experimental SM-contiguous block mapping)
     RowTilePlan rt;
     const int rt_mode = tuning_value(kTuneSpmmRtile);
     if (vec && rt_mode != 0 && C / 4 <= 256 && find_rowtile_plan(col, N, &rt) &&
@@ -709,13 +721,23 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             else spmm_step_rtile_kernel<false, RR, MB><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
                                                                               (float4*)out, V, ntiles, alpha, beta); \
         } while (0)
-        if (rt.R == 8) {
+#define TGCN_SPMM_RT_REMAP(RR, MB)                                                                                  \
+        do {                                                                                                        \
+            if (prev) spmm_step_rtile_kernel<true, RR, MB, true><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
+                                                                                        (const float4*)prev, (float4*)out, V, ntiles, alpha, beta); \
+            else spmm_step_rtile_kernel<false, RR, MB, true><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
+                                                                                    (float4*)out, V, ntiles, alpha, beta); \
+        } while (0)
+        if (rt_mode >= 16) {                                    // experimental SM-contiguous block mapping
+            if (rt.R == 8) TGCN_SPMM_RT_REMAP(8, 3); else TGCN_SPMM_RT_REMAP(4, 4);
+        } else if (rt.R == 8) {
             if (rt_mode >= 4 && rt_mode != 8) TGCN_SPMM_RT(8, 4); else TGCN_SPMM_RT(8, 3);
         } else {
             if (rt_mode >= 8) TGCN_SPMM_RT(4, 8); else if (rt_mode == 6) TGCN_SPMM_RT(4, 6);
             else if (rt_mode == 5) TGCN_SPMM_RT(4, 5); else TGCN_SPMM_RT(4, 4);
         }
 #undef TGCN_SPMM_RT
+#undef TGCN_SPMM_RT_REMAP
         TGCN_LAUNCH_CHECK("spmm_step");
         return TGCN_OK;
     }
