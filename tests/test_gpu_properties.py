@@ -5,6 +5,8 @@
 * K=1 reduces to a per-vertex dense contraction
 * data-parallel invariance: batch halves give the same outputs / summed weight gradients
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -311,7 +313,7 @@ def test_register_tiled_spmm_through_the_layer():
 
 # SPMM_RTILE: the builds for 4/5/6/8 blocks per SM; 16 = the experimental SM-contiguous block mapping, which has not run on
 # a GPU yet (written after the round's GPU budget was spent): opt in with TGCN_EXPERIMENTAL=1
-_RT_MODES = [1, 4, 5, 6, 8] + ([16] if __import__("os").environ.get("TGCN_EXPERIMENTAL") == "1" else [])
+_RT_MODES = [1, 4, 5, 6, 8] + ([16] if os.environ.get("TGCN_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.mark.parametrize("mode", _RT_MODES)
