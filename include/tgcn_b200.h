@@ -95,7 +95,10 @@ int tgcn_plan_destroy(int64_t handle);
  * (tile, source) pairs; pad > 1 pads every non-empty tile to a multiple of `pad` entries with zero-coefficient repeats
  * of its last source, so a kernel with `pad` gathers in flight has no one-at-a-time tail; 1 = no padding); upload the arrays (w_dev 16-byte aligned) and register them keyed by the device address of
  * the CSR `col` array; n_src_rows = number of rows of the gathered operand (every source id < n_src_rows: N for a
- * square operand, N + halo rows for a row partition).  The arrays stay owned by the caller and must outlive the plan. */
+ * square operand, N + halo rows for a row partition).  The arrays stay owned by the caller and must outlive the plan.
+ * A plan holds the operand's VALUES (the coefficient vectors): destroy and rebuild it when val[] changes.  A zero
+ * coefficient still multiplies its source row, so a non-finite activation reaches every row of a tile that shares the
+ * source (exact for finite inputs). */
 int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N, int R,
                                int pad, int32_t* tile_ptr_host, int32_t* src_host, float* w_host);
 int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int n_src_rows, int R, const int32_t* tile_ptr_dev,
