@@ -66,8 +66,8 @@ long long tgcn_launch_count(void);
  * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes), "RES_ENT" =
  * keep each thread's CSR entries in registers across the K steps of the resident forward (bit-identical; 0 default:
  * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us), "SPMM_RTILE" = use
- * registered row-tile plans (1; 4/5/6/8 = the build for that many blocks per SM; 16 = experimental SM-contiguous
- * block mapping, unmeasured; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
+ * registered row-tile plans (1; 4/5/6/8 = the build for that many blocks per SM; 16 = SM-contiguous block mapping,
+ * measured 4 % slower, kept as a recorded experiment; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
 int tgcn_set_tuning(const char* key, int value);
 
 /* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */

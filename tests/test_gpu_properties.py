@@ -311,8 +311,8 @@ def test_register_tiled_spmm_through_the_layer():
     assert rel(x.grad.cpu().numpy(), dx) < 1e-4
 
 
-# SPMM_RTILE: the builds for 4/5/6/8 blocks per SM; 16 = the experimental SM-contiguous block mapping, which has not run on
-# a GPU yet (written after the round's GPU budget was spent): opt in with TGCN_EXPERIMENTAL=1
+# SPMM_RTILE: the builds for 4/5/6/8 blocks per SM; 16 = the SM-contiguous block mapping experiment (ran once on a B200:
+# bit-identical output, 4 % slower; it has not been through this test on a GPU): opt in with TGCN_EXPERIMENTAL=1
 _RT_MODES = [1, 4, 5, 6, 8] + ([16] if os.environ.get("TGCN_EXPERIMENTAL") == "1" else [])
 
 

@@ -143,9 +143,9 @@ def make_rowtile_plan(rowptr, col, val, n, rows_per_tile, col_dev, min_gain=1.5,
     `col_dev`.  Returns (handle, device arrays to keep alive, stats), or None when the row order has too little
     locality: CSR entries / distinct (tile, source row) pairs < min_gain -- below that the kernel would do as many
     gathers as the per-entry kernels and R times their multiply-adds.  pad > 1 pads every tile to a multiple of `pad`
-    entries (zero coefficients) so the kernel never runs its one-at-a-time tail loop; the measured configuration is
-    pad=1 (the ncu source view of the round-1 capture puts ~40 % of the gather latency in that tail: pad=8 is the
-    first thing to measure next).  The gain is computed on the unpadded count."""
+    entries (zero coefficients) so the kernel never runs its one-at-a-time tail loop: measured -2.4 % at pad=8 on the
+    1M-vertex graph (profiles/r01/spmm_variants.txt); the recorded bench lines use pad=1.  The gain is computed on the
+    unpadded count."""
     from . import _lib
     lib = _lib.load()
     R = int(rows_per_tile)

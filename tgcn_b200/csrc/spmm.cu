@@ -535,9 +535,10 @@ __device__ __forceinline__ void rtile_load_w(const float* w, int64_t s, unsigned
 constexpr int kRtCap = 768;        // staged (tile, source) pairs per block: 3 KB of ids + 768*R*4 bytes of coefficients
 constexpr int kRtMaxTiles = 32;
 
-// kRemap (experimental, "SPMM_RTILE" = 16, unmeasured): block b works on tile group (b mod 148) * per + b / 148, so the
-// blocks that are resident on one SM together, and the ones that follow them there, own ADJACENT tile groups and find
-// each other's source rows in that SM's L1 (ncu: 2.6 GB of L2 -> L1 fills for a 768 MB slab with the identity mapping).
+// kRemap (experiment, "SPMM_RTILE" = 16): block b works on tile group (b mod 148) * per + b / 148, so the blocks that are
+// resident on one SM together, and the ones that follow them there, own ADJACENT tile groups and find each other's source
+// rows in that SM's L1.  Measured 4 % SLOWER than the identity mapping on the 1M-vertex graph (bit-identical output;
+// profiles/r01/spmm_variants.txt): kept only as the recorded negative result, never selected by default.
 template <bool kHasPrev, int R, int MINB, bool kRemap = false>
 __global__ void __launch_bounds__(256, MINB)
 spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
