@@ -52,6 +52,16 @@ extern "C" {
 #define TGCN_ENGINE_TCGEN05 2 /* tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulate in TMEM   */
 #define TGCN_ENGINE_RESIDENT 3 /* sample-resident fused layer kernels (small graphs), fp32 FFMA    */
 
+/* Fused dropout (nn.Dropout of the reference models, pytorch_hcp_tgcn.py:106,125,136,150): out = x * mask / (1-p)
+ * with mask ~ Bernoulli(1-p) drawn per activation element from a counter-based hash of (seed, *step, element index).
+ * `step` points to a device uint32 the caller advances once per training step (NULL: 0), so a CUDA-graph replay
+ * draws a fresh mask.  NULL descriptor or p <= 0: no dropout.  p must be < 1. */
+typedef struct tgcn_dropout {
+    float p;
+    uint32_t seed;
+    const uint32_t* step;
+} tgcn_dropout_t;
+
 int tgcn_version(void);
 const char* tgcn_last_error(void);
 /* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
@@ -167,13 +177,15 @@ int tgcn_bias_grad(const float* dout, float* db, void* workspace, int Q, int N, 
 /* ---- K3: permuted max-pool ---------------------------------------------------------------- */
 /* y[q,m,g] = max_{s<p} x[q,m*p+s,g]; idx = first maximal s (NaN wins), torch.max(dim) rule.
  * Replaces gcn_pool / gcn_pool_4 (gcn.py:246-255).  `relu` != 0 applies max(x,0) first
- * (F.relu before the pool, pytorch_hcp_tgcn.py:135-137).  idx is uint8 [Q,N/p,G]. */
+ * (F.relu before the pool, pytorch_hcp_tgcn.py:135-137); `drop` (needs relu) then applies the dropout that sits
+ * between them (drop1, pytorch_hcp_tgcn.py:136).  idx is uint8 [Q,N/p,G]. */
 int tgcn_pool_max_fwd(const float* x, float* y, uint8_t* idx, int Q, int N, int G, int p, int relu,
-                      void* stream);
-/* dx[q,m*p+s,g] = (s == idx) ? dy[q,m,g] : 0; with relu: additionally 0 where x <= 0
- * (pass the pool input `x`, or NULL when relu == 0). */
-int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, float* dx, int Q, int N,
-                      int G, int p, int relu, void* stream);
+                      const tgcn_dropout_t* drop, void* stream);
+/* dx[q,m*p+s,g] = (s == idx) ? dy[q,m,g] : 0; with relu: additionally 0 where the source did not pass the ReLU --
+ * decided from the pool input `x` (x <= 0), or from the forward's pooled output `y` when it is given (y <= 0; the
+ * only form that is valid with dropout, whose 1/(1-p) scale is then applied: a positive y means its source was kept). */
+int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, const float* y, float* dx, int Q, int N,
+                      int G, int p, int relu, const tgcn_dropout_t* drop, void* stream);
 
 /* ---- fused whole-layer entry points (one host call per layer direction) -------------------- */
 /* forward: basis + mix + contraction.  `stack` [K,N,Q*D] and `workspace`
@@ -220,15 +232,19 @@ int64_t tgcn_pack_csr_host(const int32_t* rowptr_host, const int32_t* col_host, 
 int tgcn_resident_pack_classes(int Q, int N, int D, int backward);
 int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* entries, int N, int64_t E,
                             const float* x, const float* W, const float* bias, int bias_mode,
-                            float* out, float* y, uint8_t* idx, int pool_p, int relu, float* stack,
+                            float* out, float* y, uint8_t* idx, int pool_p, int relu,
+                            const tgcn_dropout_t* drop, float* stack,
                             float* wimages, int Q, int D, int G, int K, int recursion, void* stream);
 /* Backward of the above.  Pass exactly one of `dout` [Q,N,G] (un-pooled output was returned) or
  * `dy` [Q,N/pool_p,G] with the forward's `idx` and pooled output `y` (the max-pool / ReLU gradient
  * routing is applied on the fly).  Produces dW [K,D,G], db (per bias_mode), dx [Q,N,D] (if non-NULL;
- * needs the packed CSR of L^T).  `workspace`: tgcn_resident_bwd_workspace(...) bytes.  Deterministic. */
+ * needs the packed CSR of L^T).  `workspace`: tgcn_resident_bwd_workspace(...) bytes.  Deterministic.
+ * `drop` (fused pool + relu only): the descriptor given to the forward -- only its p is used (the gradient of a
+ * positive pooled output is scaled by 1/(1-p); no mask is regenerated). */
 int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, int N, int64_t E,
                             const float* dout, const float* dy, const uint8_t* idx, const float* y,
-                            int pool_p, int relu, const float* stack, const float* wimages,
+                            int pool_p, int relu, const tgcn_dropout_t* drop, const float* stack,
+                            const float* wimages,
                             float* dW, float* db, int bias_mode, float* dx, void* workspace,
                             int Q, int D, int G, int K, int recursion, void* stream);
 
@@ -240,14 +256,36 @@ int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, in
  * used.  act[Q,Hd] (post-ReLU), xhat[Q,Hd] and invstd[Hd] are saved for the backward.  C <= 32. */
 int tgcn_head_fwd(const float* x, const float* W1, const float* b1, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, int training,
-                  const float* W2, const float* b2, float* act, float* xhat, float* invstd, float* logp,
-                  int Q, int I, int Hd, int C, void* stream);
+                  const float* W2, const float* b2, const tgcn_dropout_t* drop, float* act, float* xhat, float* invstd,
+                  float* logp, void* workspace, int Q, int I, int Hd, int C, void* stream);
+/* Large fc1 (I * Hd > 2^21 weights, Q <= 8, I % 4 == 0; the cortical-mesh model: 167 424 x 200 = 134 MB): the weight is
+ * streamed once by a dedicated kernel that needs `workspace` of tgcn_head_workspace(Q, I, Hd) bytes (0: not needed). */
+int64_t tgcn_head_workspace(int Q, int I, int Hd);
+
+/* Optimizer step of fc1.weight fused into the head backward (large fc1 only, tgcn_head_fused_update_supported):
+ *     buf = momentum * buf + dW1 / world;  W1 -= lr * buf          (torch.optim.SGD semantics, pytorch_hcp_tgcn.py:169,259)
+ * applied while W1 is streamed for dx, with dW1 = sum over ranks of dh_r^T x_r formed on the fly -- the 134 MB gradient
+ * is never written, and for world > 1 never exchanged: every rank publishes its activations x [Q, I] and dh [Q, Hd] in
+ * an IPC-mapped region (tgcn_peer_alloc / _export / _import; tgcn_peer_region_bytes(Q*I + Q*Hd, 2) bytes) and reads
+ * the peers' copies over NVLink inside the update kernel (replaces the DataParallel gradient gather for this tensor,
+ * pytorch_hcp_tgcn.py:271-272).  `regions`: host array [world] of region bases as mapped in this process (NULL for
+ * world 1); `state`: 4 device uint32 owned by this rank, zero-initialised (NULL for world 1). */
+typedef struct tgcn_fc1_update {
+    float lr, momentum;
+    float* mom;             /* [Hd, I] momentum buffer (device) */
+    int world, rank;
+    void* const* regions;
+    unsigned int* state;
+} tgcn_fc1_update_t;
+int tgcn_head_fused_update_supported(int Q, int I, int Hd);
 /* Backward of tgcn_head_fwd (training statistics): gradients of every operand from dlogp[Q,C]; dx may be NULL;
- * dh_scratch holds Q*Hd floats.  Two launches. */
+ * dh_scratch holds Q*Hd floats.  `drop`: the forward's descriptor (only p is used).  `upd` != NULL: fc1.weight is
+ * updated in place as described above and dW1 may be NULL; `upd` == NULL: dW1 is written. */
 int tgcn_head_bwd(const float* dlogp, const float* logp, const float* act, const float* xhat, const float* invstd,
-                  const float* x, const float* W1, const float* gamma, const float* W2,
+                  const float* x, float* W1, const float* gamma, const float* W2,
                   float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2,
-                  float* dh_scratch, int Q, int I, int Hd, int C, void* stream);
+                  float* dh_scratch, const tgcn_dropout_t* drop, const tgcn_fc1_update_t* upd, int Q, int I, int Hd, int C,
+                  void* stream);
 
 /* ---- data-parallel step tail: gradient allreduce fused with SGD over NVLink peer memory -------- */
 /* Replaces DataParallel's gradient gather + optim.SGD(momentum).step() (pytorch_hcp_tgcn.py:164-169, 271-272).

@@ -80,7 +80,7 @@ def main():
                             def resident():
                                 st = torch.cuda.current_stream().cuda_stream
                                 assert lib.tgcn_resident_layer_fwd(rowinfo.data_ptr(), entries.data_ptr(), N, E, x.data_ptr(), W.data_ptr(),
-                                                                   bias.data_ptr(), 1, out.data_ptr(), None, None, 0, 0, None, wimg.data_ptr(),
+                                                                   bias.data_ptr(), 1, out.data_ptr(), None, None, 0, 0, None, None, wimg.data_ptr(),
                                                                    Q, D, G, K, 0, st) == 0, _lib.last_error()
                             tr = time_graph(resident, flush)
                         S = 4.0 * N * C

@@ -40,9 +40,9 @@ def test_edge_operators_vs_reference_golden(case, engine):
         assert lay.bias.grad.shape == r["db"].shape
         assert rel_err(lay.bias.grad.cpu().numpy(), r["db"]) < TOL
     # second call with the same edge tensors hits the cached CSR operand
-    n_cached = len(lay._edge_cache)
+    n_cached = len(lay._edge_cache_list)
     lay(x.detach(), ei, ew)
-    assert len(lay._edge_cache) == n_cached
+    assert len(lay._edge_cache_list) == n_cached
 
 
 def test_time_dft_folded_into_the_weights():

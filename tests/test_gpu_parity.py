@@ -233,5 +233,5 @@ def test_empty_batch_and_error_reporting():
         lay(torch.zeros(2, 8, 5, device="cuda"))
     with pytest.raises(RuntimeError, match="fp32"):
         lay(torch.zeros(2, 8, 2, device="cuda", dtype=torch.float64))
-    rc = lib.tgcn_pool_max_fwd(None, None, None, 1, 6, 2, 3, 0, None)
+    rc = lib.tgcn_pool_max_fwd(None, None, None, 1, 6, 2, 3, 0, None, None)
     assert rc == -2 and "pool size" in _lib.last_error()

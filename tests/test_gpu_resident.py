@@ -188,7 +188,7 @@ def test_fused_pool_indices_and_nan_rule():
     wimg = torch.empty(int(lib.tgcn_resident_weights_bytes(D, G, K)) // 4, device="cuda")
     rowinfo, entries, E = plan.packed(lib.tgcn_resident_pack_classes(Q, N, D, 0))
     rc = lib.tgcn_resident_layer_fwd(rowinfo.data_ptr(), entries.data_ptr(), N, E,
-                                     x.data_ptr(), W.data_ptr(), bias.data_ptr(), 1, None, y.data_ptr(), idx.data_ptr(), 4, 1,
+                                     x.data_ptr(), W.data_ptr(), bias.data_ptr(), 1, None, y.data_ptr(), idx.data_ptr(), 4, 1, None,
                                      stack.data_ptr(), wimg.data_ptr(), Q, D, G, K, 0, st)
     assert rc == 0, _lib.last_error()
     ref_v, ref_i = torch.max(torch.relu(bias).reshape(1, N // 4, 4, G).expand(Q, -1, -1, -1), dim=2)
@@ -204,7 +204,7 @@ def test_fused_pool_indices_and_nan_rule():
     ws = torch.empty(max(int(lib.tgcn_resident_bwd_workspace(Q, N, D, G, K)) // 4, 1), device="cuda")
     dyq = dy.expand(Q, -1, -1).contiguous()
     rc = lib.tgcn_resident_layer_bwd(rowinfo.data_ptr(), entries.data_ptr(), N, E,
-                                     None, dyq.data_ptr(), idx.data_ptr(), y.data_ptr(), 4, 1, stack.data_ptr(), wimg.data_ptr(),
+                                     None, dyq.data_ptr(), idx.data_ptr(), y.data_ptr(), 4, 1, None, stack.data_ptr(), wimg.data_ptr(),
                                      dW.data_ptr(), db.data_ptr(), 1, None, ws.data_ptr(), Q, D, G, K, 0, st)
     assert rc == 0, _lib.last_error()
     assert torch.equal(torch.nan_to_num(db, nan=-7.0), torch.nan_to_num(a.grad * Q, nan=-7.0))

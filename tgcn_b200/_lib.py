@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtgcn_b200.so")
 
 OK = 0
+ABI_VERSION = 200      # tgcn_version(): bumped whenever a C-ABI signature changes (include/tgcn_b200.h)
 BIAS_NONE, BIAS_PER_VERTEX, BIAS_PER_FILTER = 0, 1, 2
 RECURSION_REFERENCE, RECURSION_CHEBYSHEV = 0, 1
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TCGEN05, ENGINE_RESIDENT = 0, 1, 2, 3
@@ -46,8 +47,8 @@ SIGNATURES = {
     "tgcn_contract_bwd_x": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_cheb_adjoint": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_bias_grad": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
-    "tgcn_pool_max_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "tgcn_pool_max_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_pool_max_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "tgcn_pool_max_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "tgcn_layer_fwd_workspace": (_l, [_i, _i, _i, _i, _i]),
     "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_layer_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
@@ -58,11 +59,13 @@ SIGNATURES = {
     "tgcn_pack_csr_host": (_l, [_p, _p, _p, _i, _i, _p, _p]),
     "tgcn_resident_pack_classes": (_i, [_i, _i, _i, _i]),
     "tgcn_resident_weights_bytes": (_l, [_i, _i, _i]),
-    "tgcn_resident_layer_fwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "tgcn_resident_layer_bwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p,
+    "tgcn_resident_layer_fwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "tgcn_resident_layer_bwd": (_i, [_p, _p, _i, _l, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p,
                                      _i, _i, _i, _i, _i, _p]),
-    "tgcn_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "tgcn_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_head_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "tgcn_head_workspace": (_l, [_i, _i, _i]),
+    "tgcn_head_fused_update_supported": (_i, [_i, _i, _i]),
+    "tgcn_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "tgcn_peer_alloc": (_i, [_l, _p]),
     "tgcn_peer_free": (_i, [_p]),
     "tgcn_peer_export": (_i, [_p, _p]),
@@ -73,6 +76,26 @@ SIGNATURES = {
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
 }
+
+
+
+class Dropout(ctypes.Structure):
+    """tgcn_dropout_t (include/tgcn_b200.h)."""
+    _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_uint32), ("step", ctypes.c_void_p)]
+
+
+class Fc1Update(ctypes.Structure):
+    """tgcn_fc1_update_t (include/tgcn_b200.h)."""
+    _fields_ = [("lr", ctypes.c_float), ("momentum", ctypes.c_float), ("mom", ctypes.c_void_p), ("world", ctypes.c_int),
+                ("rank", ctypes.c_int), ("regions", ctypes.c_void_p), ("state", ctypes.c_void_p)]
+
+
+def dropout_arg(p, seed=0, step_ptr=None):
+    """byref(tgcn_dropout_t) for the C calls, or None when p == 0 (the struct must outlive the call only)."""
+    if not p:
+        return None
+    return ctypes.byref(Dropout(float(p), int(seed) & 0xFFFFFFFF, step_ptr))
+
 
 _lib = None
 _lock = threading.Lock()
@@ -86,8 +109,10 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
+        from . import build as _build
+        if os.path.exists(_build.nvcc_path()) or not os.path.exists(LIB_PATH):
+            # the fingerprint check inside build() is cheap: a stale, git-ignored .so must never be bound to newer
+            # ctypes signatures.  Without nvcc a prebuilt library is used as it is (and must pass the version check).
             _build.build()
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libtgcn_b200.so is missing and could not be built; there is no fallback path")
@@ -96,6 +121,9 @@ def load():
             fn = getattr(lib, name)      # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        if lib.tgcn_version() != ABI_VERSION:
+            raise RuntimeError("libtgcn_b200.so reports ABI version %d, the Python side expects %d: rebuild it "
+                               "(python -m tgcn_b200.build --force)" % (lib.tgcn_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

@@ -238,12 +238,53 @@ def build_csr(L, device):
     return LaplacianCSR(n, rowptr, c, v, rowptr_t, c_t, v_t, symmetric, dev)
 
 
+def build_csr_from_coo(row, col, val, n, device):
+    """CSR operand from a COO edge list WITHOUT leaving the device (edge-index operators whose graph changes per
+    batch, reference pygeo_hcp.py:272-316): entries sorted by (row, col), duplicates summed (what the reference's
+    scatter_add does; more than two duplicates of one entry are added in atomic order), plus the transpose."""
+    dev = torch.device(device)
+    row = row.to(dev, torch.int64).reshape(-1)
+    col = col.to(dev, torch.int64).reshape(-1)
+    val = val.to(dev, torch.float32).reshape(-1)
+    if row.numel() >= 2 ** 31 - 1:
+        raise ValueError("nnz(L) does not fit int32")
+
+    def csr_of(r, c, v):
+        key, order = torch.sort(r * n + c, stable=True)
+        uniq, inverse = torch.unique_consecutive(key, return_inverse=True)
+        vals = torch.zeros(uniq.numel(), dtype=torch.float32, device=dev).index_add_(0, inverse, v[order])
+        rr = torch.div(uniq, n, rounding_mode="floor")
+        cc = uniq - rr * n
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        if uniq.numel():
+            rowptr[1:] = torch.cumsum(torch.bincount(rr, minlength=n), 0)
+        return rowptr.to(torch.int32), cc.to(torch.int32), vals, rr
+
+    rowptr, c, v, rr = csr_of(row, col, val)
+    rowptr_t, c_t, v_t, _ = csr_of(c.to(torch.int64), rr, v)
+    symmetric = bool(torch.equal(rowptr, rowptr_t) and torch.equal(c, c_t) and torch.equal(v, v_t))
+    if symmetric:
+        rowptr_t, c_t, v_t = rowptr, c, v
+    return LaplacianCSR(n, rowptr, c, v, rowptr_t, c_t, v_t, symmetric, dev)
+
+
 class CSRCache:
-    """Per-device cache of the CSR operand; shared by DataParallel replicas (thread-safe)."""
+    """Per-device cache of the CSR operand; shared by DataParallel replicas (thread-safe).  Pickling / deep-copying
+    a module drops the cached plans (they are rebuilt on first use) -- locks and device plans do not travel."""
 
     def __init__(self):
         self._plans = {}
         self._lock = threading.Lock()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self._plans = {}
+        self._lock = threading.Lock()
+
+    def __deepcopy__(self, memo):
+        return CSRCache()
 
     def get(self, L, device):
         key = (device.type, device.index)

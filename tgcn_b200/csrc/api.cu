@@ -35,6 +35,16 @@ int tuning_value(int key) {
     g_tune[key].store(v, std::memory_order_relaxed);
     return v;
 }
+
+unsigned long long peer_timeout_ns() {
+    static const unsigned long long v = [] {
+        const char* e = getenv("TGCN_PEER_TIMEOUT_S");
+        double sec = e ? atof(e) : 120.0;
+        if (!(sec > 0.0)) sec = 120.0;
+        return (unsigned long long)(sec * 1e9);
+    }();
+    return v;
+}
 }  // namespace tgcn
 
 // Select a kernel variant at run time (tests, sweeps): key in {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC", "RES_ENT", "SPMM_WARPROW", "SPMM_CSM", "SPMM_RTILE"};
@@ -52,7 +62,7 @@ extern "C" int tgcn_set_tuning(const char* key, int value) {
 
 extern "C" long long tgcn_launch_count(void) { return tgcn::g_launches.load(); }
 
-extern "C" int tgcn_version(void) { return 100; }  // 0.1.0
+extern "C" int tgcn_version(void) { return 200; }  // ABI version; tgcn_b200/_lib.py ABI_VERSION must match
 
 extern "C" const char* tgcn_last_error(void) { return tgcn::g_err; }
 

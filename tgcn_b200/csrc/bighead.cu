@@ -1,0 +1,399 @@
+// Large dense head: fc1 of the cortical-mesh model is a [Hd=200] x [I=167 424] weight (134 MB) applied to a batch
+// of 8 samples (pytorch_hcp_tgcn.py:143-155 with n2 = 10 464, g2 = 64).  At that shape fc1 is pure weight
+// streaming -- 2 flop per weight byte -- and the reference's autograd + optim.SGD touch the weight seven times per
+// step (forward, dx, dW write, dW read, momentum read/write, weight read/write).  Here:
+//
+//   bighead_fc1_kernel   forward: W1 streamed ONCE (coalesced 16-byte loads, the 8 x-rows of a column block in
+//                        registers), per-column-block partial sums [P][Q][Hd], reduced in a fixed order by
+//   bighead_bn_kernel    which also applies the bias, BatchNorm1d (batch statistics), ReLU and the dropout;
+//   bighead_bwd_kernel   backward + optimizer in one pass over W1: dx = dh W1 (old weights), the rank-Q gradient
+//                        dW1 = dh^T x formed on the fly from x and dh held in shared memory, and -- when an update
+//                        descriptor is given -- buf = momentum * buf + dW1 / world; W1 -= lr * buf applied in place:
+//                        W1 and the momentum buffer are read once and written once, dW1 never exists in memory.
+//                        Data parallel (world > 1): the gradient of a linear layer is low rank, so instead of an
+//                        allreduce of the 134 MB gradient the ranks exchange the ACTIVATIONS: every rank publishes
+//                        its x [Q, I] (5.4 MB) and dh [Q, Hd] in an IPC-mapped region (peer.cu's pack kernel + step
+//                        flags) and every rank's update kernel reads all ranks' x / dh column blocks over NVLink
+//                        (P2P loads) while it streams its own W1 -- the same sum in the same order on every rank, so
+//                        the replicas stay bit-identical.  NVLink bytes per rank and step: (world-1) * 5.4 MB instead
+//                        of 2 * (world-1)/world * 134 MB.
+// fp32, fixed summation orders (deterministic).
+#include "common.cuh"
+
+namespace tgcn {
+
+constexpr int kBhThreads = 256;
+constexpr int kBhFwdCols = 1024;      // columns per CTA of the forward (8 warps x 32 lanes x float4)
+constexpr int kBhFwdRows = 16;        // W1 rows per CTA of the forward
+constexpr int kBhCols = 128;          // columns per CTA of the backward (32 lanes x float4)
+
+// Sum each of the 8 per-lane values over the 32 lanes of the warp with 9 shuffles (recursive halving): afterwards
+// every lane holds the total of value index ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1) in v[0].
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+    const unsigned full = 0xffffffffu;
+    {
+        const bool hi = (lane & 16) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float send = hi ? v[j] : v[j + 4];
+            const float keep = hi ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = hi ? v[j] : v[j + 2];
+            const float keep = hi ? v[j + 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool hi = (lane & 4) != 0;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 2);
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+    return v[0];
+}
+
+// grid (ceil(I / 1024), ceil(Hd / 16)); block 256.  Q <= 8; I % 4 == 0.
+__global__ void __launch_bounds__(kBhThreads)
+bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, float* __restrict__ partial, int Q, int I,
+                   int Hd) {
+    __shared__ float red[8][kBhFwdRows][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kBhFwdCols + warp * 128 + lane * 4;
+    const bool ok = i < I;
+    const int o0 = blockIdx.y * kBhFwdRows;
+    const int rows = min(kBhFwdRows, Hd - o0);
+    float4 xq[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        xq[q] = (ok && q < Q) ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)q * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int qsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4 w[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int ol = half * 8 + r;
+            w[r] = (ok && ol < rows) ? __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)(o0 + ol) * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[q] = fmaf(w[r].x, xq[q].x, fmaf(w[r].y, xq[q].y, fmaf(w[r].z, xq[q].z, w[r].w * xq[q].w)));
+            const float tot = warp_reduce8(v, lane);
+            if ((lane & 3) == 0) red[warp][half * 8 + r][qsel] = tot;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kBhFwdRows * 8) {
+        const int ol = threadIdx.x >> 3, q = threadIdx.x & 7;
+        if (ol < rows && q < Q) {
+            float s = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) s += red[w8][ol][q];
+            partial[((int64_t)blockIdx.x * Q + q) * Hd + o0 + ol] = s;
+        }
+    }
+}
+
+__device__ __forceinline__ float bh_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// h = b1 + sum_p partial[p] (fixed order), BatchNorm1d statistics, ReLU, dropout: one CTA per 8 hidden features,
+// thread = (sample, feature, quarter of the partials).  Q <= 32.
+constexpr int kBhBnF = 8;
+__global__ void __launch_bounds__(kBhThreads)
+bighead_bn_kernel(const float* __restrict__ partial, int P, const float* __restrict__ b1, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
+                  int training, float* __restrict__ act, float* __restrict__ xhat, float* __restrict__ invstd_out, int Q,
+                  int Hd, float drop_p, uint32_t drop_seed, const uint32_t* drop_step) {
+    __shared__ float hs[32][kBhBnF];
+    __shared__ float s_mean[kBhBnF], s_inv[kBhBnF];
+    const DropCfg drop = drop_resolve(drop_p, drop_seed, drop_step);
+    const int f0 = blockIdx.x * kBhBnF;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int pair = tid >> 2; pair < Q * kBhBnF; pair += kBhThreads / 4) {
+        const int q = pair / kBhBnF, f = pair - q * kBhBnF;
+        const int sub = tid & 3;
+        float s = 0.f;
+        if (f0 + f < Hd)
+            for (int p = sub; p < P; p += 4) s += __ldg(partial + ((int64_t)p * Q + q) * Hd + f0 + f);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (sub == 0) hs[q][f] = s + ((b1 && f0 + f < Hd) ? __ldg(b1 + f0 + f) : 0.f);
+    }
+    __syncthreads();
+    if (warp < kBhBnF && f0 + warp < Hd) {
+        const int f = warp;
+        float mean, inv;
+        if (training) {
+            float s = 0.f;
+            for (int q = lane; q < Q; q += 32) s += hs[q][f];
+            mean = bh_warp_sum(s) / (float)Q;
+            float v = 0.f;
+            for (int q = lane; q < Q; q += 32) { const float d = hs[q][f] - mean; v = fmaf(d, d, v); }
+            const float var = bh_warp_sum(v) / (float)Q;
+            inv = 1.0f / sqrtf(var + eps);
+            if (lane == 0 && running_mean) {
+                const float unb = Q > 1 ? var * (float)Q / (float)(Q - 1) : var;
+                running_mean[f0 + f] = (1.f - momentum) * running_mean[f0 + f] + momentum * mean;
+                running_var[f0 + f] = (1.f - momentum) * running_var[f0 + f] + momentum * unb;
+            }
+        } else {
+            mean = running_mean[f0 + f];
+            inv = 1.0f / sqrtf(running_var[f0 + f] + eps);
+        }
+        if (lane == 0) { s_mean[f] = mean; s_inv[f] = inv; if (invstd_out) invstd_out[f0 + f] = inv; }
+    }
+    __syncthreads();
+    for (int i = tid; i < Q * kBhBnF; i += kBhThreads) {
+        const int q = i / kBhBnF, f = i - q * kBhBnF;
+        if (f0 + f >= Hd) continue;
+        const float xh = (hs[q][f] - s_mean[f]) * s_inv[f];
+        const float y = fmaf(xh, gamma ? __ldg(gamma + f0 + f) : 1.f, beta ? __ldg(beta + f0 + f) : 0.f);
+        if (xhat) xhat[(int64_t)q * Hd + f0 + f] = xh;
+        float a = fmaxf(y, 0.f);
+        if (drop.scale != 0.f) a = drop_apply(a, (uint64_t)((int64_t)q * Hd + f0 + f), drop);
+        act[(int64_t)q * Hd + f0 + f] = a;
+    }
+}
+
+// ---- backward (+ fused SGD-momentum update, + peer exchange of the activations) ---------------------------------
+struct BhBwdParams {
+    const float* x[kPeerMaxWorld];      // rank r's x [Q, I]  (own rank: the local tensor or the own region)
+    const float* dh[kPeerMaxWorld];     // rank r's dh [Q, Hd]
+    const unsigned int* flags;          // own flag line (slot r written by rank r), or null (world 1)
+    unsigned int* step_ctr;             // device step counter shared with the pack kernel (advanced by the last CTA), or null
+    unsigned int* done_blocks;
+    float* W1;                          // [Hd, I]; updated in place when `mom` != null
+    float* mom;                         // [Hd, I] momentum buffer, or null (plain backward)
+    float* dW1;                         // [Hd, I] gradient output of the plain backward, or null
+    float* dx;                          // [Q, I] or null
+    int world, rank, Q, I, Hd, HdP;
+    int64_t n_flat;                     // elements of one flat buffer of a region: the step's buffer starts at (step & 1) * n_flat
+    float lr, momentum, gscale;
+    unsigned long long timeout_ns;
+};
+
+// One CTA = 128 columns of W1, all Hd rows: warp w takes the row tiles w, w + 8, ... of OB rows; lane = one float4 column.
+// Shared memory: xs [S][128] (S = world * Q rows of all ranks), dhs [S][HdP]; dhs is re-used for the cross-warp
+// reduction of dx.  QN = register tile of the dx accumulators (Q <= QN).
+template <int OB, int QN, bool kUpdate>
+__global__ void __launch_bounds__(kBhThreads, 1)
+bighead_bwd_kernel(const BhBwdParams p) {
+    extern __shared__ __align__(16) float bsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Q = p.Q, I = p.I, Hd = p.Hd, HdP = p.HdP, S = p.world * Q;
+    float* xs = bsm;                                    // [S][128]
+    float* dhs = bsm + (size_t)S * kBhCols;             // [S][HdP]
+    const int64_t i0 = (int64_t)blockIdx.x * kBhCols;
+    const int64_t icol = i0 + lane * 4;
+    const bool ok = icol < I;
+    unsigned int step = 0;
+    int64_t par = 0;
+    if (p.flags) {
+        step = *p.step_ctr;
+        par = (int64_t)(step & 1u) * p.n_flat;
+        if (tid < p.world) peer_wait_flag(p.flags + tid, step + 1u, p.timeout_ns);
+        __syncthreads();
+    }
+    // stage every rank's x column block and dh (P2P loads for the peers; volatile: written by another device this step)
+    for (int t = tid; t < S * 32; t += kBhThreads) {
+        const int sq = t >> 5, l = t & 31;
+        const int r = sq / Q, q = sq - r * Q;
+        const int64_t c = i0 + l * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < I) v = ld_volatile_f4(p.x[r] + par + (int64_t)q * I + c);
+        reinterpret_cast<float4*>(xs)[t] = v;
+    }
+    for (int t = tid; t < S * HdP; t += kBhThreads) {
+        const int sq = t / HdP, f = t - sq * HdP;
+        const int r = sq / Q, q = sq - r * Q;
+        float v = 0.f;
+        if (f < Hd) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p.dh[r] + par + (int64_t)q * Hd + f) : "memory");
+        dhs[t] = v;
+    }
+    __syncthreads();
+
+    float4 dxa[QN];
+#pragma unroll
+    for (int q = 0; q < QN; ++q) dxa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* dh_own = dhs + (size_t)p.rank * Q * HdP;
+    const float4* xs4 = reinterpret_cast<const float4*>(xs);
+    const int ntiles = (Hd + OB - 1) / OB;
+    for (int tile = warp; tile < ntiles; tile += 8) {
+        const int o0 = tile * OB;
+        float4 w[OB], m[OB];
+#pragma unroll
+        for (int j = 0; j < OB; ++j) {
+            const bool live = ok && o0 + j < Hd;
+            w[j] = live ? *reinterpret_cast<const float4*>(p.W1 + (int64_t)(o0 + j) * I + icol) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kUpdate) m[j] = live ? *reinterpret_cast<const float4*>(p.mom + (int64_t)(o0 + j) * I + icol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 g[OB];
+#pragma unroll
+        for (int j = 0; j < OB; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sq = 0; sq < S; ++sq) {                     // rank-major, then sample: the same order on every rank
+            const float4 xv = xs4[sq * 32 + lane];
+            const float* dr = dhs + (size_t)sq * HdP + o0;   // o0 + OB <= HdP (HdP is padded to a multiple of OB)
+#pragma unroll
+            for (int j = 0; j < OB; ++j) {
+                const float d = dr[j];
+                g[j].x = fmaf(d, xv.x, g[j].x); g[j].y = fmaf(d, xv.y, g[j].y);
+                g[j].z = fmaf(d, xv.z, g[j].z); g[j].w = fmaf(d, xv.w, g[j].w);
+            }
+        }
+        if (p.dx) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q) {
+                if (q < Q) {
+                    const float* dr = dh_own + (size_t)q * HdP + o0;
+#pragma unroll
+                    for (int j = 0; j < OB; ++j) {
+                        const float d = dr[j];
+                        dxa[q].x = fmaf(d, w[j].x, dxa[q].x); dxa[q].y = fmaf(d, w[j].y, dxa[q].y);
+                        dxa[q].z = fmaf(d, w[j].z, dxa[q].z); dxa[q].w = fmaf(d, w[j].w, dxa[q].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < OB; ++j) {
+            if (!(ok && o0 + j < Hd)) continue;
+            const int64_t off = (int64_t)(o0 + j) * I + icol;
+            if (kUpdate) {
+                float4 mm, ww;
+                mm.x = fmaf(p.momentum, m[j].x, g[j].x * p.gscale); mm.y = fmaf(p.momentum, m[j].y, g[j].y * p.gscale);
+                mm.z = fmaf(p.momentum, m[j].z, g[j].z * p.gscale); mm.w = fmaf(p.momentum, m[j].w, g[j].w * p.gscale);
+                ww.x = fmaf(-p.lr, mm.x, w[j].x); ww.y = fmaf(-p.lr, mm.y, w[j].y);
+                ww.z = fmaf(-p.lr, mm.z, w[j].z); ww.w = fmaf(-p.lr, mm.w, w[j].w);
+                *reinterpret_cast<float4*>(p.mom + off) = mm;
+                *reinterpret_cast<float4*>(p.W1 + off) = ww;
+            } else {
+                *reinterpret_cast<float4*>(p.dW1 + off) = g[j];
+            }
+        }
+    }
+    if (p.dx) {
+        __syncthreads();                                    // dhs is dead: re-use it for the cross-warp reduction of dx
+        float4* red = reinterpret_cast<float4*>(dhs);       // [8 warps][Q][32 lanes]
+#pragma unroll
+        for (int q = 0; q < QN; ++q)
+            if (q < Q) red[(warp * Q + q) * 32 + lane] = dxa[q];
+        __syncthreads();
+        for (int t = tid; t < Q * 32; t += kBhThreads) {
+            const int q = t >> 5, l = t & 31;
+            float4 s = red[(0 * Q + q) * 32 + l];
+#pragma unroll
+            for (int w8 = 1; w8 < 8; ++w8) {
+                const float4 v = red[(w8 * Q + q) * 32 + l];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            const int64_t c = i0 + l * 4;
+            if (c < I) *reinterpret_cast<float4*>(p.dx + (int64_t)q * I + c) = s;
+        }
+    }
+    if (p.step_ctr) {                                       // the last CTA advances the step (buffers alternate with its parity)
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(p.done_blocks, 1u);
+            if (prev == gridDim.x - 1) { *p.done_blocks = 0u; *p.step_ctr = step + 1u; }
+        }
+    }
+}
+
+// peer.cu: copies this rank's tensors into flat[step & 1] of its region and publishes the step flag to every rank
+int peer_pack_launch(void* const* regions_host, int world, int rank, const float* const* srcs_host, const int64_t* numels_host,
+                     int nseg, unsigned int* state, cudaStream_t st);
+
+int bighead_workspace_chunks(int I) { return (int)ceil_div(I, kBhFwdCols); }
+
+bool bighead_applies(int Q, int I, int Hd) {
+    return (int64_t)I * Hd > ((int64_t)1 << 21) && Q >= 1 && Q <= 8 && (I % 4) == 0;
+}
+
+int bighead_fwd(const float* x, const float* W1, const float* b1, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float momentum, float eps, int training, float drop_p, uint32_t drop_seed,
+                const uint32_t* drop_step, float* act, float* xhat, float* invstd, float* partial, int Q, int I, int Hd,
+                cudaStream_t st) {
+    TGCN_REQUIRE(aligned16(x) && aligned16(W1), "tgcn_head_fwd: x / W1 must be 16-byte aligned");
+    const int P = bighead_workspace_chunks(I);
+    const dim3 grid((unsigned)P, (unsigned)ceil_div(Hd, kBhFwdRows));
+    bighead_fc1_kernel<<<grid, kBhThreads, 0, st>>>(x, W1, partial, Q, I, Hd);
+    TGCN_LAUNCH_CHECK("bighead_fc1");
+    bighead_bn_kernel<<<(unsigned)ceil_div(Hd, kBhBnF), kBhThreads, 0, st>>>(partial, P, b1, gamma, beta, running_mean, running_var,
+                                                                            momentum, eps, training, act, xhat, invstd, Q, Hd,
+                                                                            drop_p, drop_seed, drop_step);
+    TGCN_LAUNCH_CHECK("bighead_bn");
+    return TGCN_OK;
+}
+
+template <int OB, bool kUpdate>
+static int bighead_bwd_launch(const BhBwdParams& p, size_t smem, cudaStream_t st) {
+    auto kern = bighead_bwd_kernel<OB, 8, kUpdate>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_head_bwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)ceil_div(p.I, kBhCols), kBhThreads, smem, st>>>(p);
+    TGCN_LAUNCH_CHECK("bighead_bwd");
+    return TGCN_OK;
+}
+
+// dh [Q, Hd] comes from head_bwd1_kernel.  upd == null: plain backward (dW1, dx).  upd != null: fused update.
+int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* dx, const tgcn_fc1_update_t* upd, int Q, int I,
+                int Hd, cudaStream_t st) {
+    TGCN_REQUIRE(aligned16(x) && aligned16(W1) && (!dW1 || aligned16(dW1)) && (!dx || aligned16(dx)),
+                 "tgcn_head_bwd: x / W1 / dW1 / dx must be 16-byte aligned");
+    const int world = upd ? upd->world : 1, rank = upd ? upd->rank : 0;
+    TGCN_SUPPORTED(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "tgcn_head_bwd: world %d rank %d", world, rank);
+    const int OB = (Hd % 5 == 0) ? 5 : 8;
+    BhBwdParams p{};
+    p.world = world; p.rank = rank; p.Q = Q; p.I = I; p.Hd = Hd; p.HdP = (int)ceil_div(Hd, OB) * OB;
+    p.W1 = W1; p.dW1 = dW1; p.dx = dx;
+    p.timeout_ns = peer_timeout_ns();
+    if (upd) {
+        TGCN_REQUIRE(upd->mom && aligned16(upd->mom), "tgcn_head_bwd: update descriptor without a 16-byte aligned momentum buffer");
+        p.mom = upd->mom; p.lr = upd->lr; p.momentum = upd->momentum; p.gscale = 1.0f / (float)world;
+    } else {
+        TGCN_REQUIRE(dW1, "tgcn_head_bwd: neither dW1 nor an update descriptor");
+    }
+    const int S = world * Q;
+    const size_t smem_stage = sizeof(float) * ((size_t)S * kBhCols + (size_t)S * p.HdP);
+    const size_t smem_red = sizeof(float) * ((size_t)S * kBhCols + (size_t)8 * Q * kBhCols);
+    const size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
+    TGCN_SUPPORTED(smem <= 200 * 1024, "tgcn_head_bwd: world %d x batch %d x Hd %d does not fit shared memory", world, Q, Hd);
+    if (world == 1) {
+        p.x[0] = x; p.dh[0] = dh;
+    } else {
+        TGCN_REQUIRE(upd->regions && upd->state, "tgcn_head_bwd: world > 1 needs the peer regions and the state buffer");
+        // publish x and dh of this step in the own region, then read every rank's copy
+        const float* srcs[2] = {x, dh};
+        const int64_t numels[2] = {(int64_t)Q * I, (int64_t)Q * Hd};
+        TGCN_PROPAGATE(peer_pack_launch(upd->regions, world, rank, srcs, numels, 2, upd->state, st));
+        const int64_t nx = ((int64_t)Q * I + 3) & ~(int64_t)3, nd = ((int64_t)Q * Hd + 3) & ~(int64_t)3;
+        p.n_flat = nx + nd;
+        for (int r = 0; r < world; ++r) {
+            p.x[r] = reinterpret_cast<const float*>(upd->regions[r]);
+            p.dh[r] = reinterpret_cast<const float*>(upd->regions[r]) + nx;
+        }
+        p.flags = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(upd->regions[rank]) + 2 * p.n_flat * sizeof(float));
+        p.step_ctr = upd->state; p.done_blocks = upd->state + 2;
+    }
+    if (upd) return OB == 5 ? bighead_bwd_launch<5, true>(p, smem, st) : bighead_bwd_launch<8, true>(p, smem, st);
+    return OB == 5 ? bighead_bwd_launch<5, false>(p, smem, st) : bighead_bwd_launch<8, false>(p, smem, st);
+}
+
+}  // namespace tgcn

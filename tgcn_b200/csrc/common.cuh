@@ -44,6 +44,73 @@ __device__ __forceinline__ void fma4_packed(float4& acc, float w, const float4& 
 }
 #endif
 
+// ---- fused dropout (nn.Dropout between ReLU and the pool / fc2 in the reference models, pytorch_hcp_tgcn.py:106,125,136,150)
+// Counter-based: the keep decision of activation element `elem` is a hash of (seed, step counter, elem), so the
+// forward needs no mask tensor and a CUDA-graph replay draws a new mask whenever the caller's step counter moved.
+// The backward never regenerates the mask: a positive pooled / post-ReLU output implies its source element was kept,
+// so the gradient is the routed gradient times `scale` = 1/(1-p).
+#ifdef __CUDACC__
+namespace tgcn {
+struct DropCfg { float scale; uint32_t thresh; uint32_t key; };      // scale == 0: dropout off
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// torch semantics: out = x * mask / (1 - p); a dropped NaN stays NaN (NaN * 0)
+__device__ __forceinline__ float drop_apply(float v, uint64_t elem, const DropCfg& d) {
+    const uint32_t h = mix32((uint32_t)elem ^ mix32((uint32_t)(elem >> 32) ^ d.key));
+    return v * (h >= d.thresh ? d.scale : 0.f);
+}
+// resolved on the device at kernel start: key from the seed and the step counter the caller advances every step
+__device__ __forceinline__ DropCfg drop_resolve(float p, uint32_t seed, const uint32_t* step) {
+    DropCfg d;
+    if (!(p > 0.f)) { d.scale = 0.f; d.thresh = 0u; d.key = 0u; return d; }
+    d.scale = 1.0f / (1.0f - p);
+    d.thresh = (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f);
+    d.key = mix32(seed + 0x9E3779B9u * (step ? *step : 0u));
+    return d;
+}
+}  // namespace tgcn
+#endif
+
+// ---- cross-rank flags over NVLink peer memory (peer.cu, bighead.cu, halo reads) --------------------------------
+#ifdef __CUDACC__
+namespace tgcn {
+constexpr int kPeerMaxWorld = 8;
+// Bound of every cross-rank wait, in nanoseconds of %globaltimer (TGCN_PEER_TIMEOUT_S, default 120 s: ordinary rank
+// skew -- a validation pass, a checkpoint, a first-step lazy load on one rank -- must not kill the job; a lost
+// peer still cannot hang the device for ever: the waiter traps, which surfaces as a CUDA error on the host).
+unsigned long long peer_timeout_ns();
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *slot >= want (acquire, system scope); traps after limit_ns
+__device__ __forceinline__ void peer_wait_flag(const unsigned int* slot, unsigned int want, unsigned long long limit_ns) {
+    if (ld_acquire_sys(slot) >= want) return;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(slot) < want) {
+        __nanosleep(64);
+        if (global_ns() - t0 > limit_ns) __trap();
+    }
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+}  // namespace tgcn
+#endif
+
 #define TGCN_REQUIRE(cond, ...)                                            \
     do {                                                                   \
         if (!(cond)) return tgcn::set_error(TGCN_ERR_INVALID, __VA_ARGS__); \

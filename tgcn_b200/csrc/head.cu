@@ -30,8 +30,9 @@ head_fwd1_kernel(const float* __restrict__ x, const float* __restrict__ W1, cons
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
                  float momentum, float eps, int training,
                  float* __restrict__ act, float* __restrict__ xhat, float* __restrict__ invstd_out,
-                 int Q, int I, int Hd) {
+                 int Q, int I, int Hd, float drop_p, uint32_t drop_seed, const uint32_t* drop_step) {
     extern __shared__ float hs[];                  // [Q][FB] pre-activations
+    const DropCfg drop = drop_resolve(drop_p, drop_seed, drop_step);
     __shared__ float s_mean[kHeadFB], s_inv[kHeadFB];
     const int f0 = blockIdx.x * kHeadFB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -112,7 +113,9 @@ head_fwd1_kernel(const float* __restrict__ x, const float* __restrict__ W1, cons
         const float xh = (hs[i] - s_mean[f]) * s_inv[f];
         const float y = fmaf(xh, gamma ? __ldg(gamma + f0 + f) : 1.f, beta ? __ldg(beta + f0 + f) : 0.f);
         if (xhat) xhat[(int64_t)q * Hd + f0 + f] = xh;
-        act[(int64_t)q * Hd + f0 + f] = fmaxf(y, 0.f);
+        float a = fmaxf(y, 0.f);
+        if (drop.scale != 0.f) a = drop_apply(a, (uint64_t)((int64_t)q * Hd + f0 + f), drop);   // drop2, pytorch_hcp_tgcn.py:150
+        act[(int64_t)q * Hd + f0 + f] = a;
     }
 }
 
@@ -168,7 +171,7 @@ head_bwd1_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp
                  const float* __restrict__ xhat, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const float* __restrict__ W2, float* __restrict__ dW2, float* __restrict__ db2,
                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db1, float* __restrict__ dh,
-                 int Q, int Hd, int C) {
+                 int Q, int Hd, int C, float drop_scale) {
     extern __shared__ float sm[];                  // dlogits [Q][C]
     float* dlog = sm;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -199,7 +202,7 @@ head_bwd1_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp
     for (int q = lane; q < Q; q += 32) {           // dy = relu'(.) * (dlogits W2)[q][f]
         float d = 0.f;
         for (int c = 0; c < C; ++c) d = fmaf(dlog[q * C + c], __ldg(W2 + (int64_t)c * Hd + f), d);
-        d = __ldg(act + (int64_t)q * Hd + f) > 0.f ? d : 0.f;
+        d = __ldg(act + (int64_t)q * Hd + f) > 0.f ? d * drop_scale : 0.f;   // act > 0: passed the ReLU and kept by the dropout
         sg = fmaf(d, __ldg(xhat + (int64_t)q * Hd + f), sg);
         sb += d;
     }
@@ -210,7 +213,7 @@ head_bwd1_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp
     for (int q = lane; q < Q; q += 32) {
         float d = 0.f;
         for (int c = 0; c < C; ++c) d = fmaf(dlog[q * C + c], __ldg(W2 + (int64_t)c * Hd + f), d);
-        d = __ldg(act + (int64_t)q * Hd + f) > 0.f ? d : 0.f;
+        d = __ldg(act + (int64_t)q * Hd + f) > 0.f ? d * drop_scale : 0.f;
         const float v = k * ((float)Q * d - sb - __ldg(xhat + (int64_t)q * Hd + f) * sg);
         dh[(int64_t)q * Hd + f] = v;
         s1 += v;
@@ -308,14 +311,33 @@ head_bwd2_kernel(const float* __restrict__ dh, const float* __restrict__ x, cons
     }
 }
 
+// bighead.cu
+bool bighead_applies(int Q, int I, int Hd);
+int bighead_workspace_chunks(int I);
+int bighead_fwd(const float* x, const float* W1, const float* b1, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float momentum, float eps, int training, float drop_p, uint32_t drop_seed,
+                const uint32_t* drop_step, float* act, float* xhat, float* invstd, float* partial, int Q, int I, int Hd,
+                cudaStream_t st);
+int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* dx, const tgcn_fc1_update_t* upd, int Q, int I,
+                int Hd, cudaStream_t st);
+
 }  // namespace tgcn
 
 using namespace tgcn;
 
+extern "C" int64_t tgcn_head_workspace(int Q, int I, int Hd) {
+    if (Q < 1 || I < 1 || Hd < 1 || !bighead_applies(Q, I, Hd)) return 0;
+    return (int64_t)bighead_workspace_chunks(I) * Q * Hd * (int64_t)sizeof(float);
+}
+
+extern "C" int tgcn_head_fused_update_supported(int Q, int I, int Hd) { return bighead_applies(Q, I, Hd) ? 1 : 0; }
+
 extern "C" int tgcn_head_fwd(const float* x, const float* W1, const float* b1, const float* gamma, const float* beta,
                              float* running_mean, float* running_var, float momentum, float eps, int training,
-                             const float* W2, const float* b2, float* act, float* xhat, float* invstd, float* logp,
-                             int Q, int I, int Hd, int C, void* stream) {
+                             const float* W2, const float* b2, const tgcn_dropout_t* drop, float* act, float* xhat,
+                             float* invstd, float* logp, void* workspace, int Q, int I, int Hd, int C, void* stream) {
+    const float drop_p = (drop && drop->p > 0.f && training) ? drop->p : 0.f;
+    TGCN_REQUIRE(drop_p < 1.f, "tgcn_head_fwd: dropout p = %g must be < 1", (double)drop_p);
     TGCN_REQUIRE(Q >= 1 && I >= 1 && Hd >= 1 && C >= 1, "tgcn_head_fwd: bad sizes");
     TGCN_REQUIRE(x && W1 && W2 && act && logp, "tgcn_head_fwd: null pointer");
     TGCN_SUPPORTED(C <= 32, "tgcn_head_fwd: at most 32 classes (one warp per sample), got %d", C);
@@ -324,8 +346,19 @@ extern "C" int tgcn_head_fwd(const float* x, const float* W1, const float* b1, c
     const size_t smem = sizeof(float) * (size_t)(Q + 1) * kHeadFB;
     TGCN_SUPPORTED(smem <= 48 * 1024, "tgcn_head_fwd: batch %d too large for the fused head", Q);
     cudaStream_t st = as_stream(stream);
+    if (bighead_applies(Q, I, Hd)) {
+        // large fc1: the weight is streamed once by a dedicated kernel (bighead.cu), the rest of the head is unchanged
+        TGCN_REQUIRE(workspace && aligned16(workspace), "tgcn_head_fwd: this shape needs tgcn_head_workspace(Q, I, Hd) bytes of workspace");
+        TGCN_PROPAGATE(bighead_fwd(x, W1, b1, gamma, beta, running_mean, running_var, momentum, eps, training, drop_p,
+                                   drop ? drop->seed : 0u, drop ? drop->step : nullptr, act, xhat, invstd,
+                                   reinterpret_cast<float*>(workspace), Q, I, Hd, st));
+        head_fwd2_kernel<<<(unsigned)ceil_div(Q, 2), 64, 0, st>>>(act, W2, b2, logp, Q, Hd, C);
+        TGCN_LAUNCH_CHECK("head_fwd2");
+        return TGCN_OK;
+    }
     head_fwd1_kernel<<<(unsigned)ceil_div(Hd, kHeadFB), kHeadFwd1Threads, smem, st>>>(x, W1, b1, gamma, beta, running_mean, running_var,
-                                                                                 momentum, eps, training, act, xhat, invstd, Q, I, Hd);
+                                                                                 momentum, eps, training, act, xhat, invstd, Q, I, Hd,
+                                                                                 drop_p, drop ? drop->seed : 0u, drop ? drop->step : nullptr);
     TGCN_LAUNCH_CHECK("head_fwd1");
     head_fwd2_kernel<<<(unsigned)ceil_div(Q, 2), 64, 0, st>>>(act, W2, b2, logp, Q, Hd, C);
     TGCN_LAUNCH_CHECK("head_fwd2");
@@ -333,26 +366,32 @@ extern "C" int tgcn_head_fwd(const float* x, const float* W1, const float* b1, c
 }
 
 extern "C" int tgcn_head_bwd(const float* dlogp, const float* logp, const float* act, const float* xhat, const float* invstd,
-                             const float* x, const float* W1, const float* gamma, const float* W2,
+                             const float* x, float* W1, const float* gamma, const float* W2,
                              float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2, float* db2,
-                             float* dh_scratch, int Q, int I, int Hd, int C, void* stream) {
+                             float* dh_scratch, const tgcn_dropout_t* drop, const tgcn_fc1_update_t* upd, int Q, int I, int Hd,
+                             int C, void* stream) {
     TGCN_REQUIRE(Q >= 1 && I >= 1 && Hd >= 1 && C >= 1, "tgcn_head_bwd: bad sizes");
-    TGCN_REQUIRE(dlogp && logp && act && xhat && invstd && x && W1 && W2 && dW1 && dW2 && dh_scratch, "tgcn_head_bwd: null pointer");
+    const float drop_p = (drop && drop->p > 0.f) ? drop->p : 0.f;
+    TGCN_REQUIRE(drop_p < 1.f, "tgcn_head_bwd: dropout p = %g must be < 1", (double)drop_p);
+    TGCN_REQUIRE(dlogp && logp && act && xhat && invstd && x && W1 && W2 && (dW1 || upd) && dW2 && dh_scratch, "tgcn_head_bwd: null pointer");
+    const bool big = bighead_applies(Q, I, Hd);
+    TGCN_SUPPORTED(!upd || big, "tgcn_head_bwd: the fused fc1 update covers large heads only (tgcn_head_fused_update_supported)");
     const size_t smem1 = sizeof(float) * (size_t)Q * C;
     const int HdP = (Hd + 3) & ~3;
     const size_t smem2 = sizeof(float) * ((size_t)Q * HdP + (size_t)Q * kHeadCB + (size_t)HdP * kHeadCB);
-    TGCN_SUPPORTED(smem1 <= 200 * 1024 && smem2 <= 200 * 1024, "tgcn_head_bwd: Q=%d Hd=%d too large for the fused head", Q, Hd);
+    TGCN_SUPPORTED(smem1 <= 200 * 1024 && (big || smem2 <= 200 * 1024), "tgcn_head_bwd: Q=%d Hd=%d too large for the fused head", Q, Hd);
     cudaStream_t st = as_stream(stream);
     if (smem1 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(head_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_head_bwd: %s", cudaGetErrorString(e));
     }
-    if (smem2 > 48 * 1024) {
+    if (!big && smem2 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(head_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_head_bwd: %s", cudaGetErrorString(e));
     }
-    head_bwd1_kernel<<<(unsigned)ceil_div(Hd, kHeadFB), kHeadFB * 32, smem1, st>>>(dlogp, logp, act, xhat, invstd, gamma, W2, dW2, db2, dgamma, dbeta, db1, dh_scratch, Q, Hd, C);
+    head_bwd1_kernel<<<(unsigned)ceil_div(Hd, kHeadFB), kHeadFB * 32, smem1, st>>>(dlogp, logp, act, xhat, invstd, gamma, W2, dW2, db2, dgamma, dbeta, db1, dh_scratch, Q, Hd, C, 1.0f / (1.0f - drop_p));
     TGCN_LAUNCH_CHECK("head_bwd1");
+    if (big) return bighead_bwd(dh_scratch, x, W1, dW1, dx, upd, Q, I, Hd, st);
     head_bwd2_kernel<<<(unsigned)ceil_div(I, kHeadCB), kHeadThreads, smem2, st>>>(dh_scratch, x, W1, dW1, dx, Q, I, Hd, HdP);
     TGCN_LAUNCH_CHECK("head_bwd2");
     return TGCN_OK;

@@ -14,18 +14,24 @@
 //                        all ranks' buffers straight over NVLink (P2P loads), sums them in rank order -- the same
 //                        order on every rank, so the replicas stay bit-identical --, scales by 1/world and applies
 //                        buf = momentum * buf + g;  param -= lr * buf.  No intermediate averaged-gradient tensor.
+// Two-shot variant (large gradients / many ranks, chosen identically on every rank from n and world): the one-shot
+// kernel makes every rank pull ALL ranks' copies of the WHOLE gradient ((world-1) * n elements over NVLink per rank).
+//   peer_rs_kernel     : reduce-scatter -- rank r sums only slice r of the flat index space from all ranks' buffers
+//                        (rank order), scales by 1/world and PUSHES the averaged slice into every rank's `avg` buffer
+//                        (P2P stores), then publishes a second flag;
+//   peer_apply_kernel  : waits for every rank's second flag and applies the SGD update from its local `avg` buffer.
+// NVLink traffic per rank drops to 2 (world-1)/world * n at the price of a second flag round trip.
 // Buffers alternate with the step parity, so a rank may start writing step s+2 only after all peers have posted
 // ready(s+1), i.e. after they finished reading step s: one flag exchange per step is the only synchronisation.
-// Waits are bounded (trap after ~2 s) so a lost peer cannot hang the device.  Step numbers live in device memory,
+// Waits are bounded (TGCN_PEER_TIMEOUT_S, default 120 s, then trap) so a lost peer cannot hang the device for ever.  Step numbers live in device memory,
 // so the two launches are CUDA-graph capturable.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
 namespace tgcn {
 
 constexpr int kPeerMaxSeg = 24;
-constexpr int kPeerMaxWorld = 8;
-constexpr unsigned long long kPeerSpinLimit = 4000000000ull;
 
 struct PeerSegs {
     const float* grad[kPeerMaxSeg];
@@ -39,17 +45,11 @@ struct PeerSegs {
 struct PeerRanks {
     const float* flat[kPeerMaxWorld];           // each rank's region base
     unsigned int* flag[kPeerMaxWorld];          // each rank's flag line (kPeerMaxWorld slots, slot s written by rank s)
+    float* avg[kPeerMaxWorld];                  // two-shot: each rank's averaged-gradient buffers (2 x n)
+    unsigned int* flag2[kPeerMaxWorld];         // two-shot: second flag line (averaged slices pushed)
     int world, rank;
+    unsigned long long timeout_ns;
 };
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Segment offsets are multiples of 4 elements, so every tensor is walked as float4 (plus a scalar tail) and ONE
 // grid-wide index space covers all tensors: one float4 per thread, all loads of a thread in flight at once -- the
@@ -97,22 +97,14 @@ peer_pack_kernel(const PeerSegs segs, const PeerRanks ranks, float* flat_base, i
     }
 }
 
-__device__ __forceinline__ float4 ldcv4(const float* p) {
-    float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
+__device__ __forceinline__ float4 ldcv4(const float* p) { return ld_volatile_f4(p); }
 
 __global__ void __launch_bounds__(256)
 peer_reduce_sgd_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, float lr, float momentum,
                        unsigned int* step_ctr, unsigned int* done_blocks) {
     const unsigned int step = *step_ctr;
-    if ((int)threadIdx.x < ranks.world) {              // own flag line: slot r is pushed by rank r's pack kernel
-        const unsigned long long t0 = clock64();
-        const unsigned int* slot = ranks.flag[ranks.rank] + threadIdx.x;
-        while (ld_acquire_sys(slot) < step + 1u)
-            if (clock64() - t0 > kPeerSpinLimit) __trap();
-    }
+    if ((int)threadIdx.x < ranks.world)                // own flag line: slot r is pushed by rank r's pack kernel
+        peer_wait_flag(ranks.flag[ranks.rank] + threadIdx.x, step + 1u, ranks.timeout_ns);
     __syncthreads();
     const int64_t par = (int64_t)(step & 1u) * n;
     const float inv = 1.0f / (float)ranks.world;
@@ -147,6 +139,95 @@ peer_reduce_sgd_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, fl
                     prm[c] = fmaf(-lr, bcur, prm[c]);
                 }
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_blocks = 0u;
+            *step_ctr = step + 1u;
+        }
+    }
+}
+
+__device__ __forceinline__ void sgd_apply4(const PeerSegs& segs, int64_t e, const float (&gg)[4], float lr, float momentum) {
+    const int s = find_seg(segs, e);
+    const int64_t loc = e - segs.off[s], len = segs.len[s];
+    float* prm = segs.param[s] + loc;
+    float* mom = segs.mom[s] + loc;
+    if (loc + 4 <= len) {
+        float4 m = *reinterpret_cast<float4*>(mom), w = *reinterpret_cast<float4*>(prm);
+        m.x = fmaf(momentum, m.x, gg[0]); m.y = fmaf(momentum, m.y, gg[1]);
+        m.z = fmaf(momentum, m.z, gg[2]); m.w = fmaf(momentum, m.w, gg[3]);
+        w.x = fmaf(-lr, m.x, w.x); w.y = fmaf(-lr, m.y, w.y); w.z = fmaf(-lr, m.z, w.z); w.w = fmaf(-lr, m.w, w.w);
+        *reinterpret_cast<float4*>(mom) = m;
+        *reinterpret_cast<float4*>(prm) = w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (loc + c < len) {
+                const float bcur = fmaf(momentum, mom[c], gg[c]);
+                mom[c] = bcur;
+                prm[c] = fmaf(-lr, bcur, prm[c]);
+            }
+    }
+}
+
+// two-shot, first half: rank r reduces float4 indices [r * per, (r + 1) * per) and pushes the average to every rank
+__global__ void __launch_bounds__(256)
+peer_rs_kernel(const PeerRanks ranks, int64_t n, const unsigned int* step_ctr, unsigned int* done_blocks) {
+    __shared__ int s_last;
+    const unsigned int step = *step_ctr;
+    if ((int)threadIdx.x < ranks.world)
+        peer_wait_flag(ranks.flag[ranks.rank] + threadIdx.x, step + 1u, ranks.timeout_ns);
+    __syncthreads();
+    const int64_t par = (int64_t)(step & 1u) * n;
+    const float inv = 1.0f / (float)ranks.world;
+    const int64_t n4 = n / 4, per = (n4 + ranks.world - 1) / ranks.world;
+    const int64_t lo = (int64_t)ranks.rank * per, hi = lo + per < n4 ? lo + per : n4;
+    for (int64_t i4 = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < hi; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 4 * i4;
+        float4 gr[kPeerMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < ranks.world) gr[r] = ldcv4(ranks.flat[r] + par + e);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < ranks.world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+        g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+#pragma unroll
+        for (int r = 0; r < kPeerMaxWorld; ++r)
+            if (r < ranks.world) *reinterpret_cast<float4*>(ranks.avg[r] + par + e) = g;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *done_blocks = 0u;
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < ranks.world) {
+        __threadfence_system();
+        st_release_sys(ranks.flag2[threadIdx.x] + ranks.rank, step + 1u);
+    }
+}
+
+// two-shot, second half: every slice has arrived in the local `avg` buffer -> SGD with momentum on all parameters
+__global__ void __launch_bounds__(256)
+peer_apply_kernel(const PeerSegs segs, const PeerRanks ranks, int64_t n, float lr, float momentum, unsigned int* step_ctr,
+                  unsigned int* done_blocks) {
+    const unsigned int step = *step_ctr;
+    if ((int)threadIdx.x < ranks.world)
+        peer_wait_flag(ranks.flag2[ranks.rank] + threadIdx.x, step + 1u, ranks.timeout_ns);
+    __syncthreads();
+    const float* avg = ranks.avg[ranks.rank] + (int64_t)(step & 1u) * n;
+    for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < n / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = 4 * i4;
+        const float4 g = ldcv4(avg + e);
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+        sgd_apply4(segs, e, gg, lr, momentum);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -244,10 +325,52 @@ extern "C" int tgcn_peer_close(void* ptr) {
 }
 
 // bytes of one rank's region for n gradient elements in nseg tensors (each padded to 4 elements): two flat
-// buffers + the flag line
+// gradient buffers, two averaged-gradient buffers (two-shot variant) and the two flag lines
+static int64_t peer_flat_elems(int64_t n, int nseg) { return n + 3 * (int64_t)nseg; }
 extern "C" int64_t tgcn_peer_region_bytes(int64_t n, int nseg) {
-    return (n < 0 || nseg < 0) ? 0 : 2 * (n + 3 * (int64_t)nseg) * (int64_t)sizeof(float) + 256;
+    return (n < 0 || nseg < 0) ? 0 : 4 * peer_flat_elems(n, nseg) * (int64_t)sizeof(float) + 512;
 }
+
+namespace tgcn {
+// Region layout for a flat buffer of n (padded) elements: [flat0 | flat1 | flags (256 B) | flags2 (256 B) | avg0 | avg1].
+// The flag lines sit right behind the two flat buffers, so a region that is only ever packed and read (bighead.cu)
+// needs 2 n floats + 512 bytes.
+static void peer_fill_ranks(PeerRanks& ranks, void* const* regions_host, int world, int rank, int64_t n) {
+    ranks.world = world; ranks.rank = rank; ranks.timeout_ns = peer_timeout_ns();
+    for (int r = 0; r < world; ++r) {
+        char* base = reinterpret_cast<char*>(regions_host[r]);
+        ranks.flat[r] = reinterpret_cast<const float*>(base);
+        ranks.flag[r] = reinterpret_cast<unsigned int*>(base + 2 * n * sizeof(float));
+        ranks.flag2[r] = reinterpret_cast<unsigned int*>(base + 2 * n * sizeof(float) + 256);
+        ranks.avg[r] = reinterpret_cast<float*>(base + 2 * n * sizeof(float) + 512);
+    }
+}
+
+// Copy `nseg` tensors of this rank into flat[step & 1] of its region and publish the step flag to every rank
+// (state[0] = step counter, state[1] = block counter).  Used by the gradient exchange below and by bighead.cu.
+int peer_pack_launch(void* const* regions_host, int world, int rank, const float* const* srcs_host, const int64_t* numels_host,
+                     int nseg, unsigned int* state, cudaStream_t st) {
+    TGCN_SUPPORTED(nseg >= 1 && nseg <= kPeerMaxSeg, "peer_pack: %d tensors (max %d)", nseg, kPeerMaxSeg);
+    PeerSegs segs{};
+    segs.nseg = nseg;
+    int64_t n = 0;
+    for (int s = 0; s < nseg; ++s) {
+        TGCN_REQUIRE(!srcs_host[s] || aligned16(srcs_host[s]), "peer_pack: tensor %d is not 16-byte aligned", s);
+        segs.grad[s] = srcs_host[s];
+        segs.off[s] = n;
+        segs.len[s] = numels_host[s];
+        n += (numels_host[s] + 3) & ~(int64_t)3;
+    }
+    segs.off[nseg] = n;
+    PeerRanks ranks{};
+    for (int r = 0; r < world; ++r) TGCN_REQUIRE(regions_host[r], "peer_pack: null region for rank %d", r);
+    peer_fill_ranks(ranks, regions_host, world, rank, n);
+    const int blocks = (int)min64(ceil_div(n > 0 ? n / 4 : 1, 256), (int64_t)kNumSMs * 8);
+    peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, ranks, reinterpret_cast<float*>(regions_host[rank]), n, state, state + 1);
+    TGCN_LAUNCH_CHECK("peer_pack");
+    return TGCN_OK;
+}
+}  // namespace tgcn
 
 // One data-parallel optimizer step.  regions_host[r]: rank r's region base as seen from THIS process (own region
 // for r == rank); grads/params/moms/numels: nseg host arrays describing the parameter tensors in a fixed order
@@ -271,14 +394,6 @@ extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int
                      "tgcn_peer_allreduce_sgd: segment %d is not 16-byte aligned", s);
     }
     segs.off[nseg] = n;
-    PeerRanks ranks{};
-    ranks.world = world; ranks.rank = rank;
-    for (int r = 0; r < world; ++r) {
-        TGCN_REQUIRE(regions_host[r], "tgcn_peer_allreduce_sgd: null region for rank %d", r);
-        ranks.flat[r] = reinterpret_cast<const float*>(regions_host[r]);
-        ranks.flag[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[r]) + 2 * n * sizeof(float));
-    }
-    float* my_flat = reinterpret_cast<float*>(regions_host[rank]);
     cudaStream_t st = as_stream(stream);
     const int blocks = (int)min64(ceil_div(n > 0 ? n / 4 : 1, 256), (int64_t)kNumSMs * 8);
     if (world == 1) {
@@ -286,9 +401,26 @@ extern "C" int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int
         TGCN_LAUNCH_CHECK("sgd_direct");
         return TGCN_OK;
     }
+    PeerRanks ranks{};
+    for (int r = 0; r < world; ++r) TGCN_REQUIRE(regions_host[r], "tgcn_peer_allreduce_sgd: null region for rank %d", r);
+    peer_fill_ranks(ranks, regions_host, world, rank, n);
+    float* my_flat = reinterpret_cast<float*>(regions_host[rank]);
     peer_pack_kernel<<<blocks, 256, 0, st>>>(segs, ranks, my_flat, n, state, state + 1);
     TGCN_LAUNCH_CHECK("peer_pack");
-    peer_reduce_sgd_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);
-    TGCN_LAUNCH_CHECK("peer_reduce_sgd");
+    // one-shot (every rank reads everything: (world-1) n elements in, one flag round trip) or two-shot (reduce-scatter +
+    // pushed all-gather: 2 (world-1)/world n elements, two flag round trips).  Decided from (n, world) only, so every
+    // rank takes the same branch; TGCN_PEER_TWOSHOT=0/1 forces it.
+    static const int forced = [] { const char* e = getenv("TGCN_PEER_TWOSHOT"); return e ? atoi(e) : -1; }();
+    const bool twoshot = forced >= 0 ? forced != 0 : (world >= 4 && n * (int64_t)sizeof(float) >= ((int64_t)2 << 20));
+    if (!twoshot) {
+        peer_reduce_sgd_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);
+        TGCN_LAUNCH_CHECK("peer_reduce_sgd");
+        return TGCN_OK;
+    }
+    const int rs_blocks = (int)min64(ceil_div(ceil_div(n / 4, world), 256), (int64_t)kNumSMs * 4);
+    peer_rs_kernel<<<rs_blocks > 0 ? rs_blocks : 1, 256, 0, st>>>(ranks, n, state, state + 3);
+    TGCN_LAUNCH_CHECK("peer_rs");
+    peer_apply_kernel<<<blocks, 256, 0, st>>>(segs, ranks, n, lr, momentum, state, state + 2);
+    TGCN_LAUNCH_CHECK("peer_apply");
     return TGCN_OK;
 }

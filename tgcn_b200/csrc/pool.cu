@@ -17,7 +17,8 @@ __device__ __forceinline__ void take_max(float cand, int s, float& best, int& ar
 template <int P, bool RELU, int VEC>
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, int64_t rows_out,
-                int G) {
+                int G, float drop_p, uint32_t drop_seed, const uint32_t* drop_step) {
+    const DropCfg drop = drop_resolve(RELU ? drop_p : 0.f, drop_seed, drop_step);
     // rows_out = Q * N/P pooled rows; a pooled row reads P consecutive input rows of G floats
     const int GV = G / VEC;
     const int64_t total = rows_out * GV;
@@ -40,6 +41,7 @@ pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __r
             for (int c = 0; c < VEC; ++c) {
                 float u = v[c];
                 if (RELU) u = (u != u) ? u : fmaxf(u, 0.f);   // F.relu keeps NaN
+                if (RELU && drop.scale != 0.f) u = drop_apply(u, (uint64_t)((r * P + s) * G + gv * VEC + c), drop);
                 if (s == 0) { best[c] = u; arg[c] = 0; }
                 else take_max(u, s, best[c], arg[c]);
             }
@@ -60,7 +62,7 @@ pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __r
 template <int P, bool RELU>
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, const float* __restrict__ x,
-                float* __restrict__ dx, int64_t rows_out, int G) {
+                const float* __restrict__ y, float drop_scale, float* __restrict__ dx, int64_t rows_out, int G) {
     const int64_t total = rows_out * G;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / G;
@@ -71,7 +73,11 @@ pool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, c
         for (int s = 0; s < P; ++s) {
             const int64_t o = (r * P + s) * G + g;
             float v = (s == a) ? gval : 0.f;
-            if (RELU && s == a) {
+            if (RELU && s == a && y != nullptr) {
+                // gate on the pooled OUTPUT: y > 0 <=> its source passed the ReLU and was kept by the dropout
+                const float yv = __ldg(y + i);
+                v = (yv > 0.f || yv != yv) ? gval * drop_scale : 0.f;
+            } else if (RELU && s == a) {
                 const float xv = __ldg(x + o);
                 // relu'(x) = 1 for x > 0, 0 for x <= 0; NaN input propagates NaN like autograd's threshold_backward
                 v = (xv > 0.f) ? gval : ((xv != xv) ? gval : 0.f);
@@ -86,7 +92,12 @@ pool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, c
 using namespace tgcn;
 
 extern "C" int tgcn_pool_max_fwd(const float* x, float* y, uint8_t* idx, int Q, int N, int G, int p, int relu,
-                                 void* stream) {
+                                 const tgcn_dropout_t* drop, void* stream) {
+    const float dp = (drop && drop->p > 0.f) ? drop->p : 0.f;
+    TGCN_REQUIRE(dp < 1.f, "tgcn_pool_max_fwd: dropout p = %g must be < 1", (double)dp);
+    TGCN_REQUIRE(dp == 0.f || relu, "tgcn_pool_max_fwd: dropout is fused behind the ReLU only");
+    const uint32_t dseed = drop ? drop->seed : 0u;
+    const uint32_t* dstep = drop ? drop->step : nullptr;
     TGCN_REQUIRE(Q >= 0 && N >= 0 && G >= 1, "tgcn_pool_max_fwd: bad sizes");
     TGCN_SUPPORTED(p == 2 || p == 4, "tgcn_pool_max_fwd: pool size %d (reference has gcn_pool p=2, gcn_pool_4 p=4)", p);
     TGCN_REQUIRE(N % p == 0, "tgcn_pool_max_fwd: vertex count %d not divisible by pool size %d", N, p);
@@ -99,8 +110,8 @@ extern "C" int tgcn_pool_max_fwd(const float* x, float* y, uint8_t* idx, int Q, 
     const unsigned blocks = (unsigned)min64(ceil_div(total, 256), (int64_t)kNumSMs * 32);
 #define TGCN_POOL_FWD(P, R)                                                                            \
     do {                                                                                               \
-        if (vec) pool_fwd_kernel<P, R, 4><<<blocks, 256, 0, st>>>(x, y, idx, rows_out, G);             \
-        else pool_fwd_kernel<P, R, 1><<<blocks, 256, 0, st>>>(x, y, idx, rows_out, G);                 \
+        if (vec) pool_fwd_kernel<P, R, 4><<<blocks, 256, 0, st>>>(x, y, idx, rows_out, G, dp, dseed, dstep);             \
+        else pool_fwd_kernel<P, R, 1><<<blocks, 256, 0, st>>>(x, y, idx, rows_out, G, dp, dseed, dstep);                 \
     } while (0)
     if (p == 2) { if (relu) TGCN_POOL_FWD(2, true); else TGCN_POOL_FWD(2, false); }
     else        { if (relu) TGCN_POOL_FWD(4, true); else TGCN_POOL_FWD(4, false); }
@@ -109,23 +120,27 @@ extern "C" int tgcn_pool_max_fwd(const float* x, float* y, uint8_t* idx, int Q, 
     return TGCN_OK;
 }
 
-extern "C" int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, float* dx, int Q, int N,
-                                 int G, int p, int relu, void* stream) {
+extern "C" int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, const float* y, float* dx, int Q,
+                                 int N, int G, int p, int relu, const tgcn_dropout_t* drop, void* stream) {
+    const float dp = (drop && drop->p > 0.f) ? drop->p : 0.f;
+    TGCN_REQUIRE(dp < 1.f, "tgcn_pool_max_bwd: dropout p = %g must be < 1", (double)dp);
+    TGCN_REQUIRE(dp == 0.f || (relu && y), "tgcn_pool_max_bwd: the dropout backward gates on the pooled output y");
+    const float dscale = 1.0f / (1.0f - dp);
     TGCN_REQUIRE(Q >= 0 && N >= 0 && G >= 1, "tgcn_pool_max_bwd: bad sizes");
     TGCN_SUPPORTED(p == 2 || p == 4, "tgcn_pool_max_bwd: pool size %d", p);
     TGCN_REQUIRE(N % p == 0, "tgcn_pool_max_bwd: vertex count %d not divisible by pool size %d", N, p);
     const int64_t rows_out = (int64_t)Q * (N / p);
     if (rows_out == 0) return TGCN_OK;
     TGCN_REQUIRE(dy && idx && dx, "tgcn_pool_max_bwd: null pointer");
-    TGCN_REQUIRE(!relu || x, "tgcn_pool_max_bwd: relu backward needs the pool input");
+    TGCN_REQUIRE(!relu || x || y, "tgcn_pool_max_bwd: relu backward needs the pool input x or the pooled output y");
     cudaStream_t st = as_stream(stream);
     const unsigned blocks = (unsigned)min64(ceil_div(rows_out * G, 256), (int64_t)kNumSMs * 32);
     if (p == 2) {
-        if (relu) pool_bwd_kernel<2, true><<<blocks, 256, 0, st>>>(dy, idx, x, dx, rows_out, G);
-        else pool_bwd_kernel<2, false><<<blocks, 256, 0, st>>>(dy, idx, x, dx, rows_out, G);
+        if (relu) pool_bwd_kernel<2, true><<<blocks, 256, 0, st>>>(dy, idx, x, y, dscale, dx, rows_out, G);
+        else pool_bwd_kernel<2, false><<<blocks, 256, 0, st>>>(dy, idx, x, y, dscale, dx, rows_out, G);
     } else {
-        if (relu) pool_bwd_kernel<4, true><<<blocks, 256, 0, st>>>(dy, idx, x, dx, rows_out, G);
-        else pool_bwd_kernel<4, false><<<blocks, 256, 0, st>>>(dy, idx, x, dx, rows_out, G);
+        if (relu) pool_bwd_kernel<4, true><<<blocks, 256, 0, st>>>(dy, idx, x, y, dscale, dx, rows_out, G);
+        else pool_bwd_kernel<4, false><<<blocks, 256, 0, st>>>(dy, idx, x, y, dscale, dx, rows_out, G);
     }
     TGCN_LAUNCH_CHECK("pool_max_bwd");
     return TGCN_OK;

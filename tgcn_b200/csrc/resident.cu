@@ -181,6 +181,7 @@ struct ResFwdParams {
     float* stack;          // [Q][NP][K][DP] or null (inference)
     int N, NP, E, D, DP, V, G, GP, GG, K;
     int bias_mode, recursion, pool_p, relu;
+    float drop_p; uint32_t drop_seed; const uint32_t* drop_step;   // dropout between the ReLU and the pool (common.cuh)
     int CL, rg_per;        // CTAs per sample (cluster size) and row groups (of 4 rows) per CTA
     int GP16, MT;          // kTC: padded filter count of the MMA and number of 128-row tiles of this CTA's rows
 };
@@ -243,6 +244,7 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
     const int CL = p.CL;
     const int q = blockIdx.x / CL, c = blockIdx.x - q * CL;    // 1-D clusters: c is the rank in the cluster
     const int N = p.N, NP = p.NP, D = p.D, DP = p.DP, V = p.V, G = p.G, GG = p.GG, K = p.K;
+    const DropCfg drop = drop_resolve((p.relu && p.y) ? p.drop_p : 0.f, p.drop_seed, p.drop_step);
     const int slab = NP * DP;                                  // floats per P buffer
     const int rg0 = min(c * p.rg_per, NP / 4), rg1 = min(NP / 4, rg0 + p.rg_per);   // a trailing rank may own no rows
     const int row0 = rg0 * 4, row1 = min(N, rg1 * 4);          // rows this CTA computes
@@ -534,6 +536,7 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
                     for (int i = 0; i < 16; ++i) {
                         float x0 = v[i];
                         if (p.relu) x0 = (x0 != x0) ? x0 : fmaxf(x0, 0.f);
+                        if (drop.scale != 0.f) x0 = drop_apply(x0, (uint64_t)(((int64_t)q * N + n) * G + cb + i), drop);
                         float b0 = x0;
                         int a0 = 0;
                         for (int s2 = 1; s2 < pp; ++s2) {
@@ -619,8 +622,11 @@ resident_fwd_kernel(const ResFwdParams p, const ResSmemFwd lay) {
 #pragma unroll
                     for (int s2 = 0; s2 < 4; ++s2) {
                         if (s2 >= pp) break;
-                        float vv = (pp == 4) ? o[s2][cc] : o[(u * 2 + s2) & 3][cc];
+                        const int rsel = (pp == 4) ? s2 : ((u * 2 + s2) & 3);
+                        float vv = o[rsel][cc];
                         if (p.relu) vv = (vv != vv) ? vv : fmaxf(vv, 0.f);
+                        if (drop.scale != 0.f)
+                            vv = drop_apply(vv, (uint64_t)(((int64_t)q * N + rg * 4 + rsel) * G + g0 + cc), drop);
                         if (s2 == 0) { best[cc] = vv; arg[cc] = 0; }
                         else take_max_r(vv, s2, best[cc], arg[cc]);
                     }
@@ -656,6 +662,7 @@ struct ResBwdParams {
     float* dx;             // [Q,N,D] or null
     int N, NP, E, D, DP, V, G, GP, GG, K;
     int recursion, pool_p, relu;
+    float drop_scale;      // 1 / (1 - p) of the dropout fused behind the ReLU (1 when off)
     int S, Vh;             // CTAs per sample (gridDim.y) and float4 column groups of dx per CTA
     int R;                 // rows of the saved basis per ring stage
 };
@@ -753,8 +760,9 @@ resident_bwd_kernel(const ResBwdParams p, const ResSmemBwd lay) {
                 float4 v = __ldg(reinterpret_cast<const float4*>(p.dy + off));
                 if (p.relu) {   // relu(x_argmax) = y: > 0 <=> x_argmax > 0, NaN <=> NaN (gradient passes)
                     const float4 yy = __ldg(reinterpret_cast<const float4*>(p.y + off));
-                    v.x = (yy.x > 0.f || yy.x != yy.x) ? v.x : 0.f; v.y = (yy.y > 0.f || yy.y != yy.y) ? v.y : 0.f;
-                    v.z = (yy.z > 0.f || yy.z != yy.z) ? v.z : 0.f; v.w = (yy.w > 0.f || yy.w != yy.w) ? v.w : 0.f;
+                    const float ds = p.drop_scale;   // y > 0: the source passed the ReLU and was kept by the dropout
+                    v.x = (yy.x > 0.f || yy.x != yy.x) ? v.x * ds : 0.f; v.y = (yy.y > 0.f || yy.y != yy.y) ? v.y * ds : 0.f;
+                    v.z = (yy.z > 0.f || yy.z != yy.z) ? v.z * ds : 0.f; v.w = (yy.w > 0.f || yy.w != yy.w) ? v.w * ds : 0.f;
                 }
                 for (int s = 0; s < pp; ++s) {
                     const float4 o = make_float4(a.x == s ? v.x : 0.f, a.y == s ? v.y : 0.f, a.z == s ? v.z : 0.f,
@@ -775,7 +783,7 @@ resident_bwd_kernel(const ResBwdParams p, const ResSmemBwd lay) {
                         v = __ldg(p.dy + off);
                         if (p.relu) {
                             const float yy = __ldg(p.y + off);
-                            v = (yy > 0.f || yy != yy) ? v : 0.f;
+                            v = (yy > 0.f || yy != yy) ? v * p.drop_scale : 0.f;
                         }
                     }
                 }
@@ -988,6 +996,7 @@ struct ResReduceParams {
     const float* dout; const float* dy; const uint8_t* idx; const float* y;
     float* db;
     int Q, N, D, DP, G, GP, K, recursion, bias_mode, pool_p, relu;
+    float drop_scale;
     int w_blocks;          // blocks [0, w_blocks) reduce weights, the rest the bias
 };
 
@@ -1082,7 +1091,7 @@ resident_reduce_kernel(const ResReduceParams p) {
                 float v = __ldg(p.dy + off);
                 if (p.relu) {
                     const float yy = __ldg(p.y + off);
-                    v = (yy > 0.f || yy != yy) ? v : 0.f;
+                    v = (yy > 0.f || yy != yy) ? v * p.drop_scale : 0.f;
                 }
                 s0 += a == 0 ? v : 0.f; s1 += a == 1 ? v : 0.f; s2 += a == 2 ? v : 0.f; s3 += a == 3 ? v : 0.f;
             }
@@ -1282,9 +1291,13 @@ extern "C" int64_t tgcn_resident_bwd_workspace(int Q, int N, int D, int G, int K
 
 extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* entries, int N, int64_t E,
                                        const float* x, const float* W, const float* bias, int bias_mode,
-                                       float* out, float* y, uint8_t* idx, int pool_p, int relu, float* stack,
+                                       float* out, float* y, uint8_t* idx, int pool_p, int relu,
+                                       const tgcn_dropout_t* drop, float* stack,
                                        float* wimages, int Q, int D, int G, int K, int recursion, void* stream) {
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && G >= 1 && K >= 1, "tgcn_resident_layer_fwd: bad sizes");
+    const float drop_p = (drop && drop->p > 0.f) ? drop->p : 0.f;
+    TGCN_REQUIRE(drop_p < 1.f, "tgcn_resident_layer_fwd: dropout p = %g must be < 1", (double)drop_p);
+    TGCN_REQUIRE(drop_p == 0.f || (relu && y), "tgcn_resident_layer_fwd: dropout is fused between the ReLU and the pool only");
     TGCN_REQUIRE(recursion == TGCN_RECURSION_REFERENCE || recursion == TGCN_RECURSION_CHEBYSHEV,
                  "tgcn_resident_layer_fwd: unknown recursion %d", recursion);
     if (Q == 0 || N == 0) return TGCN_OK;
@@ -1317,6 +1330,7 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* en
     p.stack = stack; p.N = N; p.NP = pl.NP; p.E = (int)E; p.D = D; p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP;
     p.GG = pl.GG; p.K = K; p.bias_mode = bias_mode; p.recursion = recursion; p.pool_p = y ? pool_p : 4; p.relu = relu;
     p.CL = pl.split; p.rg_per = pl.rg_per;
+    p.drop_p = drop_p; p.drop_seed = drop ? drop->seed : 0u; p.drop_step = drop ? drop->step : nullptr;
     const ResSmemFwd lay = res_fwd_smem(N, E, pl.DP, pl.GP, K, pl.csr_smem, pl.w_smem, pl.tc ? pl.MT : 0, pl.GP16);
     const dim3 grid((unsigned)(Q * pl.split));
     if (pl.tc) {
@@ -1356,10 +1370,14 @@ extern "C" int tgcn_resident_layer_fwd(const int32_t* rowinfo, const int32_t* en
 
 extern "C" int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* entriesT, int N, int64_t E,
                                        const float* dout, const float* dy, const uint8_t* idx, const float* y,
-                                       int pool_p, int relu, const float* stack, const float* wimages,
+                                       int pool_p, int relu, const tgcn_dropout_t* drop, const float* stack,
+                                       const float* wimages,
                                        float* dW, float* db, int bias_mode, float* dx, void* workspace,
                                        int Q, int D, int G, int K, int recursion, void* stream) {
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && G >= 1 && K >= 1, "tgcn_resident_layer_bwd: bad sizes");
+    const float drop_p = (drop && drop->p > 0.f) ? drop->p : 0.f;
+    TGCN_REQUIRE(drop_p < 1.f, "tgcn_resident_layer_bwd: dropout p = %g must be < 1", (double)drop_p);
+    TGCN_REQUIRE(drop_p == 0.f || (relu && dy), "tgcn_resident_layer_bwd: dropout is fused between the ReLU and the pool only");
     TGCN_REQUIRE(recursion == TGCN_RECURSION_REFERENCE || recursion == TGCN_RECURSION_CHEBYSHEV,
                  "tgcn_resident_layer_bwd: unknown recursion %d", recursion);
     TGCN_REQUIRE(dW, "tgcn_resident_layer_bwd: null dW");
@@ -1394,6 +1412,7 @@ extern "C" int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* e
     p.N = N; p.NP = pl.NP; p.E = (int)E; p.D = D;
     p.DP = pl.DP; p.V = pl.V; p.G = G; p.GP = pl.GP; p.GG = pl.GG; p.K = K; p.recursion = recursion;
     p.pool_p = dy ? pool_p : 4; p.relu = relu; p.S = pl.split; p.Vh = pl.Vh; p.R = pl.R;
+    p.drop_scale = 1.0f / (1.0f - drop_p);
     const ResSmemBwd lay = res_bwd_smem(N, E, pl.DP, pl.Vh, pl.GP, K, pl.R, dx != nullptr, pl.csr_smem, pl.w_smem);
     const dim3 grid((unsigned)Q, (unsigned)pl.split);
 #define TGCN_RES_BWD2(DWT, CS, WS) \
@@ -1412,7 +1431,7 @@ extern "C" int tgcn_resident_layer_bwd(const int32_t* rowinfoT, const int32_t* e
     ResReduceParams r{};
     r.dWpart = p.dWpart; r.dbpart = p.dbpart; r.dW = dW; r.dout = dout; r.dy = dy; r.idx = idx; r.y = y; r.db = db;
     r.Q = Q; r.N = N; r.D = D; r.DP = pl.DP; r.G = G; r.GP = pl.GP; r.K = K; r.recursion = recursion;
-    r.bias_mode = bias_mode; r.pool_p = p.pool_p; r.relu = relu;
+    r.bias_mode = bias_mode; r.pool_p = p.pool_p; r.relu = relu; r.drop_scale = p.drop_scale;
     r.w_blocks = (int)ceil_div((int64_t)D * G, kRedElems);
     int b_blocks = 0;
     if (bias_mode == TGCN_BIAS_PER_VERTEX)

@@ -36,6 +36,16 @@ def _require_cuda_f32(t, name):
         raise RuntimeError("%s has dtype %s: tgcn_b200 kernels are fp32" % (name, t.dtype))
 
 
+def _drop_arg(drop):
+    """drop = None or (p, seed, step_tensor_or_None) -> ctypes argument for a `const tgcn_dropout_t*` parameter."""
+    if drop is None or not drop[0]:
+        return None
+    p, seed, step = drop
+    if not 0.0 <= p < 1.0:
+        raise ValueError("dropout probability has to be in [0, 1), got %r" % (p,))
+    return _lib.dropout_arg(p, seed, None if step is None else step.data_ptr())
+
+
 class _DeviceGuard:
     """Make the tensor's device current for the raw launches (ctypes calls bypass torch's guard)."""
 
@@ -127,8 +137,10 @@ class ResidentChebFunction(torch.autograd.Function):
     activation.  Same math as ChebLayerFunction (+ PoolFunction); gcn.py:108-154, :246-255."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, plan, bias_mode, recursion, pool_p, relu):
+    def forward(ctx, x, weight, bias, plan, bias_mode, recursion, pool_p, relu, drop=None):
         lib = _lib.load()
+        if drop is not None and drop[0] and not (pool_p and relu):
+            raise RuntimeError("dropout is fused between the ReLU and the pool only")
         Q, N, D = x.shape
         K, Dw, G = weight.shape
         if Dw != D:
@@ -157,12 +169,13 @@ class ResidentChebFunction(torch.autograd.Function):
         rowinfo, entries, E = plan.packed(lib.tgcn_resident_pack_classes(Q, N, D, 0))
         with _DeviceGuard(dev):
             rc = lib.tgcn_resident_layer_fwd(_ptr(rowinfo), _ptr(entries), N, E, _ptr(x), _ptr(w),
-                                             _ptr(b), bm, _ptr(out), _ptr(y), _ptr(idx), pool_p, int(relu), _ptr(stack),
-                                             _ptr(wimg), Q, D, G, K, recursion, _stream(dev))
+                                             _ptr(b), bm, _ptr(out), _ptr(y), _ptr(idx), pool_p, int(relu), _drop_arg(drop),
+                                             _ptr(stack), _ptr(wimg), Q, D, G, K, recursion, _stream(dev))
         _lib.check(rc, "tgcn_resident_layer_fwd")
         ctx.plan = plan
         ctx.dims = (Q, N, D, G, K)
         ctx.cfg = (bm, recursion, pool_p, bool(relu))
+        ctx.drop_p = float(drop[0]) if (drop is not None and drop[0]) else 0.0
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.w_shape = tuple(weight.shape)
         ctx.x_shape = tuple(x.shape)
@@ -178,7 +191,7 @@ class ResidentChebFunction(torch.autograd.Function):
     def backward(ctx, grad, _didx=None):
         lib = _lib.load()
         if grad is None:
-            return (None,) * 8
+            return (None,) * 9
         Q, N, D, G, K = ctx.dims
         bm, recursion, pool_p, relu = ctx.cfg
         plan = ctx.plan
@@ -198,19 +211,21 @@ class ResidentChebFunction(torch.autograd.Function):
         with _DeviceGuard(dev):
             rc = lib.tgcn_resident_layer_bwd(_ptr(rowinfo), _ptr(entries), N, E,
                                              None if pool_p else _ptr(grad), _ptr(grad) if pool_p else None, _ptr(idx), _ptr(y),
-                                             pool_p, int(relu), _ptr(stack), _ptr(wimg), _ptr(dW), _ptr(db), bm, _ptr(dx), _ptr(ws),
-                                             Q, D, G, K, recursion, _stream(dev))
+                                             pool_p, int(relu), _lib.dropout_arg(ctx.drop_p), _ptr(stack), _ptr(wimg), _ptr(dW),
+                                             _ptr(db), bm, _ptr(dx), _ptr(ws), Q, D, G, K, recursion, _stream(dev))
         _lib.check(rc, "tgcn_resident_layer_bwd")
-        return dx, dW, db, None, None, None, None, None
+        return dx, dW, db, None, None, None, None, None, None
 
 
 class PoolFunction(torch.autograd.Function):
     """Permuted max-pool with first-argmax gradient routing (tgcn/nn/gcn.py:246-255), optional fused ReLU."""
 
     @staticmethod
-    def forward(ctx, x, p, relu):
+    def forward(ctx, x, p, relu, drop=None):
         lib = _lib.load()
         _require_cuda_f32(x, "x")
+        if drop is not None and drop[0] and not relu:
+            raise RuntimeError("dropout is fused between the ReLU and the pool only")
         if x.dim() != 3:
             raise RuntimeError("pool expects [Q, N, G], got %s" % (tuple(x.shape),))
         Q, N, G = x.shape
@@ -222,11 +237,14 @@ class PoolFunction(torch.autograd.Function):
         y = torch.empty((Q, N // p, G), dtype=torch.float32, device=dev)
         idx = torch.empty((Q, N // p, G), dtype=torch.uint8, device=dev)
         with _DeviceGuard(dev):
-            rc = lib.tgcn_pool_max_fwd(_ptr(x), _ptr(y), _ptr(idx), Q, N, G, p, int(relu), _stream(dev))
+            rc = lib.tgcn_pool_max_fwd(_ptr(x), _ptr(y), _ptr(idx), Q, N, G, p, int(relu), _drop_arg(drop), _stream(dev))
         _lib.check(rc, "tgcn_pool_max_fwd")
         ctx.p, ctx.relu, ctx.dims = p, relu, (Q, N, G)
+        ctx.drop_p = float(drop[0]) if (drop is not None and drop[0]) else 0.0
         if relu:
-            ctx.save_for_backward(idx, x)
+            # the ReLU (and dropout) gate of the backward is read off the pooled OUTPUT: y > 0 <=> its source passed
+            # the ReLU (and was kept) -- a quarter of the bytes of the un-pooled input
+            ctx.save_for_backward(idx, y)
         else:
             ctx.save_for_backward(idx)
         ctx.mark_non_differentiable(idx)
@@ -237,18 +255,19 @@ class PoolFunction(torch.autograd.Function):
     def backward(ctx, dy, _didx=None):
         lib = _lib.load()
         if dy is None:
-            return None, None, None
+            return None, None, None, None
         saved = ctx.saved_tensors
         idx = saved[0]
-        x = saved[1] if ctx.relu else None
+        y = saved[1] if ctx.relu else None
         Q, N, G = ctx.dims
         dy = dy.contiguous()
         dev = dy.device
         dx = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
         with _DeviceGuard(dev):
-            rc = lib.tgcn_pool_max_bwd(_ptr(dy), _ptr(idx), _ptr(x), _ptr(dx), Q, N, G, ctx.p, int(ctx.relu), _stream(dev))
+            rc = lib.tgcn_pool_max_bwd(_ptr(dy), _ptr(idx), None, _ptr(y), _ptr(dx), Q, N, G, ctx.p, int(ctx.relu),
+                                       _lib.dropout_arg(ctx.drop_p), _stream(dev))
         _lib.check(rc, "tgcn_pool_max_bwd")
-        return dx, None, None
+        return dx, None, None, None
 
 
 def cheb_basis(x, plan, K, recursion=_lib.RECURSION_REFERENCE, reference_layout=True):

@@ -30,6 +30,18 @@ def dft_real_matrix(H):
     return torch.cos(2.0 * math.pi * torch.outer(h, h) / H).to(torch.float32)
 
 
+def _num_vertices(L):
+    """N of the operand.  The reference writes `L[0].shape[0]` (gcn.py:22,96), which is N for the dense / torch-sparse
+    tensors its examples pass; for a scipy CSR matrix (also accepted here) `L[0]` is a 1 x N row, so N is taken from
+    the matrix shape itself."""
+    shape = getattr(L, "shape", None)
+    if shape is not None and len(shape) == 2:
+        if shape[0] != shape[1]:
+            raise ValueError("L must be square, got %s" % (tuple(shape),))
+        return int(shape[0])
+    return int(L[0].shape[0])
+
+
 def uniform(size, tensor):
     """U(-1/sqrt(size), 1/sqrt(size)) in place; no-op for None (reference gcn.py:240-243)."""
     bound = 1.0 / math.sqrt(size)
@@ -44,7 +56,8 @@ class _ChebBase(torch.nn.Module):
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.weight = Parameter(torch.Tensor(*weight_shape))
-        self.L = L                      # plain attribute, exactly like the reference (not in state_dict)
+        self._csr = CSRCache()
+        self.L = L                      # attribute like the reference's (not in state_dict); see the `L` property
         self.filter_order = filter_order
         if bias:
             self.bias = Parameter(torch.Tensor(*bias_shape))
@@ -56,8 +69,20 @@ class _ChebBase(torch.nn.Module):
             raise ValueError("engine must be one of %s" % sorted(_ENGINE))
         self.recursion = recursion
         self.engine = engine
-        self._csr = CSRCache()
         self.reset_parameters()
+
+    # The reference re-reads `self.L` on every forward (gcn.py:141,223); here the operand is converted once per device
+    # and cached, so assigning a new `layer.L` drops the cached CSR plans.
+    @property
+    def L(self):
+        return self.__dict__.get("_L")
+
+    @L.setter
+    def L(self, value):
+        self.__dict__["_L"] = value
+        cache = self.__dict__.get("_csr")
+        if cache is not None:
+            cache.clear()
 
     def reset_parameters(self):
         size = self.in_channels * self.weight.size(0)
@@ -89,7 +114,28 @@ class _ChebBase(torch.nn.Module):
     def _effective_weight(self):
         return self.weight
 
-    def _run(self, x3, pool_p=0, relu=False):
+    # -- fused dropout stream (the nn.Dropout between ReLU and pool of the reference models) ------------------------
+    dropout_step = None      # optional external device uint32 counter advanced once per training step by the caller
+                             # (e.g. PeerAllreduceSGD.state): saves the layer's own counter bump launch
+
+    def _drop_spec(self, p, device):
+        """(p, seed, step tensor) for the kernels.  The mask of a step is a hash of (seed, step counter, element): the
+        seed derives from torch.initial_seed() and the layer's shape (no draw from the global RNG); the counter is the
+        caller's `dropout_step` tensor, or a per-layer device counter bumped on every dropout forward."""
+        if not p:
+            return None
+        seed = (torch.initial_seed() * 0x9E3779B1 + self.weight.numel() * 0x85EBCA77 + self.out_channels) & 0xFFFFFFFF
+        step = self.dropout_step
+        if step is None:
+            ctr = self.__dict__.get("_drop_ctr")
+            if ctr is None or ctr.device != device:
+                ctr = torch.zeros(1, dtype=torch.int32, device=device)
+                self.__dict__["_drop_ctr"] = ctr
+            ctr.add_(1)
+            step = ctr
+        return (float(p), seed, step)
+
+    def _run(self, x3, pool_p=0, relu=False, dropout=0.0):
         F_._require_cuda_f32(x3, "x")
         w = self._effective_weight()
         F_._require_cuda_f32(w, "weight")
@@ -97,25 +143,35 @@ class _ChebBase(torch.nn.Module):
         w3 = w.reshape(K, -1, w.shape[-1])
         plan = self._plan(x3.device)
         rec = _RECURSION[self.recursion]
+        if self.bias is not None:
+            # the kernels index the bias by (vertex, filter) or (filter): a wrong size would be an out-of-bounds access
+            want = plan.n * w3.shape[2] if self._bias_mode == _lib.BIAS_PER_VERTEX else w3.shape[2]
+            if self.bias.numel() != want:
+                raise RuntimeError("bias has %d elements, expected %d (%s, N=%d, G=%d)"
+                                   % (self.bias.numel(), want,
+                                      "per-vertex" if self._bias_mode == _lib.BIAS_PER_VERTEX else "per-filter",
+                                      plan.n, w3.shape[2]))
+        drop = self._drop_spec(dropout, x3.device) if (pool_p and relu) else None
         if self._use_resident(plan, w3.shape[1], w3.shape[2], K):
-            res = F_.ResidentChebFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, pool_p, relu)
+            res = F_.ResidentChebFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, pool_p, relu, drop)
             return res[0] if pool_p else res
         out = F_.ChebLayerFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, _ENGINE[self.engine])
         if pool_p:
-            out = F_.PoolFunction.apply(out, pool_p, relu)[0]
+            out = F_.PoolFunction.apply(out, pool_p, relu, drop)[0]
         return out
 
     def forward(self, x):
         x3 = self._canon(x)
         return self._run(x3)
 
-    def forward_relu_pool(self, x, p):
-        """gcn_pool / gcn_pool_4 (p = 2 / 4) of F.relu(self(x)) as one fused operation
-        (pytorch_hcp_tgcn.py:133-141 applies exactly this chain after each conv layer): identical
-        values, pool indices and gradients, without writing the un-pooled activation."""
+    def forward_relu_pool(self, x, p, dropout=0.0):
+        """gcn_pool / gcn_pool_4 (p = 2 / 4) of dropout(F.relu(self(x))) as one fused operation
+        (pytorch_hcp_tgcn.py:134-141 applies exactly this chain after each conv layer; `dropout` is the rate of the
+        nn.Dropout between the ReLU and the pool, 0 in evaluation mode): identical values, pool indices and
+        gradients to the unfused chain with the same mask, without writing the un-pooled activation."""
         if p not in (2, 4):
             raise ValueError("pool size must be 2 (gcn_pool) or 4 (gcn_pool_4)")
-        return self._run(self._canon(x), pool_p=p, relu=True)
+        return self._run(self._canon(x), pool_p=p, relu=True, dropout=dropout)
 
     def _basis(self, x):
         x3 = self._canon(x)
@@ -131,7 +187,7 @@ class TGCNCheb_H(_ChebBase):
                  engine="auto", time_dft=False):
         super(TGCNCheb_H, self).__init__()
         self._setup(L, in_channels, out_channels, filter_order,
-                    (filter_order, horizon, in_channels, out_channels), (1, L[0].shape[0], out_channels), bias,
+                    (filter_order, horizon, in_channels, out_channels), (1, _num_vertices(L), out_channels), bias,
                     recursion, engine)
         # time_dft=True folds the models' prologue `x = real(fft(x, axis=2))` (pytorch_mnist_tgcn.py:87,
         # pytorch_hcp_tgcn.py:133) into the weights: the real DFT is linear along h and commutes with L~, so
@@ -172,7 +228,7 @@ class TGCNCheb(_ChebBase):
     def __init__(self, L, in_channels, out_channels, filter_order, bias=True, *, recursion="reference", engine="auto"):
         super(TGCNCheb, self).__init__()
         self._setup(L, in_channels, out_channels, filter_order, (filter_order, in_channels, out_channels),
-                    (1, L[0].shape[0], out_channels), bias, recursion, engine)
+                    (1, _num_vertices(L), out_channels), bias, recursion, engine)
 
     def _canon(self, x):
         if x.dim() != 3:
@@ -225,10 +281,10 @@ def gcn_pool_with_indices(x, p):
     return y, idx.to(torch.int64)
 
 
-def relu_pool(x, p):
-    """F.relu followed by gcn_pool / gcn_pool_4 in one kernel (pytorch_hcp_tgcn.py:135-137 without
-    the dropout); identical values, indices and gradients to the unfused pair."""
-    return F_.PoolFunction.apply(x, p, True)[0]
+def relu_pool(x, p, drop=None):
+    """F.relu (-> dropout) -> gcn_pool / gcn_pool_4 in one kernel (pytorch_hcp_tgcn.py:135-137); identical values,
+    indices and gradients to the unfused chain.  drop: None or (rate, seed, device step counter or None)."""
+    return F_.PoolFunction.apply(x, p, True, drop)[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -272,26 +328,32 @@ class _EdgeChebBase(_ChebBase):
         self.engine = engine
         self.filter_order = weight_shape[0]
         self.L = None
-        self._edge_cache = {}
+        self._edge_cache_list = []
         self.reset_parameters()
 
     def __repr__(self):
         return '{}({}, {}, K={})'.format(self.__class__.__name__, self.in_channels, self.out_channels, self.weight.size(0))
 
     def _edge_plan(self, edge_index, edge_weight, num_nodes, device):
-        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
-               None if edge_weight is None else (edge_weight.data_ptr(), edge_weight._version), num_nodes, str(device))
-        plan = self._edge_cache.get(key)
-        if plan is None:
-            import scipy.sparse as sp
-            from ..csr import build_csr
-            row, col, lap = laplacian_from_edges(edge_index, edge_weight, num_nodes)
-            m = sp.coo_matrix((lap.detach().cpu().numpy(), (row.cpu().numpy(), col.cpu().numpy())),
-                              shape=(num_nodes, num_nodes)).tocsr()      # duplicate edges add up, like scatter_add
-            plan = build_csr(m, device)
-            if len(self._edge_cache) >= 8:
-                self._edge_cache.pop(next(iter(self._edge_cache)))
-            self._edge_cache[key] = plan
+        """CSR operand of this edge list, converted once and cached.  A hit requires the SAME tensor objects
+        (identity, not address: a freed per-batch `edge_index` can be re-allocated at the same address) at the same
+        in-place version; the cache holds references to them, so their storage cannot be recycled while cached."""
+        if edge_weight is not None and edge_weight.requires_grad:
+            raise NotImplementedError("edge_weight.requires_grad: the Laplacian is built once per edge list and is not "
+                                      "differentiated (the reference back-propagates through it, gcn.py:383-398); "
+                                      "detach the weights or build L~ with laplacian_from_edges yourself")
+        for ent in self._edge_cache_list:
+            ei, ev, ew, wv, n, dev, plan = ent
+            if ei is edge_index and ev == edge_index._version and ew is edge_weight and \
+                    (ew is None or wv == edge_weight._version) and n == num_nodes and dev == device:
+                return plan
+        from ..csr import build_csr_from_coo
+        row, col, lap = laplacian_from_edges(edge_index, edge_weight, num_nodes)
+        plan = build_csr_from_coo(row, col, lap.detach(), num_nodes, device)   # duplicate edges add up, like scatter_add
+        if len(self._edge_cache_list) >= 8:
+            self._edge_cache_list.pop(0)
+        self._edge_cache_list.append((edge_index, edge_index._version, edge_weight,
+                                      None if edge_weight is None else edge_weight._version, num_nodes, device, plan))
         return plan
 
     def _run_edges(self, x3, edge_index, edge_weight):

@@ -97,7 +97,7 @@ class GradientBucket:
             off += p.numel()
         self.n_early = sum(p.numel() for p in self.early)
         self._pending = None
-        self._seen = 0
+        self._seen = set()
         self._hooks = []
         if self.world > 1 and self.late and self.early:
             for p in self.early:
@@ -113,9 +113,11 @@ class GradientBucket:
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
         torch._foreach_copy_(views, grads)
 
-    def _on_grad(self, _param):
-        self._seen += 1
-        if self._seen == len(self.early):          # every early gradient exists: reduce them under the rest of the backward
+    def _on_grad(self, param):
+        if self._pending is not None:
+            return
+        self._seen.add(id(param))                  # parameters seen, not hook firings
+        if len(self._seen) == len(self.early):     # every early gradient exists: reduce them under the rest of the backward
             self._pack(self.early, self.views[:len(self.early)])
             self._pending = self._reduce(0, self.n_early, async_op=True)
 
@@ -131,7 +133,7 @@ class GradientBucket:
             self._reduce(self.n_early, self.flat.numel(), async_op=False)
         if self._pending is not None:
             self._pending.wait()
-        self._pending, self._seen = None, 0
+        self._pending, self._seen = None, set()
         if dist.get_backend(self.group) != "nccl":
             self.flat.div_(self.world)
         for p, v in zip(self.params, self.views):
@@ -176,12 +178,21 @@ class _PeerGroup:
             dist.barrier(group=group)
         self._regions_c = (ctypes.c_void_p * world)(*self.regions)
         self._numels_c = (ctypes.c_int64 * len(params))(*[p.numel() for p in params])
+        self._keep = []
 
     def launch(self, lr, momentum, stream):
         from . import _lib
         ct = self._ct
         k = len(self.params)
-        grads = (ct.c_void_p * k)(*[None if p.grad is None else p.grad.contiguous().data_ptr() for p in self.params])
+        # contiguous copies (if any were needed) must stay alive until the launches that read them are enqueued ON THE
+        # STREAM THAT USES THEM -- they are held until the next launch of this group, and recorded on that stream so the
+        # caching allocator does not hand their memory to the producing stream early
+        held = [None if p.grad is None else p.grad.contiguous() for p in self.params]
+        for g in held:
+            if g is not None:
+                g.record_stream(stream)
+        self._keep = held
+        grads = (ct.c_void_p * k)(*[None if g is None else g.data_ptr() for g in held])
         prms = (ct.c_void_p * k)(*[p.data_ptr() for p in self.params])
         moms = (ct.c_void_p * k)(*[m.data_ptr() for m in self.moms])
         with torch.cuda.device(self.device):
@@ -202,7 +213,8 @@ class PeerAllreduceSGD:
     the last of their gradients exists (autograd post-accumulate hooks) their exchange + update is launched on a
     side stream and runs under the rest of the backward; `step()` then exchanges only the late group and joins the
     side stream.  Requirement: nothing enqueued after the last early gradient reads an early parameter (true for a
-    feed-forward model whose `late` parameters belong to its first layers)."""
+    feed-forward model whose `late` parameters belong to its first layers), and ONE backward pass per `step()` -- with
+    gradient accumulation over several backward passes construct the optimizer without `late`."""
 
     def __init__(self, params, lr, momentum=0.0, group=None, late=()):
         from . import _lib
@@ -220,7 +232,7 @@ class PeerAllreduceSGD:
         late_ids = {id(p) for p in late}
         early = [p for p in self.params if id(p) not in late_ids]
         latep = [p for p in self.params if id(p) in late_ids]
-        self._hooks, self._seen, self._launched = [], 0, False
+        self._hooks, self._seen, self._launched = [], set(), False
         if self.world > 1 and early and latep:
             self._early = _PeerGroup(self.lib, early, self.world, self.rank, group)
             self._main = _PeerGroup(self.lib, latep, self.world, self.rank, group)
@@ -241,9 +253,13 @@ class PeerAllreduceSGD:
         """Device-side counters of the group exchanged at `step()` (element 0 = steps taken)."""
         return self._main.state
 
-    def _on_grad(self, _param):
-        self._seen += 1
-        if self._seen == len(self._early.params):      # every early gradient exists: exchange + update them now
+    def _on_grad(self, param):
+        # which parameters have produced a gradient, not how often a hook fired: gradient accumulation over several
+        # backward passes must not trigger the exchange early
+        if self._launched:
+            return
+        self._seen.add(id(param))
+        if len(self._seen) == len(self._early.params):      # every early gradient exists: exchange + update them now
             cur = torch.cuda.current_stream(self.device)
             self._side.wait_stream(cur)
             self._early.launch(self.lr, self.momentum, self._side)
@@ -263,7 +279,7 @@ class PeerAllreduceSGD:
         self._main.launch(self.lr, self.momentum, cur)
         if self._launched:
             cur.wait_stream(self._side)
-        self._seen, self._launched = 0, False
+        self._seen, self._launched = set(), False
 
 
 def broadcast_parameters(module, src=0, group=None):

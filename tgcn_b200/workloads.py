@@ -132,38 +132,66 @@ def synthetic_signals(Q, N0, H, n_real, perm, seed, F_in=None):
 # models
 # ------------------------------------------------------------------------------------------------
 class NetTGCN_HCP(nn.Module):
-    """TGCNCheb_H(L0,1,32,K,H) -> ReLU -> pool4 -> GCNCheb(L2,32,64,K) -> ReLU -> pool4 -> fc(200) -> BN -> ReLU
-    -> fc(n_classes) -> log_softmax   (pytorch_hcp_tgcn.py:93-155; dropout layers omitted: rate-0
-    equivalent, they are elementwise and outside the measured path)."""
+    """real(fft_t(x)) -> TGCNCheb_H(L0,1,32,K,H) -> ReLU -> Dropout(0.1) -> pool4 -> GCNCheb(L2,32,64,K) -> ReLU -> pool4
+    -> fc(200) -> BN -> ReLU -> Dropout(0.5) -> fc(n_classes) -> log_softmax        (pytorch_hcp_tgcn.py:93-155).
+
+    `time_dft`: the model's prologue `torch.rfft(x, 1, onesided=False)[..., 0]` (:133, the real part of the DFT along the
+    time window) is folded into tgcn1's weights (TGCNCheb_H(time_dft=True)) instead of transforming every batch.
+    The dropouts are fused into the pool / head kernels (counter-based masks); `set_dropout_step(t)` hands every fused
+    dropout the device counter the optimizer advances once per step (else each owner bumps its own counter).
+    `fc1_update`: an `nn.head.Fc1FusedSGD` -- fc1.weight's optimizer step then happens inside the backward."""
 
     def __init__(self, L, horizon=15, K=10, g1=32, g2=64, hidden=200, n_classes=6, fused_relu_pool=True, fused_head=True,
-                 **layer_kw):
+                 time_dft=True, drop1=0.1, drop2=0.5, **layer_kw):
         super().__init__()
-        self.tgcn1 = TGCNCheb_H(L[0], 1, g1, K, horizon, **layer_kw)
+        self.tgcn1 = TGCNCheb_H(L[0], 1, g1, K, horizon, time_dft=time_dft, **layer_kw)
+        self.drop1 = nn.Dropout(drop1)
         self.gcn2 = GCNCheb(L[2], g1, g2, K, **layer_kw)
         n2 = L[2].shape[0]
         self.fc1 = nn.Linear(int(n2 * g2 / 4), hidden)
         self.dense1_bn = nn.BatchNorm1d(hidden)
+        self.drop2 = nn.Dropout(drop2)
         self.fc2 = nn.Linear(hidden, n_classes)
         self.fused = fused_relu_pool
         self.fused_head = fused_head
+        self.time_dft = time_dft
+        self.fc1_update = None
+        self._head_step = None
+        self._head_ctr = None
+
+    def set_dropout_step(self, step):
+        """step: device int32/uint32 tensor advanced once per training step (e.g. PeerAllreduceSGD.state)."""
+        self.tgcn1.dropout_step = step
+        self._head_step = step
+
+    def _head_drop(self, device):
+        p = self.drop2.p if self.training else 0.0
+        if not p:
+            return None
+        step = self._head_step
+        if step is None:
+            if self._head_ctr is None or self._head_ctr.device != device:
+                self._head_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+            self._head_ctr.add_(1)
+            step = self._head_ctr
+        return (float(p), (torch.initial_seed() * 0x9E3779B1 + 0x5bd1e995) & 0xFFFFFFFF, step)
 
     def forward(self, x):
+        p1 = self.drop1.p if self.training else 0.0
         if self.fused:
-            x = self.gcn2.forward_relu_pool(self.tgcn1.forward_relu_pool(x, 4), 4)
+            x = self.gcn2.forward_relu_pool(self.tgcn1.forward_relu_pool(x, 4, dropout=p1), 4)
         else:
-            x = gcn_pool_4(F.relu(self.tgcn1(x)))
+            x = gcn_pool_4(self.drop1(F.relu(self.tgcn1(x))))
             x = gcn_pool_4(F.relu(self.gcn2(x)))
         x = x.reshape(x.shape[0], -1)
-        # the fused head is a latency optimisation for small dense tails (parcellation-sized graphs); a large fc1
-        # (cortical mesh: 167 424 x 200) is a bandwidth-bound GEMM and stays with cuBLAS
-        small = self.fc1.in_features * self.fc1.out_features <= (1 << 21)
-        # (its backward covers training-mode batch statistics; evaluation mode is fused for inference only)
-        usable = (self.training and x.shape[0] > 1) or (not self.training and not torch.is_grad_enabled())
-        if self.fused_head and small and x.is_cuda and usable:
-            from .nn.head import fused_head
-            return fused_head(x, self.fc1, self.dense1_bn, self.fc2)
-        x = F.relu(self.dense1_bn(self.fc1(x)))
+        if self.fused_head and x.is_cuda:
+            from .nn.head import fused_head, head_covers
+            if head_covers(x.shape[0], self.fc1.in_features, self.fc1.out_features, self.training, torch.is_grad_enabled()):
+                upd = self.fc1_update if (self.training and torch.is_grad_enabled()) else None
+                return fused_head(x, self.fc1, self.dense1_bn, self.fc2, drop=self._head_drop(x.device), fc1_update=upd)
+        if self.fc1_update is not None and self.training:
+            raise RuntimeError("fc1_update is set but the fused head does not cover this batch / mode")
+        x = self.drop2(F.relu(self.dense1_bn(self.fc1(x))))
         return F.log_softmax(self.fc2(x), dim=1)
 
 
