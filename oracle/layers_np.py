@@ -93,9 +93,9 @@ def layer_forward(L, x, W, b=None, kind="tgcn_h", recursion="reference"):
     K = W.shape[0]
     Xt = cheb_basis(L, x, K, recursion)
     if kind == "tgcn_h":
-        out = np.einsum("kqnhf,khfg->qng", Xt, W)               # gcn.py:113
+        out = np.einsum("kqnhf,khfg->qng", Xt, W, optimize=True)   # gcn.py:113 (optimize: BLAS contraction, same sum)
     else:
-        out = np.einsum("kqnf,kfg->qng", Xt, W)                 # gcn.py:39,194
+        out = np.einsum("kqnf,kfg->qng", Xt, W, optimize=True)     # gcn.py:39,194
     if b is not None:
         out = out + np.asarray(b, dtype=F64)                     # gcn.py:115-116
     return out
@@ -112,11 +112,11 @@ def layer_backward(L, x, W, dout, bias_shape=None, kind="tgcn_h", recursion="ref
     K = W.shape[0]
     Xt = cheb_basis(L, xin, K, recursion)
     if kind == "tgcn_h":
-        dW = np.einsum("kqnhf,qng->khfg", Xt, dout)
-        dXt = np.einsum("qng,khfg->kqnhf", dout, W)
+        dW = np.einsum("kqnhf,qng->khfg", Xt, dout, optimize=True)
+        dXt = np.einsum("qng,khfg->kqnhf", dout, W, optimize=True) if need_dx else None
     else:
-        dW = np.einsum("kqnf,qng->kfg", Xt, dout)
-        dXt = np.einsum("qng,kfg->kqnf", dout, W)
+        dW = np.einsum("kqnf,qng->kfg", Xt, dout, optimize=True)
+        dXt = np.einsum("qng,kfg->kqnf", dout, W, optimize=True) if need_dx else None
     db = None
     if bias_shape is not None:
         if tuple(bias_shape)[1] == 1:

@@ -24,13 +24,13 @@ def check_dp(rank, world, dev):
     graphs, perm, Ls, n_real = wl.hcp_parcellation()
     Lt = wl.as_torch_operands(Ls, device=dev)
     torch.manual_seed(10 + rank)
-    model = wl.NetTGCN_HCP(Lt, horizon=15).to(dev)
+    model = wl.NetTGCN_HCP(Lt, horizon=15, drop1=0.0, drop2=0.0).to(dev)
     broadcast_parameters(model)
     model.eval()
     Q = 16 * world
     x = wl.synthetic_signals(Q, Ls[0].shape[0], 15, n_real, perm, seed=3).to(dev)
     y = torch.randint(0, 6, (Q,), generator=torch.Generator().manual_seed(4)).to(dev)
-    ref = wl.NetTGCN_HCP(Lt, horizon=15).to(dev)
+    ref = wl.NetTGCN_HCP(Lt, horizon=15, drop1=0.0, drop2=0.0).to(dev)
     ref.load_state_dict(model.state_dict()); ref.eval()
     F.nll_loss(ref(x), y).backward()
     ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])

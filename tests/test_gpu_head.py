@@ -62,8 +62,8 @@ def test_model_with_fused_head_matches_unfused():
     graphs, perm, Ls, n_real = wl.hcp_parcellation()
     Lt = wl.as_torch_operands(Ls, device="cuda")
     torch.manual_seed(0)
-    ma = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=True).cuda()
-    mb = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=False).cuda()
+    ma = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=True, drop1=0.0, drop2=0.0).cuda()
+    mb = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=False, drop1=0.0, drop2=0.0).cuda()
     mb.load_state_dict(ma.state_dict())
     x = wl.synthetic_signals(16, Ls[0].shape[0], 15, n_real, perm, seed=2).cuda()
     y = torch.randint(0, 6, (16,), device="cuda")

@@ -1,0 +1,301 @@
+"""Whole-model parity and the round-2 fusions on the GPU:
+
+  * `NetTGCN_HCP` (fused ReLU + pool epilogues, fused head, own SGD launch, the whole step replayed from a CUDA graph)
+    trains next to the CPU port of the reference model (oracle/model_torch.py, pytorch_hcp_tgcn.py:93-169) from the
+    same state_dict: per-step loss and every parameter after 5 SGD steps within 1e-4;
+  * the same on a mesh-sized model whose fc1 takes the large-head path with the optimizer step of fc1.weight fused
+    into the backward (csrc/bighead.cu);
+  * fused dropout (pool kernel, resident epilogue, head): masks are Bernoulli(1-p), kept values are scaled by
+    1/(1-p), the pooled result equals the unfused chain under the same mask, gradients flow through kept elements only.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _train_both(model, port, xs, ys, steps, lr=0.01, momentum=0.5, fc1_fused=False, graph=True):
+    """Run `steps` SGD steps on both models; returns (losses_gpu, losses_cpu)."""
+    from tgcn_b200.nn.head import Fc1FusedSGD
+    from tgcn_b200.parallel import PeerAllreduceSGD
+    params = list(model.parameters())
+    if fc1_fused:
+        model.fc1_update = Fc1FusedSGD(model.fc1.weight, lr=lr, momentum=momentum)
+        params = [p for p in params if p is not model.fc1.weight]
+    opt = PeerAllreduceSGD(params, lr=lr, momentum=momentum)                  # world 1: one fused update launch
+    opt_cpu = torch.optim.SGD(port.parameters(), lr=lr, momentum=momentum)
+    model.train(); port.train()
+    xd = xs[0].cuda().clone()
+    yd = ys[0].cuda().clone()
+    loss_dev = torch.zeros((), device="cuda")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = F.nll_loss(model(xd), yd)
+        loss.backward()
+        loss_dev.copy_(loss.detach())
+        opt.step()
+
+    g = None
+    lg, lc = [], []
+    for i in range(steps):
+        xd.copy_(xs[i]); yd.copy_(ys[i])
+        if graph and i == 1:                     # step 0 eager (allocator warm-up), then capture once and replay
+            s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            # capture does not execute: snapshot and restore nothing, just record
+            with torch.cuda.graph(g):
+                step()
+        if g is not None:
+            g.replay()
+        else:
+            step()
+        lg.append(float(loss_dev))
+        opt_cpu.zero_grad()
+        lossc = F.nll_loss(port(xs[i]), ys[i])
+        lossc.backward()
+        opt_cpu.step()
+        lc.append(float(lossc))
+    return lg, lc
+
+
+def _compare(model, port, lg, lc):
+    for a, b in zip(lg, lc):
+        assert abs(a - b) <= TOL * max(1.0, abs(b)), (lg, lc)
+    sd = port.state_dict()
+    for name, p in model.state_dict().items():
+        if name.endswith("num_batches_tracked"):
+            assert int(p) == int(sd[name])
+            continue
+        assert rel_err(p.detach().cpu().numpy(), sd[name].numpy()) < TOL, name
+
+
+def test_hcp360_model_trains_like_the_reference_port():
+    from oracle import model_torch
+    from tgcn_b200 import workloads as wl
+    graphs, perm, Ls, n_real = wl.hcp_parcellation()
+    torch.manual_seed(0)
+    model = wl.NetTGCN_HCP(wl.as_torch_operands(Ls, device="cuda"), horizon=15, drop1=0.0, drop2=0.0).cuda()
+    port = model_torch.PortNetTGCN_HCP(wl.as_torch_operands(Ls, dense=True), horizon=15, drop1=0.0, drop2=0.0)
+    port.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    steps, Q = 5, 64
+    xs = [wl.synthetic_signals(Q, Ls[0].shape[0], 15, n_real, perm, seed=10 + i) for i in range(steps)]
+    gy = torch.Generator().manual_seed(3)
+    ys = [torch.randint(0, 6, (Q,), generator=gy) for _ in range(steps)]
+    lg, lc = _train_both(model, port, xs, ys, steps)
+    _compare(model, port, lg, lc)
+
+
+def test_mesh_model_with_large_head_and_fused_fc1_update_trains_like_the_port():
+    """A 9 000-vertex spherical mesh (same generator as configs[2]): N0 ~ 11.6k, fc1 = 11.6k x 200 weights > 2^21, so the
+    head runs csrc/bighead.cu and fc1.weight is updated inside the backward; the conv layers take the streaming path."""
+    from oracle import model_torch
+    from tgcn_b200 import workloads as wl
+    graphs, perm, Ls, n_real = wl.cortical_mesh(n_real=9000)
+    H, Q, steps = 30, 8, 5
+    torch.manual_seed(1)
+    model = wl.NetTGCN_HCP(wl.as_torch_operands(Ls, device="cuda"), horizon=H, drop1=0.0, drop2=0.0).cuda()
+    assert model.fc1.in_features * model.fc1.out_features > (1 << 21)
+    Lcpu = [t.to_sparse_csr() for t in wl.as_torch_operands(Ls)]
+    port = model_torch.PortNetTGCN_HCP(Lcpu, horizon=H, drop1=0.0, drop2=0.0)
+    port.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    xs = [wl.synthetic_signals(Q, Ls[0].shape[0], H, n_real, perm, seed=20 + i) for i in range(steps)]
+    gy = torch.Generator().manual_seed(4)
+    ys = [torch.randint(0, 6, (Q,), generator=gy) for _ in range(steps)]
+    lg, lc = _train_both(model, port, xs, ys, steps, fc1_fused=True)
+    assert model.fc1.weight.grad is None                   # the gradient never existed
+    _compare(model, port, lg, lc)
+
+
+@pytest.mark.parametrize("shape", [(8, 167424 // 8, 200, 6), (5, 12000, 200, 6), (8, 10240, 256, 10)])
+def test_large_head_matches_torch(shape):
+    """csrc/bighead.cu (fc1 weight streamed once; dW1 = dh^T x on the fly) against the torch modules."""
+    import torch.nn as nn
+    from tgcn_b200.nn.head import fused_head
+    Q, I, Hd, C = shape
+    torch.manual_seed(0)
+    mods = [nn.Linear(I, Hd), nn.BatchNorm1d(Hd), nn.Linear(Hd, C)]
+    with torch.no_grad():
+        mods[1].weight.uniform_(0.5, 1.5); mods[1].bias.uniform_(-0.3, 0.3)
+    a = [m.cuda() for m in mods]
+    import copy
+    b = [copy.deepcopy(m) for m in a]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(Q, I, device="cuda", generator=g)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = torch.randint(0, C, (Q,), device="cuda", generator=g)
+    for m in a + b:
+        m.train()
+    la = fused_head(xa, *a)
+    lb = F.log_softmax(b[2](F.relu(b[1](b[0](xb.double().float())))), dim=1)
+    assert rel_err(la.detach().cpu().numpy(), lb.detach().cpu().numpy()) < 1e-5
+    F.nll_loss(la, y).backward()
+    F.nll_loss(lb, y).backward()
+    assert rel_err(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < TOL
+    for ma, mb in zip(a, b):
+        for (na, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if ma is a[0] and na == "bias":
+                assert float(pa.grad.abs().max()) < 1e-5 and float(pb.grad.abs().max()) < 1e-5
+                continue
+            assert rel_err(pa.grad.cpu().numpy(), pb.grad.cpu().numpy()) < TOL, na
+
+
+def test_fused_fc1_update_follows_torch_sgd():
+    """Fc1FusedSGD (update inside the backward) == torch.optim.SGD(momentum) on the same head, 4 steps."""
+    import copy
+    import torch.nn as nn
+    from tgcn_b200.nn.head import Fc1FusedSGD, fused_head
+    Q, I, Hd, C = 8, 16384, 200, 6
+    torch.manual_seed(2)
+    a = [nn.Linear(I, Hd).cuda(), nn.BatchNorm1d(Hd).cuda(), nn.Linear(Hd, C).cuda()]
+    b = [copy.deepcopy(m) for m in a]
+    upd = Fc1FusedSGD(a[0].weight, lr=0.05, momentum=0.5)
+    rest = [p for m in a for p in m.parameters() if p is not a[0].weight]
+    oa = torch.optim.SGD(rest, lr=0.05, momentum=0.5)
+    ob = torch.optim.SGD([p for m in b for p in m.parameters()], lr=0.05, momentum=0.5)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(4):
+        x = torch.randn(Q, I, device="cuda", generator=g)
+        y = torch.randint(0, C, (Q,), device="cuda", generator=g)
+        oa.zero_grad(); ob.zero_grad()
+        F.nll_loss(fused_head(x, *a, fc1_update=upd), y).backward()
+        F.nll_loss(F.log_softmax(b[2](F.relu(b[1](b[0](x)))), dim=1), y).backward()
+        oa.step(); ob.step()
+        assert a[0].weight.grad is None
+        for ma, mb in zip(a, b):
+            for (na, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                assert rel_err(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()) < 1e-5, (it, na)
+
+
+# ---- fused dropout -----------------------------------------------------------------------------------------------
+def _scale32(p):
+    """1 / (1 - p) exactly as the kernels form it (fp32 arithmetic, common.cuh drop_resolve)."""
+    return float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+
+
+def _layer(engine):
+    from tgcn_b200 import workloads as wl
+    from tgcn_b200.nn import gcn as G
+    graphs, perm, Ls, n_real = wl.hcp_parcellation(n_real=200, knn=8)
+    torch.manual_seed(0)
+    lay = G.TGCNCheb_H(Ls[0], 1, 16, 5, 6, engine=engine).cuda()
+    x = torch.randn(12, Ls[0].shape[0], 6, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    return lay, x
+
+
+@pytest.mark.parametrize("engine", ["resident", "ffma"])
+def test_fused_dropout_between_relu_and_pool(engine):
+    from tgcn_b200.nn import gcn as G
+    p = 0.3
+    lay, x = _layer(engine)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lay.dropout_step = step
+    z = torch.relu(lay(x)).detach()                                   # un-dropped activation [Q, N, G]
+    xg = x.clone().requires_grad_(True)
+    y = lay.forward_relu_pool(xg, 4, dropout=p)
+    Q, N, Gc = z.shape
+    zs = (z * _scale32(p)).reshape(Q, N // 4, 4, Gc)
+    # every pooled value is 0 or one of its (scaled) siblings
+    hit = (y.detach().unsqueeze(2) == zs) | (y.detach().unsqueeze(2) == 0)
+    assert bool(hit.any(dim=2).all())
+    # the same mask through the stand-alone pool kernel (same seed, same step, same element indices): bit-identical
+    spec = lay._drop_spec(p, x.device)
+    y2 = G.relu_pool(lay(x), 4, drop=spec)
+    assert torch.equal(y.detach(), y2.detach())
+    # keep rate: a pooled value of 0 where all four siblings are positive means all four were dropped (p^4)
+    allpos = (zs > 0).all(dim=2)
+    dropped_all = ((y.detach() == 0) & allpos).float().sum() / allpos.float().sum().clamp(min=1)
+    assert abs(float(dropped_all) - p ** 4) < 0.01
+    # per-element keep rate from groups with exactly one positive sibling
+    onepos = (zs > 0).sum(dim=2) == 1
+    kept = ((y.detach() > 0) & onepos).float().sum() / onepos.float().sum().clamp(min=1)
+    assert abs(float(kept) - (1 - p)) < 0.02
+    # gradient: dx only through kept elements -- compare with autograd over the unfused chain under the SAME mask
+    dy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    y.backward(dy)
+    xr = x.clone().requires_grad_(True)
+    lay.zero_grad()
+    y3 = G.relu_pool(lay(xr), 4, drop=spec)      # the stand-alone pool kernel under the same mask, through autograd
+    y3.backward(dy)
+    assert rel_err(xg.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-5
+    # a new step draws a new mask; the same step reproduces it
+    y_same = lay.forward_relu_pool(x, 4, dropout=p)
+    assert torch.equal(y_same, y.detach())
+    step.add_(1)
+    y_new = lay.forward_relu_pool(x, 4, dropout=p)
+    assert not torch.equal(y_new, y.detach())
+    # evaluation semantics: dropout 0 is the plain fused chain
+    assert torch.equal(lay.forward_relu_pool(x, 4, dropout=0.0), G.relu_pool(lay(x), 4))
+
+
+def test_pool_dropout_gradient_routing():
+    """relu -> dropout -> max-pool in one kernel: values are 0 or a scaled sibling, the gradient reaches exactly the
+    selected sibling of groups whose pooled value is positive, scaled by 1/(1-p)."""
+    from tgcn_b200.nn import gcn as G
+    p = 0.4
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(6, 64, 8, device="cuda", generator=g)
+    step = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    spec = (p, 1234, step)
+    xa = x.clone().requires_grad_(True)
+    y = G.relu_pool(xa, 4, drop=spec)
+    scale = _scale32(p)
+    z = torch.relu(x).reshape(6, 16, 4, 8) * scale
+    yv = y.detach()
+    assert bool(((yv.unsqueeze(2) == z) | (yv.unsqueeze(2) == 0)).any(dim=2).all())
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy)
+    dx = xa.grad.reshape(6, 16, 4, 8)
+    nz = (dx != 0).sum(dim=2)
+    assert bool((nz <= 1).all())
+    assert bool(((nz == 1) == ((yv > 0) & (dy != 0))).all())
+    assert torch.equal(dx.sum(dim=2), torch.where(yv > 0, dy * scale, torch.zeros_like(dy)))
+    sel = dx != 0                                    # the receiving sibling is the one the pooled value came from
+    assert bool((z[sel] == yv.unsqueeze(2).expand_as(z)[sel]).all())
+
+
+def test_head_dropout_matches_torch_under_the_same_mask():
+    """drop2 (pytorch_hcp_tgcn.py:150) fused behind BN + ReLU: read the mask back through an identity fc2, then the
+    log-probabilities and every gradient must equal torch's with that mask applied explicitly."""
+    import copy
+    import torch.nn as nn
+    from tgcn_b200.nn.head import fused_head
+    Q, I, Hd, p = 64, 512, 32, 0.5
+    torch.manual_seed(4)
+    a = [nn.Linear(I, Hd).cuda(), nn.BatchNorm1d(Hd).cuda(), nn.Linear(Hd, Hd).cuda()]
+    with torch.no_grad():
+        a[2].weight.copy_(torch.eye(Hd)); a[2].bias.zero_()
+    b = [copy.deepcopy(m) for m in a]
+    for m in a + b:
+        m.train()
+    x = torch.randn(Q, I, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    lp = fused_head(xa, *a, drop=(p, 7, step))
+    # identity fc2: logits = post-dropout activation >= 0 with (almost surely) a zero in every row -> act = lp - min(lp)
+    act = lp.detach() - lp.detach().min(dim=1, keepdim=True).values
+    pre = torch.relu(b[1](b[0](xb)))
+    mask = (act > 0).float()
+    assert bool(((pre.detach() > 0) | (mask == 0)).all())                 # only positive activations can be "kept"
+    frac = float(mask.sum() / (pre.detach() > 0).float().sum())
+    assert abs(frac - (1 - p)) < 0.06
+    lb = F.log_softmax(b[2](pre * mask * _scale32(p)), dim=1)
+    assert rel_err(lp.detach().cpu().numpy(), lb.detach().cpu().numpy()) < 1e-5
+    y = torch.randint(0, Hd, (Q,), device="cuda")
+    F.nll_loss(lp, y).backward()
+    F.nll_loss(lb, y).backward()
+    assert rel_err(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < TOL
+    assert rel_err(a[0].weight.grad.cpu().numpy(), b[0].weight.grad.cpu().numpy()) < TOL
+    assert rel_err(a[2].weight.grad.cpu().numpy(), b[2].weight.grad.cpu().numpy()) < TOL
+    # evaluation mode: no dropout
+    for m in a + b:
+        m.eval()
+    with torch.no_grad():
+        assert rel_err(fused_head(x, *a, drop=(p, 7, step)).cpu().numpy(),
+                       F.log_softmax(b[2](torch.relu(b[1](b[0](x)))), dim=1).cpu().numpy()) < 1e-5

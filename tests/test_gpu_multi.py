@@ -31,7 +31,7 @@ def test_layers_under_torch_dataparallel():
     graphs, perm, Ls, n_real = wl.hcp_parcellation()
     Lt = wl.as_torch_operands(Ls, device="cuda:0")
     torch.manual_seed(0)
-    model = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=False).to("cuda:0")
+    model = wl.NetTGCN_HCP(Lt, horizon=15, fused_head=False, drop1=0.0, drop2=0.0).to("cuda:0")
     model.eval()
     x = wl.synthetic_signals(8, Ls[0].shape[0], 15, n_real, perm, seed=1).to("cuda:0")
     ref = model(x)

@@ -44,7 +44,7 @@ def _dp_worker(rank, world):
     r = load_golden("graph_grid28_k8_seed0.npz")        # 992 / 496 / 248 vertices: divisible by the two pool4
     Ls = [torch.tensor(np.asarray(csr_from(r, "L_%d" % i).todense()), dtype=torch.float) for i in range(3)]
     torch.manual_seed(100 + rank)                       # deliberately different init per rank
-    model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3, drop1=0.0, drop2=0.0)
     broadcast_parameters(model, src=0)
     gen = torch.Generator().manual_seed(7)
     Q = 8
@@ -52,7 +52,7 @@ def _dp_worker(rank, world):
     y = torch.randint(0, 3, (Q,), generator=gen)
     model.eval()                                        # BN in eval mode: batch statistics are not sharded
     # single-process result on the full batch (every rank computes it for reference)
-    ref_model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    ref_model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3, drop1=0.0, drop2=0.0)
     ref_model.load_state_dict(model.state_dict()); ref_model.eval()
     F.nll_loss(ref_model(x), y).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in ref_model.parameters()])
@@ -82,14 +82,14 @@ def _bucket_worker(rank, world):
     r = load_golden("graph_grid28_k8_seed0.npz")
     Ls = [torch.tensor(np.asarray(csr_from(r, "L_%d" % i).todense()), dtype=torch.float) for i in range(3)]
     torch.manual_seed(5 + rank)
-    model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3, drop1=0.0, drop2=0.0)
     broadcast_parameters(model, src=0)
     model.eval()
     gen = torch.Generator().manual_seed(3)
     Q = 6
     x = torch.randn(Q, Ls[0].shape[0], 5, generator=gen)
     y = torch.randint(0, 3, (Q,), generator=gen)
-    ref_model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3)
+    ref_model = model_torch.PortNetTGCN_HCP(Ls, horizon=5, K=4, g1=6, g2=8, hidden=10, n_classes=3, drop1=0.0, drop2=0.0)
     ref_model.load_state_dict(model.state_dict()); ref_model.eval()
     F.nll_loss(ref_model(x), y).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in ref_model.parameters()])
