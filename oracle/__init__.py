@@ -17,8 +17,11 @@ root = cassianobecker/tgcn):
                   laplacian, rescale_L).
 * ``coarsening_np`` restatement of ``gcn/coarsening.py`` (metis, compute_perm,
                   perm_adjacency, coarsen, perm_data).
-* ``csrc/oracle_cheb.c`` plain-C restatement of the CSR recursion + contraction
-                  (built by ``oracle/Makefile`` into ``oracle/_build/``).
+* ``model_torch`` the reference's model compositions (pytorch_hcp_tgcn.py:93-155,
+                  pytorch_mnist_tgcn.py:67-92) over ``layers_torch``.
+
+Everything is Python (numpy / scipy / torch-CPU), like the reference itself: there is
+no C restatement and nothing to build.
 
 Parity pinning: the reference has exactly one known-answer test on this path
 (``gcn/coarsening.py:216-217``, the ``compute_perm`` KAT) -- checked in

@@ -6,9 +6,8 @@ producers); everything is seeded.  The models mirror the reference's experiment 
   * `NetTGCN_HCP`   examples/pytorch_based/pytorch_hcp_tgcn.py:93-155
   * `NetTGCN_MNIST` examples/pytorch_based/pytorch_mnist_tgcn.py:67-92 (+ tgcn_mnist.py hyper-parameters)
 
-The conv layers and pooling are tgcn_b200's CUDA path; the dense classifier head
-(Linear/BatchNorm/log_softmax) is plain torch -- SURVEY.md section 8f ranks it "next", outside
-the hot path.
+The conv layers, pooling, dropouts and the dense classifier head all run in tgcn_b200's CUDA kernels
+(nn/gcn.py, nn/head.py); plain torch modules own the head's parameters.
 """
 import math
 
@@ -18,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import coarsening, graph
+from . import coarsening, graph, synth
 from .nn.gcn import GCNCheb, TGCNCheb_H, gcn_pool, gcn_pool_4, relu_pool
 
 
@@ -41,91 +40,22 @@ def mnist_grid(k=8, levels=4, seed=0):
 
 
 def hcp_parcellation(n_real=360, knn=16, levels=4, seed=0, dense=False):
-    """Config 2: HCP-shaped parcellation connectome, lognormal symmetric weights; sparse variant
-    keeps the top-`knn` entries per row and symmetrises by max."""
-    rng = np.random.default_rng(seed)
-    M = rng.lognormal(0.0, 1.0, size=(n_real, n_real)).astype(np.float32)
-    M = np.maximum(M, M.T)
-    np.fill_diagonal(M, 0.0)
-    if not dense:
-        thresh = np.sort(M, axis=1)[:, -knn][:, None]
-        M = np.where(M >= thresh, M, 0.0).astype(np.float32)
-        M = np.maximum(M, M.T)
-    A = sp.csr_matrix(M)
-    return _coarsened_laplacians(A, levels, seed) + (n_real,)
-
-
-def fibonacci_sphere(n):
-    i = np.arange(n, dtype=np.float64) + 0.5
-    phi = np.arccos(1.0 - 2.0 * i / n)
-    theta = math.pi * (1.0 + 5.0 ** 0.5) * i
-    return np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+    """Config 2: HCP-shaped parcellation connectome (synth.hcp_adjacency), coarsened."""
+    return _coarsened_laplacians(synth.hcp_adjacency(n_real, knn, seed, dense), levels, seed) + (n_real,)
 
 
 def cortical_mesh(n_real=32492, levels=4, seed=0):
-    """Config 3: closed genus-0 triangulated surface with the fsLR-32k vertex count
-    (load/data_hcp.py:86), unit edge weights from the faces (load/create_hcp.py:330-361,459-460)."""
-    from scipy.spatial import ConvexHull
-    pts = fibonacci_sphere(n_real)
-    faces = ConvexHull(pts).simplices
-    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], axis=0)
-    e = np.concatenate([e, e[:, ::-1]], axis=0)
-    A = sp.coo_matrix((np.ones(e.shape[0], np.float32), (e[:, 0], e[:, 1])), shape=(n_real, n_real)).tocsr()
-    A.data[:] = 1.0                                            # duplicate edges collapse to weight 1
-    return _coarsened_laplacians(A, levels, seed) + (n_real,)
-
-
-def _morton2(ix, iy):
-    """Interleave the bits of two uint32 arrays (Z-order code)."""
-    def spread(v):
-        v = v.astype(np.uint64) & np.uint64(0xFFFFFFFF)
-        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
-        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
-        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
-        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
-        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
-        return v
-    return spread(ix) | (spread(iy) << np.uint64(1))
+    """Config 3: closed genus-0 triangulated surface with the fsLR-32k vertex count (synth.mesh_adjacency), coarsened."""
+    return _coarsened_laplacians(synth.mesh_adjacency(n_real), levels, seed) + (n_real,)
 
 
 def random_geometric(n=1_000_000, mean_degree=12.0, seed=0, order="strip-morton", strips=8):
-    """Config 4: points uniform in the unit square, edges within r = sqrt(mean_degree / (pi n)), Gaussian weights;
-    no coarsening.  Returns L~ (CSR) and the points in vertex order.
-
-    Vertex order ("sorted by x (strip partition) or Morton order"): `strips` vertical strips of equal
-    population in x order -- so a contiguous row partition over <= `strips` ranks is a strip partition with thin
-    halos -- and Z-order (Morton) inside each strip, so that consecutive rows are spatial neighbours and share most
-    of their gathered rows.  order="x" keeps the plain x sort."""
-    from scipy.spatial import cKDTree
-    rng = np.random.default_rng(seed)
-    pts = rng.random((n, 2))
-    pts = pts[np.argsort(pts[:, 0], kind="stable")]
-    if order == "strip-morton":
-        strip = (np.arange(n) * strips) // n                      # equal-population strips of the x-sorted points
-        code = _morton2((pts[:, 0] * 65535).astype(np.uint32), (pts[:, 1] * 65535).astype(np.uint32))
-        pts = pts[np.lexsort((code, strip))]
-    elif order != "x":
-        raise ValueError(order)
-    r = math.sqrt(mean_degree / (math.pi * n))
-    pairs = cKDTree(pts).query_pairs(r, output_type='ndarray')
-    d = np.linalg.norm(pts[pairs[:, 0]] - pts[pairs[:, 1]], axis=1)
-    w = np.exp(-(d / (0.5 * r)) ** 2).astype(np.float32)
-    rows = np.concatenate([pairs[:, 0], pairs[:, 1]])
-    cols = np.concatenate([pairs[:, 1], pairs[:, 0]])
-    A = sp.coo_matrix((np.concatenate([w, w]), (rows, cols)), shape=(n, n)).tocsr()
+    """Config 4: random geometric graph (synth.rgg_adjacency); returns L~ (CSR) and the points in vertex order."""
+    A, pts = synth.rgg_adjacency(n, mean_degree, seed, order, strips)
     return graph.rescaled_laplacian_csr(A), pts
 
 
-def synthetic_signals(Q, N0, H, n_real, perm, seed, F_in=None):
-    """x[Q, N0, H(,F)] ~ N(0,1) on real vertices, exact zeros on the fake vertices the coarsening
-    added (what perm_data_time produces)."""
-    g = torch.Generator().manual_seed(seed)
-    shape = (Q, N0, H) if F_in is None else (Q, N0, H, F_in)
-    x = torch.randn(shape, generator=g)
-    if perm is not None:
-        fake = torch.tensor(np.asarray(perm) >= n_real)
-        x[:, fake] = 0.0
-    return x
+synthetic_signals = synth.synthetic_signals
 
 
 # ------------------------------------------------------------------------------------------------
