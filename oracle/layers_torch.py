@@ -32,7 +32,7 @@ def _vertex_mix(L, X):
 
 def basis_stack(L, X, K, recursion="reference"):
     """gcn.py:126-154 (see oracle/layers_np.py for the reference-vs-textbook note)."""
-    stack = torch.empty((K,) + tuple(X.shape), dtype=torch.float32, device=X.device)
+    stack = torch.empty((K,) + tuple(X.shape), dtype=X.dtype, device=X.device)
     stack[0] = X
     run = X
     if K > 1:

@@ -18,6 +18,9 @@ SHAPES = [  # Q, N, D, G, K
     (2, 130, 40, 24, 3),      # D > 32: two k-blocks per order
     (1, 300, 192, 64, 2),     # config-4 family: D = 192
     (5, 33, 8, 136, 4),       # G > 128
+    (8, 5000, 32, 32, 10),    # TMA-fed kernel (contract_tc3.cu): resident weight images, 313 row tiles -> up to 3 per CTA
+    (4, 6000, 64, 48, 3),     # two 32-column blocks per order, G padded to 48, both TMEM accumulator buffers in use
+    (8, 2400, 32, 64, 10),    # layer-2 family at > 148 tiles: weight images streamed with their tile
 ]
 
 

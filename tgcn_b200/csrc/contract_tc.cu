@@ -587,6 +587,9 @@ int contract_fwd_tc2(const float* stack, const uint8_t* wimg, const float* bias,
 int contract_bwd_w_tc2(const float* stack, const float* dout, float* partial, int* P_out,
                        int Q, int N, int D, int G, int K, cudaStream_t st, int* launched);
 int bwd_w2_partials(int Q, int N, int D, int G, int K);
+// third-generation kernels (TMA tensor copies into the swizzled operand layout), contract_tc3.cu
+int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias, int bias_mode, float* out,
+                     int Q, int N, int D, int G, int GP, int K, cudaStream_t st, int* launched);
 
 static bool use_v2() {
     static const bool on = [] { const char* e = getenv("TGCN_TC_V1"); return !(e && e[0] == '1'); }();
@@ -690,6 +693,11 @@ int contract_fwd_tc(const float* stack, const float* Wmix, const float* bias, in
     FwdTcParams p{};
     p.stack = stack; p.S = (int64_t)N * Q * D; p.wimg = img; p.bias = bias; p.bias_mode = bias_mode; p.out = out;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GP = t.GP; p.K = K; p.KB = t.KB;
+    {
+        int launched = 0;
+        TGCN_PROPAGATE(contract_fwd_tc3(stack, img, bias, bias_mode, out, Q, N, D, G, t.GP, K, st, &launched));
+        if (launched) return TGCN_OK;
+    }
     if (use_v2()) {
         int launched = 0;
         TGCN_PROPAGATE(contract_fwd_tc2(stack, img, bias, bias_mode, out, Q, N, D, G, t.GP, K, st, &launched));

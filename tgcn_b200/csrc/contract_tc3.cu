@@ -1,0 +1,336 @@
+// Third-generation tensor-core contraction kernels: operand tiles arrive by 2-D/3-D TMA tensor copies
+// (cp.async.bulk.tensor, hardware SWIZZLE_128B) straight into the layout tcgen05.mma reads.
+//
+// What the second generation (contract_tc2.cu) left on the table (profiles/r01/time_tc_v2_mesh32k.txt: 1.9-2.2 TB/s
+// of the K-slab stream, tensor pipe 7 % active):
+//   * every 128 x D fp32 chunk went raw -> shared (bulk copy) -> registers -> TWO swizzled tiles (hi and lo): 5 bytes
+//     of shared-memory traffic per operand byte before the tensor core read anything, plus the weight image of the
+//     order copied shared -> shared once per unit;
+//   * the eight transform warps also ran the epilogue, so the MMA pipe drained at every tile boundary (one TMEM
+//     accumulator).
+// Here (requires slab rows padded to a multiple of 32 floats -- `Dp`, the layer pads D = 30 -> 32):
+//   warp 0      producer   one elected lane: a TMA tensor copy per (row tile, order, 32-column block) lands a
+//                          [128 x 32 fp32] tile in SWIZZLE_128B layout.  kind::tf32 reads the upper 19 bits of each
+//                          fp32, so this tile IS the "hi" operand -- no hi pass at all;
+//   warps 6-13  transform  lo = x - trunc_tf32(x), element-wise at the SAME swizzled offsets (LDS.128 -> 3 ALU ->
+//                          STS.128, conflict-free, no address arithmetic), then a proxy fence;
+//   warp 1      MMA        one lane issues the 3xTF32 products (lo*Wh, hi*Wl, hi*Wh) for the 4 k-steps of the tile
+//                          and commits the stage back to the producer; accumulators alternate between TWO TMEM
+//                          buffers, so the next row tile's MMAs start while the epilogue drains the previous one;
+//   warps 2-5   epilogue   tcgen05.ld (one TMEM lane quarter per warp), bias, stores.
+// The weight images (hi | lo, K-major SWIZZLE_128B, built once per call by prep_wimg_kernel) stay resident in shared
+// memory when they fit (cortical mesh layer 1: 80 KB), else they are streamed with their tile (1-D bulk copy, L2 hits).
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace tgcn {
+using namespace tc;
+
+constexpr int kT3Threads = 448;            // producer, MMA, 4 epilogue, 8 transform warps
+constexpr int kT3TransformWarp0 = 6;
+constexpr int kT3TransformWarps = 8;
+constexpr int kT3MaxStages = 6;
+constexpr uint32_t kT3Tile = 128 * 128;    // one [128 x 32 fp32] operand tile
+constexpr size_t kT3SmemLimit = 224 * 1024;
+
+// ---- TMA ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp32 tensor [d2][d1][d0] (d0 innermost, contiguous), box [b2][b1][b0], swizzle mode `sw`; out-of-range rows read as 0
+static int make_tmap3(CUtensorMap* out, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return set_error(TGCN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    const cuuint32_t box[3] = {b0, b1, b2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(TGCN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return TGCN_OK;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ uint8_t* align1024_3(uint8_t* p) {
+    const uint32_t a = smem_u32(p);
+    return p + (((a + 1023u) & ~1023u) - a);
+}
+
+// 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// lo part of a float4 of fp32 values under the tensor core's tf32 read (upper 19 bits): x - trunc(x), exact in fp32
+__device__ __forceinline__ float4 tf32_lo4(const float4& x) {
+    float4 r;
+    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward:  out[m, g] = sum_j sum_d P_j[m, d] W'_j[d, g] + bias
+// unit u = (order j, column block db) of a row tile: one [128 x 32] TMA tile of the stack
+// ------------------------------------------------------------------------------------------------
+struct Fwd3Params {
+    const uint8_t* wimg;           // per unit: [hi | lo] x [GP rows x 128 B], K-major SWIZZLE_128B image
+    const float* bias; int bias_mode;
+    float* out;
+    int M, Q, N, G, GP, K, DB;     // DB = Dp / 32 column blocks per order
+    int ntiles, NS, w_resident;
+    uint32_t wunit;                // bytes of one weight image: 2 * GP * 128
+};
+
+__global__ void __launch_bounds__(kT3Threads, 1)
+contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Params p) {
+    extern __shared__ uint8_t smem_raw3[];
+    uint8_t* smem = align1024_3(smem_raw3);
+    __shared__ __align__(8) uint64_t full[kT3MaxStages], lo_ready[kT3MaxStages], empty[kT3MaxStages], acc_full[2], acc_empty[2], w_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NS = p.NS, units = p.K * p.DB;
+    const uint32_t stage_bytes = 2 * kT3Tile + (p.w_resident ? 0u : p.wunit);
+    uint8_t* stage0 = smem;
+    uint8_t* wres = smem + (size_t)NS * stage_bytes;                  // resident weight images (w_resident)
+    const uint32_t ncols = tmem_cols_pow2(2u * (uint32_t)p.GP);
+
+    if (tid == 0) {
+        for (int i = 0; i < kT3MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&lo_ready[i], kT3TransformWarps); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(&w_full, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            if (p.w_resident) {
+                const uint32_t wtotal = (uint32_t)units * p.wunit;
+                mbar_arrive_expect_tx(&w_full, wtotal);
+                for (uint32_t off = 0; off < wtotal; off += 32768u)
+                    bulk_g2s(wres + off, p.wimg + off, min(32768u, wtotal - off), &w_full);
+            }
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int m0 = tile * 128;
+                for (int u = 0; u < units; ++u, ++g) {
+                    const uint32_t s = g % (uint32_t)NS;
+                    if (g >= (uint32_t)NS) mbar_wait(&empty[s], ((g / NS) - 1) & 1);
+                    uint8_t* st = stage0 + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], kT3Tile + (p.w_resident ? 0u : p.wunit));
+                    const int j = u / p.DB, db = u - j * p.DB;
+                    tma_load_3d(st, &tmA, db * 32, m0, j, &full[s]);
+                    if (!p.w_resident) bulk_g2s(st + 2 * kT3Tile, p.wimg + (size_t)u * p.wunit, p.wunit, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.GP, 0, 0);
+            if (p.w_resident) mbar_wait(&w_full, 0);
+            uint32_t g = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+                const uint32_t a = ti & 1u;
+                if (ti >= 2) mbar_wait(&acc_empty[a], ((ti >> 1) - 1) & 1);        // the epilogue drained this buffer
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + a * (uint32_t)p.GP;
+                for (int u = 0; u < units; ++u, ++g) {
+                    const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
+                    mbar_wait(&full[s], ph);
+                    mbar_wait(&lo_ready[s], ph);
+                    tcgen05_fence_after();
+                    uint8_t* st = stage0 + (size_t)s * stage_bytes;
+                    const uint8_t* wu = p.w_resident ? wres + (size_t)u * p.wunit : st + 2 * kT3Tile;
+                    const uint64_t dah = make_desc_kmajor(smem_u32(st)), dal = make_desc_kmajor(smem_u32(st + kT3Tile));
+                    const uint64_t dbh = make_desc_kmajor(smem_u32(wu)), dbl = make_desc_kmajor(smem_u32(wu + p.wunit / 2));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);                   // 32 bytes along K, in 16-byte units
+                        umma_tf32(acc, dal + adv, dbh + adv, idesc, (u | ks) ? 1u : 0u);
+                        umma_tf32(acc, dah + adv, dbl + adv, idesc, 1u);
+                        umma_tf32(acc, dah + adv, dbh + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[a]);
+            }
+        }
+    } else if (warp < kT3TransformWarp0) {
+        // ===================== epilogue (warp e owns TMEM lanes [32 e', 32 e' + 32), e' = warp % 4) =====================
+        const int lq = warp & 3;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+            const uint32_t a = ti & 1u;
+            mbar_wait(&acc_full[a], (ti >> 1) & 1);
+            tcgen05_fence_after();
+            const int m = tile * 128 + lq * 32 + lane;
+            const bool live = m < p.M;
+            int n = 0, q = 0;
+            if (live) { n = m / p.Q; q = m - n * p.Q; }
+            float* dst = p.out + ((int64_t)q * p.N + n) * p.G;
+            const bool vec = (p.G % 4 == 0) && aligned16(p.out);
+            for (int cb = 0; cb < p.GP; cb += 32) {
+                float v[32];
+                if (p.GP - cb >= 32) {
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * (uint32_t)p.GP + (uint32_t)cb, v);
+                } else {
+                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + a * (uint32_t)p.GP + (uint32_t)cb, v);
+                }
+                const int ncol = min(32, p.GP - cb);
+                if (!live) continue;
+                if (p.bias_mode == TGCN_BIAS_PER_VERTEX) {
+                    const float* b = p.bias + (int64_t)n * p.G + cb;
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            if (i < ncol && cb + i < p.G) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(b + i));
+                                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+                            }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) v[i] += __ldg(b + i);
+                    }
+                } else if (p.bias_mode == TGCN_BIAS_PER_FILTER) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) v[i] += __ldg(p.bias + cb + i);
+                }
+                if (vec) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        if (i < ncol && cb + i < p.G) *reinterpret_cast<float4*>(dst + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) dst[cb + i] = v[i];
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+    } else {
+        // ===================== transform: lo tile from the raw (= hi) tile =====================
+        const int t = tid - kT3TransformWarp0 * 32;                   // 0..255
+        const uint32_t base_u32 = smem_u32(stage0);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int u = 0; u < units; ++u, ++g) {
+                const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
+                mbar_wait(&full[s], ph);
+                const uint32_t src = base_u32 + s * stage_bytes + (uint32_t)t * 16u;
+                float4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                                 : "r"(src + (uint32_t)i * 4096u));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 l = tf32_lo4(x[i]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)i * 4096u), "f"(l.x), "f"(l.y),
+                                 "f"(l.z), "f"(l.w) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&lo_ready[s]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+template <typename Kern>
+static int set_smem3(Kern kern, size_t bytes, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu): %s", name, bytes, cudaGetErrorString(e));
+    return TGCN_OK;
+}
+
+static bool use_v3() {
+    static const bool on = [] { const char* e = getenv("TGCN_TC_V3"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// returns with *launched = 1 when the shape is covered (slab rows of D = 32 * DB floats, 16-byte aligned stack)
+int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias, int bias_mode, float* out,
+                     int Q, int N, int D, int G, int GP, int K, cudaStream_t st, int* launched) {
+    *launched = 0;
+    const int64_t M = (int64_t)Q * N;
+    if (!use_v3() || D % 32 != 0 || GP > 128 || GP % 16 != 0 || M <= 0 || M >= (int64_t)INT32_MAX - 256 ||
+        (reinterpret_cast<uintptr_t>(stack) & 15u) != 0)
+        return TGCN_OK;
+    Fwd3Params p{};
+    p.wimg = wimg; p.bias = bias; p.bias_mode = bias_mode; p.out = out;
+    p.M = (int)M; p.Q = Q; p.N = N; p.G = G; p.GP = GP; p.K = K; p.DB = D / 32;
+    p.ntiles = (int)ceil_div(M, 128);
+    p.wunit = 2u * (uint32_t)GP * kRowBytes;
+    const size_t wtotal = (size_t)K * p.DB * p.wunit;
+    const size_t fixed = 1024 + 256;
+    p.w_resident = (wtotal <= 96 * 1024) ? 1 : 0;
+    const size_t stage = 2 * (size_t)kT3Tile + (p.w_resident ? 0 : p.wunit);
+    int NS = (int)((kT3SmemLimit - fixed - (p.w_resident ? wtotal : 0)) / stage);
+    if (NS > kT3MaxStages) NS = kT3MaxStages;
+    if (const char* e = getenv("TGCN_T3_NS")) { const int v = atoi(e); if (v >= 2 && v <= NS) NS = v; }
+    if (NS < 2) return TGCN_OK;
+    p.NS = NS;
+    const size_t smem = fixed + (size_t)NS * stage + (p.w_resident ? wtotal : 0);
+    CUtensorMap tmA;
+    TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, 128, 1,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+    TGCN_PROPAGATE(set_smem3(contract_fwd_tc3_kernel, smem, "contract_fwd_tc3"));
+    const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
+    contract_fwd_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tmA, p);
+    TGCN_LAUNCH_CHECK("contract_fwd_tc3");
+    *launched = 1;
+    return TGCN_OK;
+}
+
+}  // namespace tgcn
