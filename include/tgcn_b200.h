@@ -188,21 +188,26 @@ int tgcn_pool_max_bwd(const float* dy, const uint8_t* idx, const float* x, const
                       int G, int p, int relu, const tgcn_dropout_t* drop, void* stream);
 
 /* ---- fused whole-layer entry points (one host call per layer direction) -------------------- */
-/* forward: basis + mix + contraction.  `stack` [K,N,Q*D] and `workspace`
- * (tgcn_layer_fwd_workspace bytes; its head is Wmix[K,D,G]) are caller-owned and re-used by the
+/* Slab width Dp >= D = H*F of the streaming kernels for this layer: D rounded up to a multiple of 32 when that
+ * costs <= 12.5 % more slab bytes and the tensor-core engine runs (its TMA-fed kernels read slab rows of whole
+ * 128-byte blocks; the cortical-mesh layer has D = 30), else D.  The padding columns hold zeros and never reach
+ * the caller: x, W, dW, dx keep the reference shapes. */
+int tgcn_layer_slab_width(int Q, int N, int D, int G, int K, int engine);
+/* forward: layout change (+ padding) + basis + mix + contraction.  `stack` [K,N,Q*Dp] and `workspace`
+ * (tgcn_layer_fwd_workspace(Q, N, Dp, G, K) bytes; its head is Wmix[K,Dp,G]) are caller-owned and re-used by the
  * backward. */
 int64_t tgcn_layer_fwd_workspace(int Q, int N, int D, int G, int K);
 int tgcn_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int N,
                    const float* x, const float* W, const float* bias, int bias_mode,
                    float* out, float* stack, void* workspace,
-                   int Q, int D, int G, int K, int recursion, int engine, void* stream);
-/* backward: dW (always), db (if bias_mode != NONE), dx (if dx != NULL; needs gstack [K,N,Q*D]).
- * `workspace` holds tgcn_layer_bwd_workspace(...) bytes. */
+                   int Q, int D, int Dp, int G, int K, int recursion, int engine, void* stream);
+/* backward: dW [K,D,G] (always), db (if bias_mode != NONE), dx [Q,N,D] (if dx != NULL; needs gstack [K,N,Q*Dp]).
+ * `workspace` holds tgcn_layer_bwd_workspace(Q, N, Dp, G, K) bytes. */
 int64_t tgcn_layer_bwd_workspace(int Q, int N, int D, int G, int K);
 int tgcn_layer_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N,
                    const float* dout, const float* stack, const float* Wmix,
                    float* dW, float* db, int bias_mode, float* dx, float* gstack, void* workspace,
-                   int Q, int D, int G, int K, int recursion, int engine, void* stream);
+                   int Q, int D, int Dp, int G, int K, int recursion, int engine, void* stream);
 
 /* ---- sample-resident fused layer (graphs whose per-sample slab [N,D] fits in shared memory) ---- */
 /* One CTA per sample runs the whole layer: recursion in shared memory, contraction accumulated in

@@ -50,9 +50,10 @@ SIGNATURES = {
     "tgcn_pool_max_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "tgcn_pool_max_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "tgcn_layer_fwd_workspace": (_l, [_i, _i, _i, _i, _i]),
-    "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_layer_slab_width": (_i, [_i, _i, _i, _i, _i, _i]),
+    "tgcn_layer_fwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_layer_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),
-    "tgcn_layer_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "tgcn_layer_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "tgcn_resident_supported": (_i, [_i, _i, _i, _i, _l]),
     "tgcn_resident_stack_bytes": (_l, [_i, _i, _i, _i]),
     "tgcn_resident_bwd_workspace": (_l, [_i, _i, _i, _i, _i]),

@@ -226,13 +226,21 @@ contract_bwd_w_kernel(const float* __restrict__ stack, const float* __restrict__
     }
 }
 
+// out[i] = sum_p partial[p][i] in a FIXED order: 8 lanes per element take the partials p = l, l + 8, ... (each a
+// sequential sum), then a 3-step butterfly -- the same tree for every launch, so the result is deterministic, and
+// the P dependent loads of the old one-thread-per-element version (19 us at P = 148) become P / 8.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int P, int64_t n) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = t >> 3;
+    const int l = (int)(t & 7);
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += __ldg(partial + (int64_t)p * n + i);
-    out[i] = s;
+    if (i < n)
+        for (int p = l; p < P; p += 8) s += __ldg(partial + (int64_t)p * n + i);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (i < n && l == 0) out[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,6 +263,32 @@ mix_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int K
         for (int j = a; j >= 0; j -= 2, sign = -sign) {
             const double c = j < 2 ? 1.0 : 2.0;
             s += sign * c * (double)__ldg(src + (int64_t)j * inner + e);
+        }
+    }
+    dst[i] = (float)s;
+}
+
+// The same mix between weight tensors whose per-order row counts differ: src [K][Ds][G] -> dst [K][Dd][G].  Forward
+// (Dd >= Ds): the mixed weights of a slab padded to Dd columns per sample, padding rows zero; backward (Dd <= Ds): the
+// gradient of the real rows, padding rows dropped.
+__global__ void __launch_bounds__(256)
+mix_weights_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int Ds, int Dd, int G, int transpose) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t inner_d = (int64_t)Dd * G, inner_s = (int64_t)Ds * G;
+    if (i >= (int64_t)K * inner_d) return;
+    const int a = (int)(i / inner_d);
+    const int64_t e = i - (int64_t)a * inner_d;
+    if (e >= inner_s) { dst[i] = 0.f; return; }        // padding row of the destination (rows are the slow index)
+    double s = 0.0;
+    if (!transpose) {
+        const double c = a < 2 ? 1.0 : 2.0;
+        double sign = 1.0;
+        for (int k = a; k < K; k += 2, sign = -sign) s += sign * c * (double)__ldg(src + (int64_t)k * inner_s + e);
+    } else {
+        double sign = 1.0;
+        for (int j = a; j >= 0; j -= 2, sign = -sign) {
+            const double c = j < 2 ? 1.0 : 2.0;
+            s += sign * c * (double)__ldg(src + (int64_t)j * inner_s + e);
         }
     }
     dst[i] = (float)s;
@@ -324,6 +358,25 @@ extern "C" int tgcn_mix_weights(const float* src, float* dst, int K, int64_t inn
 }
 
 namespace tgcn {
+// src [K][Ds][G] -> dst [K][Dd][G] with the recursion's mix (identity for the textbook recursion); see the kernel
+int mix_weights_rows(const float* src, float* dst, int K, int Ds, int Dd, int G, int recursion, int transpose, cudaStream_t st) {
+    if ((int64_t)K * Dd * G == 0) return TGCN_OK;
+    if (Ds == Dd) return tgcn_mix_weights(src, dst, K, (int64_t)Ds * G, recursion, transpose, st);
+    if (recursion == TGCN_RECURSION_CHEBYSHEV) {
+        const int rows = Ds < Dd ? Ds : Dd;
+        if (Dd > Ds) {
+            cudaError_t e0 = cudaMemsetAsync(dst, 0, sizeof(float) * K * Dd * G, st);
+            if (e0 != cudaSuccess) return set_error(TGCN_ERR_CUDA, "mix_weights: %s", cudaGetErrorString(e0));
+        }
+        cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(float) * Dd * G, src, sizeof(float) * Ds * G, sizeof(float) * rows * G, K,
+                                          cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "mix_weights: %s", cudaGetErrorString(e));
+        return TGCN_OK;
+    }
+    mix_weights_rows_kernel<<<(unsigned)ceil_div((int64_t)K * Dd * G, 256), 256, 0, st>>>(src, dst, K, Ds, Dd, G, transpose);
+    TGCN_LAUNCH_CHECK("mix_weights");
+    return TGCN_OK;
+}
 int tc_supported(int Q, int N, int D, int G, int K);
 int64_t tc_fwd_scratch_bytes(int Q, int N, int D, int G, int K);
 int64_t tc_bwd_scratch_bytes(int Q, int N, int D, int G, int K);
@@ -433,7 +486,7 @@ extern "C" int tgcn_contract_bwd_w(const float* stack, const float* dout, float*
         int P = 0;
         TGCN_PROPAGATE(contract_bwd_w_tc(stack, dout, partial, &P, Q, N, D, G, K, st));
         const int64_t n = (int64_t)JD * G;
-        reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, dWmix, P, n);
+        reduce_partials_kernel<<<(unsigned)ceil_div(n * 8, 256), 256, 0, st>>>(partial, dWmix, P, n);
         TGCN_LAUNCH_CHECK("reduce_partials");
         return TGCN_OK;
     }
@@ -443,7 +496,7 @@ extern "C" int tgcn_contract_bwd_w(const float* stack, const float* dout, float*
                                                       (int64_t)N * Q * D);
     TGCN_LAUNCH_CHECK("contract_bwd_w");
     const int64_t n = (int64_t)JD * G;
-    reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const float*)workspace, dWmix, P, n);
+    reduce_partials_kernel<<<(unsigned)ceil_div(n * 8, 256), 256, 0, st>>>((const float*)workspace, dWmix, P, n);
     TGCN_LAUNCH_CHECK("reduce_partials");
     return TGCN_OK;
 }
@@ -472,7 +525,7 @@ extern "C" int tgcn_bias_grad(const float* dout, float* db, void* workspace, int
     const int B = bias_filter_blocks(rows);
     bias_grad_filter_kernel<<<B, 256, 0, st>>>(dout, (float*)workspace, rows, G);
     TGCN_LAUNCH_CHECK("bias_grad_filter");
-    reduce_partials_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, st>>>((const float*)workspace, db, B, G);
+    reduce_partials_kernel<<<(unsigned)ceil_div((int64_t)G * 8, 256), 256, 0, st>>>((const float*)workspace, db, B, G);
     TGCN_LAUNCH_CHECK("reduce_partials");
     return TGCN_OK;
 }

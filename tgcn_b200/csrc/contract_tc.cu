@@ -590,6 +590,11 @@ int bwd_w2_partials(int Q, int N, int D, int G, int K);
 // third-generation kernels (TMA tensor copies into the swizzled operand layout), contract_tc3.cu
 int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias, int bias_mode, float* out,
                      int Q, int N, int D, int G, int GP, int K, cudaStream_t st, int* launched);
+int contract_bwd_x_tc3(const float* dout, const uint8_t* wimg, float* gstack, int Q, int N, int D, int DP, int G, int K,
+                       cudaStream_t st, int* launched);
+int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, int* P_out, int Q, int N, int D, int G, int K,
+                       cudaStream_t st, int* launched);
+int bwd_w3_partials(int Q, int N, int D, int G, int K);
 
 static bool use_v2() {
     static const bool on = [] { const char* e = getenv("TGCN_TC_V1"); return !(e && e[0] == '1'); }();
@@ -655,7 +660,9 @@ int64_t tc_fwd_scratch_bytes(int Q, int N, int D, int G, int K) {
 }
 int64_t tc_bwd_scratch_bytes(int Q, int N, int D, int G, int K) {
     const TcPlan t = make_plan(Q, N, D, G, K);
-    const int p2 = bwd_w2_partials(Q, N, D, G, K);
+    int p2 = bwd_w2_partials(Q, N, D, G, K);
+    const int p3 = bwd_w3_partials(Q, N, D, G, K);
+    if (p3 > p2) p2 = p3;
     const int64_t partial = (int64_t)(t.P > p2 ? t.P : p2) * K * D * G * (int64_t)sizeof(float);
     return t.img_bwdx_bytes + partial + 2048;
 }
@@ -730,6 +737,11 @@ int contract_bwd_x_tc(const float* dout, const float* Wmix, float* gstack, void*
         prep_wimg_kernel<<<(unsigned)min64(ceil_div(total, 256), 2 * kNumSMs), 256, 0, st>>>(Wmix, img, K, D, G, t.DP, t.GB, 0);
         TGCN_LAUNCH_CHECK("prep_wimg(bwd_x)");
     }
+    {
+        int launched = 0;
+        TGCN_PROPAGATE(contract_bwd_x_tc3(dout, img, gstack, Q, N, D, t.DP, G, K, st, &launched));
+        if (launched) return TGCN_OK;
+    }
     BwdXTcParams p{};
     p.dout = dout; p.wimg = img; p.gstack = gstack; p.S = (int64_t)N * Q * D;
     p.M = Q * N; p.Q = Q; p.N = N; p.D = D; p.G = G; p.DP = t.DP; p.K = K; p.GB = t.GB; p.NT = t.NT;
@@ -770,6 +782,11 @@ int contract_bwd_w_tc(const float* stack, const float* dout, float* partial, int
                       int Q, int N, int D, int G, int K, cudaStream_t st) {
     const TcPlan t = make_plan(Q, N, D, G, K);
     TGCN_SUPPORTED(t.ok, "contract_bwd_w_tc: shape D=%d G=%d outside the tcgen05 tiles", D, G);
+    {
+        int launched = 0;
+        TGCN_PROPAGATE(contract_bwd_w_tc3(stack, dout, partial, P_out, Q, N, D, G, K, st, &launched));
+        if (launched) return TGCN_OK;
+    }
     if (use_v2()) {
         int launched = 0;
         TGCN_PROPAGATE(contract_bwd_w_tc2(stack, dout, partial, P_out, Q, N, D, G, K, st, &launched));

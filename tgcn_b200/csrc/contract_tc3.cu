@@ -287,6 +287,342 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward w.r.t. the input:  G_j[m, d] = sum_g dOut[m, g] W'_j[d, g]   for every order j
+// The dOut tile of 128 (vertex, sample) pairs is loaded ONCE (3-D TMA box over dOut[Q][N][G]: 128/Q vertices x Q
+// samples x 32 filters, rows land sample-major), its lo part is formed once, and the K orders then stream their
+// weight images through a small ring; the accumulator of order j drains (TMEM -> 16-byte stores of the slab rows)
+// while order j + 1 multiplies.
+// ------------------------------------------------------------------------------------------------
+constexpr int kX3WRing = 3;
+
+struct BwdX3Params {
+    const uint8_t* wimg;           // per (j, gb): [hi | lo] x [DP rows (d) x 128 B (32 g)], K-major SWIZZLE_128B
+    float* gstack;                 // [K][M][D]
+    int M, Q, N, D, DP, G, GB, K, nt;      // nt = 128 / Q vertices per tile
+    int ntiles, abufs;
+    uint32_t wunit;                // bytes of one order's images: GB * 2 * DP * 128
+};
+
+__global__ void __launch_bounds__(kT3Threads, 1)
+contract_bwd_x_tc3_kernel(const __grid_constant__ CUtensorMap tmD, const BwdX3Params p) {
+    extern __shared__ uint8_t smem_raw3[];
+    uint8_t* smem = align1024_3(smem_raw3);
+    __shared__ __align__(8) uint64_t a_full[2], a_lo[2], a_empty[2], w_full[kX3WRing], w_empty[kX3WRing], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t abytes = (uint32_t)p.GB * 2u * kT3Tile;            // one A buffer: GB x [raw | lo]
+    uint8_t* abase = smem;
+    uint8_t* wbase = smem + (size_t)p.abufs * abytes;
+    const uint32_t ncols = tmem_cols_pow2(2u * (uint32_t)p.DP);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_lo[i], kT3TransformWarps); mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
+        for (int i = 0; i < kX3WRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmD);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t AB = (uint32_t)p.abufs;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            auto load_a = [&](uint32_t ti, int tile) {
+                const uint32_t ab = ti % AB;
+                if (ti >= AB) mbar_wait(&a_empty[ab], ((ti / AB) - 1) & 1);
+                mbar_arrive_expect_tx(&a_full[ab], (uint32_t)p.GB * kT3Tile);
+                for (int gb = 0; gb < p.GB; ++gb)
+                    tma_load_3d(abase + (size_t)ab * abytes + (size_t)gb * 2 * kT3Tile, &tmD, gb * 32, tile * p.nt, 0, &a_full[ab]);
+            };
+            uint32_t ti = 0, gw = 0;
+            if ((int)blockIdx.x < p.ntiles) load_a(0, blockIdx.x);
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+                if (AB > 1 && tile + (int)gridDim.x < p.ntiles) load_a(ti + 1, tile + gridDim.x);
+                for (int j = 0; j < p.K; ++j, ++gw) {
+                    const uint32_t ws = gw % kX3WRing;
+                    if (gw >= kX3WRing) mbar_wait(&w_empty[ws], ((gw / kX3WRing) - 1) & 1);
+                    mbar_arrive_expect_tx(&w_full[ws], p.wunit);
+                    bulk_g2s(wbase + (size_t)ws * p.wunit, p.wimg + (size_t)j * p.wunit, p.wunit, &w_full[ws]);
+                }
+                if (AB == 1 && tile + (int)gridDim.x < p.ntiles) load_a(ti + 1, tile + gridDim.x);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.DP, 0, 0);
+            const uint32_t whalf = (uint32_t)p.DP * kRowBytes;         // hi image of one (j, gb), lo follows
+            uint32_t ti = 0, gw = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+                const uint32_t ab = ti % AB, aph = (ti / AB) & 1;
+                mbar_wait(&a_full[ab], aph);
+                mbar_wait(&a_lo[ab], aph);
+                uint8_t* at = abase + (size_t)ab * abytes;
+                for (int j = 0; j < p.K; ++j, ++gw) {
+                    const uint32_t ws = gw % kX3WRing, acb = gw & 1u;
+                    mbar_wait(&w_full[ws], (gw / kX3WRing) & 1);
+                    if (gw >= 2) mbar_wait(&acc_empty[acb], ((gw >> 1) - 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t acc = tmem_base + acb * (uint32_t)p.DP;
+                    const uint8_t* wu = wbase + (size_t)ws * p.wunit;
+                    for (int gb = 0; gb < p.GB; ++gb) {
+                        const uint64_t dah = make_desc_kmajor(smem_u32(at + (size_t)gb * 2 * kT3Tile));
+                        const uint64_t dal = make_desc_kmajor(smem_u32(at + (size_t)gb * 2 * kT3Tile + kT3Tile));
+                        const uint64_t dbh = make_desc_kmajor(smem_u32(wu + (size_t)gb * 2 * whalf));
+                        const uint64_t dbl = make_desc_kmajor(smem_u32(wu + (size_t)gb * 2 * whalf + whalf));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t adv = (uint64_t)(ks * 2);
+                            umma_tf32(acc, dal + adv, dbh + adv, idesc, (gb | ks) ? 1u : 0u);
+                            umma_tf32(acc, dah + adv, dbl + adv, idesc, 1u);
+                            umma_tf32(acc, dah + adv, dbh + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&w_empty[ws]);
+                    umma_commit(&acc_full[acb]);
+                }
+                umma_commit(&a_empty[ab]);
+            }
+        }
+    } else if (warp < kT3TransformWarp0) {
+        const int lq = warp & 3;
+        const int r = lq * 32 + lane;                                  // row of the tile: sample-major (q, vertex)
+        const int q = r / p.nt, nl = r - q * p.nt;
+        const bool vec = (p.D % 4 == 0) && aligned16(p.gstack);
+        uint32_t gw = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int n = tile * p.nt + nl;
+            const bool live = n < p.N;
+            const int64_t m = (int64_t)n * p.Q + q;
+            for (int j = 0; j < p.K; ++j, ++gw) {
+                const uint32_t acb = gw & 1u;
+                mbar_wait(&acc_full[acb], (gw >> 1) & 1);
+                tcgen05_fence_after();
+                float* dst = p.gstack + ((int64_t)j * p.M + m) * p.D;
+                for (int cb = 0; cb < p.DP; cb += 32) {
+                    float v[32];
+                    if (p.DP - cb >= 32) tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acb * (uint32_t)p.DP + (uint32_t)cb, v);
+                    else tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + acb * (uint32_t)p.DP + (uint32_t)cb, v);
+                    if (!live) continue;
+                    const int ncol = min(32, p.DP - cb);
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            if (i < ncol && cb + i < p.D) *reinterpret_cast<float4*>(dst + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.D) dst[cb + i] = v[i];
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acb]);
+            }
+        }
+    } else {
+        const int t = tid - kT3TransformWarp0 * 32;
+        const uint32_t base_u32 = smem_u32(abase);
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+            const uint32_t ab = ti % AB;
+            mbar_wait(&a_full[ab], (ti / AB) & 1);
+            for (int gb = 0; gb < p.GB; ++gb) {
+                const uint32_t src = base_u32 + ab * abytes + (uint32_t)gb * 2u * kT3Tile + (uint32_t)t * 16u;
+                float4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                                 : "r"(src + (uint32_t)i * 4096u));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 l = tf32_lo4(x[i]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)i * 4096u), "f"(l.x), "f"(l.y),
+                                 "f"(l.z), "f"(l.w) : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_lo[ab]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward w.r.t. the mixed weights:  dW'[(j, d), g] = sum_m P_j[m, d] dOut[m, g]
+// Both operands are MN-major (the reduction index m is the slow one in memory): a unit of RU pairs is, per order
+// and 32-column block, a [RU x 32 fp32] TMA tile in SWIZZLE_128B_ATOM_32B layout -- the layout tcgen05 reads
+// MN-major tf32 operands in (SWIZZLE_128B_BASE32B) -- and the dOut rows of the unit arrive through a 3-D box over
+// dOut[Q][N][G] whose strides are given vertex-major, so its rows come out in the same (vertex, sample) order.
+// Four 32-wide blocks form one 128-row output tile; accumulators for all of a CTA's blocks live in TMEM for the
+// whole kernel and are written once, as a per-CTA partial that reduce_partials sums in a fixed order.
+// ------------------------------------------------------------------------------------------------
+struct BwdW3Params {
+    float* partial;                // [P][K*D][G]
+    int M, Q, N, D, G, GPw, K, DB;
+    int NB;                        // 32-wide (order, column block) pairs handled per CTA (grid.y splits the rest)
+    int MT;                        // output tiles per CTA = ceil(NB / 4)
+    int RU, NS, units_per_cta, total_units;
+};
+
+__global__ void __launch_bounds__(kT3Threads, 1)
+contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD, const BwdW3Params p) {
+    extern __shared__ uint8_t smem_raw3[];
+    uint8_t* smem = align1024_3(smem_raw3);
+    __shared__ __align__(8) uint64_t full[kT3MaxStages], lo_ready[kT3MaxStages], empty[kT3MaxStages], acc_full;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t blk = (uint32_t)p.RU * kRowBytes;                  // one 32-wide block of RU reduction rows
+    const int GBk = p.GPw / 32;
+    const uint32_t a_part = (uint32_t)p.MT * 4u * blk;                // hi (= raw) blocks of A, tile-padded
+    const uint32_t b_part = (uint32_t)GBk * blk;
+    const uint32_t stage_bytes = 2u * a_part + 2u * b_part;           // [A hi | A lo | B hi | B lo]
+    const uint32_t ncols = tmem_cols_pow2((uint32_t)(p.MT * p.GPw));
+    const int blk0 = blockIdx.y * p.NB;                               // first (order, column block) pair of this CTA
+    const int nb = min(p.NB, p.K * p.DB - blk0);
+    const int u_begin = blockIdx.x * p.units_per_cta;
+    const int u_end = min(p.total_units, u_begin + p.units_per_cta);
+    const int NS = p.NS;
+
+    if (tid == 0) {
+        for (int i = 0; i < kT3MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&lo_ready[i], kT3TransformWarps); mbar_init(&empty[i], 1); }
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmD);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+    // zero the stages once: the padding blocks of the last output tile (and filters >= G) are never written
+    for (uint32_t i = tid; i < (uint32_t)NS * stage_bytes / 16; i += kT3Threads) reinterpret_cast<float4*>(smem)[i] = make_float4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int gblocks = (p.G + 31) / 32;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int u = u_begin; u < u_end; ++u, ++g) {
+                const uint32_t s = g % (uint32_t)NS;
+                if (g >= (uint32_t)NS) mbar_wait(&empty[s], ((g / NS) - 1) & 1);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(nb + gblocks) * blk);
+                const int m0 = u * p.RU;
+                for (int b = 0; b < nb; ++b) {
+                    const int gbk = blk0 + b, j = gbk / p.DB, db = gbk - j * p.DB;
+                    tma_load_3d(st + (size_t)b * blk, &tmA, db * 32, m0, j, &full[s]);
+                }
+                for (int gb = 0; gb < gblocks; ++gb)
+                    tma_load_3d(st + 2 * (size_t)a_part + (size_t)gb * blk, &tmD, gb * 32, 0, m0 / p.Q, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.GPw, 1, 1);
+            uint32_t g = 0;
+            for (int u = u_begin; u < u_end; ++u, ++g) {
+                const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
+                mbar_wait(&full[s], ph);
+                mbar_wait(&lo_ready[s], ph);
+                tcgen05_fence_after();
+                uint8_t* ah = smem + (size_t)s * stage_bytes;
+                uint8_t* al = ah + a_part;
+                uint8_t* bh = ah + 2 * (size_t)a_part;
+                uint8_t* bl = bh + b_part;
+                for (int t = 0; t < p.MT; ++t) {
+                    const uint32_t acc = tmem_base + (uint32_t)(t * p.GPw);
+                    const uint32_t aoff = (uint32_t)t * 4u * blk;
+                    for (int ks = 0; ks < p.RU / 8; ++ks) {
+                        const uint32_t adv = (uint32_t)ks * kAtomBytes;           // next 8 reduction rows
+                        const uint64_t dah = make_desc_mnmajor(smem_u32(ah + aoff + adv), blk);
+                        const uint64_t dal = make_desc_mnmajor(smem_u32(al + aoff + adv), blk);
+                        const uint64_t dbh = make_desc_mnmajor(smem_u32(bh + adv), blk);
+                        const uint64_t dbl = make_desc_mnmajor(smem_u32(bl + adv), blk);
+                        umma_tf32(acc, dal, dbh, idesc, (g | (uint32_t)ks) ? 1u : 0u);
+                        umma_tf32(acc, dah, dbl, idesc, 1u);
+                        umma_tf32(acc, dah, dbh, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&acc_full);
+        }
+    } else if (warp < kT3TransformWarp0) {
+        // ===================== epilogue: partial[blockIdx.x][(j, d)][g] =====================
+        const int lq = warp & 3;
+        float* dst_base = p.partial + (int64_t)blockIdx.x * p.K * p.D * p.G;
+        if (u_begin < u_end) {
+            mbar_wait(&acc_full, 0);
+            tcgen05_fence_after();
+            for (int t = 0; t < p.MT; ++t) {
+                const int b = t * 4 + lq;                                  // block of this lane quarter
+                const bool ok = b < nb;
+                float* dst = dst_base + ((int64_t)(blk0 + b) * 32 + lane) * p.G;
+                for (int cb = 0; cb < p.GPw; cb += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.GPw + cb), v);
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (cb + i < p.G) dst[cb + i] = v[i];
+                    }
+                }
+            }
+        } else {
+            for (int i = tid - 64; i < nb * 32 * p.G; i += 128) dst_base[(int64_t)blk0 * 32 * p.G + i] = 0.f;
+        }
+    } else {
+        // ===================== transform: lo parts of the A blocks and of the dOut blocks =====================
+        const int t = tid - kT3TransformWarp0 * 32;
+        const uint32_t base_u32 = smem_u32(smem);
+        const uint32_t a_f4 = (uint32_t)nb * blk / 16u, b_f4 = (uint32_t)gblocks * blk / 16u;
+        uint32_t g = 0;
+        for (int u = u_begin; u < u_end; ++u, ++g) {
+            const uint32_t s = g % (uint32_t)NS;
+            mbar_wait(&full[s], (g / NS) & 1);
+            const uint32_t st = base_u32 + s * stage_bytes;
+            for (uint32_t i0 = 0; i0 < a_f4 + b_f4; i0 += 1024u) {
+                float4 x[4];
+                uint32_t off[4], dlt[4];
+                bool ok[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t i = i0 + (uint32_t)k * 256u + (uint32_t)t;
+                    ok[k] = i < a_f4 + b_f4;
+                    const bool isb = i >= a_f4;
+                    off[k] = isb ? 2u * a_part + (i - a_f4) * 16u : i * 16u;
+                    dlt[k] = isb ? b_part : a_part;
+                    if (ok[k])
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[k].x), "=f"(x[k].y), "=f"(x[k].z), "=f"(x[k].w)
+                                     : "r"(st + off[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!ok[k]) continue;
+                    const float4 l = tf32_lo4(x[k]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + off[k] + dlt[k]), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+                                 : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lo_ready[s]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
 template <typename Kern>
 static int set_smem3(Kern kern, size_t bytes, const char* name) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -329,6 +665,102 @@ int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias,
     const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
     contract_fwd_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tmA, p);
     TGCN_LAUNCH_CHECK("contract_fwd_tc3");
+    *launched = 1;
+    return TGCN_OK;
+}
+
+// G_j for all orders; covered: D = 32 * DB <= 128 (one MMA N), G a multiple of 32, Q a power of two <= 128
+int contract_bwd_x_tc3(const float* dout, const uint8_t* wimg, float* gstack, int Q, int N, int D, int DP, int G, int K,
+                       cudaStream_t st, int* launched) {
+    *launched = 0;
+    const int64_t M = (int64_t)Q * N;
+    if (!use_v3() || D % 32 != 0 || DP != D || D > 128 || G % 32 != 0 || G > 256 || Q < 1 || Q > 128 || (128 % Q) != 0 || M <= 0 ||
+        M >= (int64_t)INT32_MAX - 256 || (reinterpret_cast<uintptr_t>(dout) & 15u) != 0 || (reinterpret_cast<uintptr_t>(gstack) & 15u) != 0)
+        return TGCN_OK;
+    BwdX3Params p{};
+    p.wimg = wimg; p.gstack = gstack; p.M = (int)M; p.Q = Q; p.N = N; p.D = D; p.DP = DP; p.G = G; p.GB = G / 32; p.K = K;
+    p.nt = 128 / Q;
+    p.ntiles = (int)ceil_div(N, p.nt);
+    p.wunit = (uint32_t)p.GB * 2u * (uint32_t)DP * kRowBytes;
+    const size_t abytes = (size_t)p.GB * 2 * kT3Tile, fixed = 1024 + 256;
+    const size_t wring = (size_t)kX3WRing * p.wunit;
+    if (fixed + wring + abytes > kT3SmemLimit) return TGCN_OK;
+    p.abufs = (fixed + wring + 2 * abytes <= kT3SmemLimit) ? 2 : 1;
+    const size_t smem = fixed + wring + (size_t)p.abufs * abytes;
+    CUtensorMap tmD;
+    TGCN_PROPAGATE(make_tmap3(&tmD, dout, (uint64_t)G, (uint64_t)N, (uint64_t)Q, (uint64_t)G * 4, (uint64_t)N * G * 4, 32, (uint32_t)p.nt,
+                              (uint32_t)Q, CU_TENSOR_MAP_SWIZZLE_128B));
+    TGCN_PROPAGATE(set_smem3(contract_bwd_x_tc3_kernel, smem, "contract_bwd_x_tc3"));
+    const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
+    contract_bwd_x_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tmD, p);
+    TGCN_LAUNCH_CHECK("contract_bwd_x_tc3");
+    *launched = 1;
+    return TGCN_OK;
+}
+
+struct BwdW3Plan { bool ok; int GPw, DB, NBtot, NB, NY, MT, RU, NS, P, units_per_cta, total_units; size_t smem; };
+
+static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
+    BwdW3Plan t{};
+    const int64_t M = (int64_t)Q * N;
+    if (!use_v3() || D % 32 != 0 || G < 1 || G > 256 || Q < 1 || M <= 0 || M >= (int64_t)INT32_MAX - 256) return t;
+    t.GPw = (G + 31) / 32 * 32;
+    t.DB = D / 32;
+    t.NBtot = K * t.DB;
+    const int max_tiles = 512 / t.GPw;                       // TMEM columns
+    if (max_tiles < 1) return t;
+    t.NB = t.NBtot < 4 * max_tiles ? t.NBtot : 4 * max_tiles;
+    t.NY = (t.NBtot + t.NB - 1) / t.NB;
+    t.NB = (t.NBtot + t.NY - 1) / t.NY;                      // balance the y groups
+    t.MT = (t.NB + 3) / 4;
+    const size_t fixed = 1024 + 256;
+    for (int ru : {32, 16, 8}) {
+        // a unit's rows must be whole vertices (its dOut box is [ru / Q vertices] x [Q samples]) unless Q > ru
+        if (ru % Q != 0) continue;
+        const size_t blk = (size_t)ru * kRowBytes;
+        const size_t stage = 2 * (size_t)t.MT * 4 * blk + 2 * (size_t)(t.GPw / 32) * blk;
+        int ns = (int)((kT3SmemLimit - fixed) / stage);
+        if (ns > kT3MaxStages) ns = kT3MaxStages;
+        if (ns >= 2) { t.RU = ru; t.NS = ns; t.smem = fixed + (size_t)ns * stage; break; }
+    }
+    if (t.RU == 0) return t;
+    if (const char* e = getenv("TGCN_T3_NS")) { const int v = atoi(e); if (v >= 2 && v <= t.NS) t.NS = v; }
+    t.total_units = (int)ceil_div(M, t.RU);
+    int64_t want = kNumSMs / t.NY;
+    if (want < 1) want = 1;
+    if (want > t.total_units) want = t.total_units;
+    t.units_per_cta = (int)ceil_div(t.total_units, want);
+    t.P = (int)ceil_div(t.total_units, t.units_per_cta);
+    t.ok = true;
+    return t;
+}
+
+int bwd_w3_partials(int Q, int N, int D, int G, int K) {
+    const BwdW3Plan t = make_bwd_w3_plan(Q, N, D, G, K);
+    return t.ok ? t.P : 0;
+}
+
+int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, int* P_out, int Q, int N, int D, int G, int K,
+                       cudaStream_t st, int* launched) {
+    *launched = 0;
+    const BwdW3Plan t = make_bwd_w3_plan(Q, N, D, G, K);
+    if (!t.ok || (reinterpret_cast<uintptr_t>(stack) & 15u) != 0 || (reinterpret_cast<uintptr_t>(dout) & 15u) != 0 || (G % 4) != 0)
+        return TGCN_OK;
+    const int64_t M = (int64_t)Q * N;
+    BwdW3Params p{};
+    p.partial = partial; p.M = (int)M; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GPw = t.GPw; p.K = K; p.DB = t.DB;
+    p.NB = t.NB; p.MT = t.MT; p.RU = t.RU; p.NS = t.NS; p.units_per_cta = t.units_per_cta; p.total_units = t.total_units;
+    CUtensorMap tmA, tmD;
+    TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, (uint32_t)t.RU, 1,
+                              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    // dOut[Q][N][G] addressed vertex-major: dimension 1 = sample (stride N*G), dimension 2 = vertex (stride G)
+    TGCN_PROPAGATE(make_tmap3(&tmD, dout, (uint64_t)G, (uint64_t)Q, (uint64_t)N, (uint64_t)N * G * 4, (uint64_t)G * 4, 32, (uint32_t)Q,
+                              (uint32_t)(t.RU / Q), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    TGCN_PROPAGATE(set_smem3(contract_bwd_w_tc3_kernel, t.smem, "contract_bwd_w_tc3"));
+    const dim3 grid((unsigned)t.P, (unsigned)t.NY);
+    contract_bwd_w_tc3_kernel<<<grid, kT3Threads, t.smem, st>>>(tmA, tmD, p);
+    TGCN_LAUNCH_CHECK("contract_bwd_w_tc3");
+    *P_out = t.P;
     *launched = 1;
     return TGCN_OK;
 }

@@ -68,6 +68,93 @@ static int swap_axes(const float* in, float* out, int A, int B, int D, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
+// x[Q,N,D] <-> slab[N, Q*Dp] with Dp >= D (zero padding columns): the layout change into the vertex-major slab
+// fused with the padding the TMA-fed contraction wants (slab rows of whole 128-byte blocks), so neither a separate
+// pad copy nor a slice ever runs.  A block owns TN consecutive vertices: per sample their TN*D inputs are one
+// contiguous run, and the TN*Q*Dp slab floats are one contiguous run.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+slab_pack_kernel(const float* __restrict__ x, float* __restrict__ slab, int Q, int N, int D, int Dp, int TN) {
+    extern __shared__ float ptile[];                 // [Q][TN][D]
+    const int n0 = blockIdx.x * TN, tn = min(TN, N - n0);
+    const int run = tn * D;
+    for (int i = threadIdx.x; i < Q * run; i += blockDim.x) {
+        const int q = i / run, r = i - q * run;
+        ptile[q * TN * D + r] = __ldg(x + ((int64_t)q * N + n0) * D + r);
+    }
+    __syncthreads();
+    const int row = Q * Dp;
+    float* dst = slab + (int64_t)n0 * row;
+    if ((Dp & 3) == 0 && aligned16(slab)) {
+        const int row4 = row >> 2, dp4 = Dp >> 2;
+        for (int i = threadIdx.x; i < tn * row4; i += blockDim.x) {
+            const int nl = i / row4, r4 = i - nl * row4;
+            const int q = r4 / dp4, d = (r4 - q * dp4) * 4;
+            const float* src = ptile + (q * TN + nl) * D + d;
+            float4 v;
+            v.x = d + 0 < D ? src[0] : 0.f; v.y = d + 1 < D ? src[1] : 0.f;
+            v.z = d + 2 < D ? src[2] : 0.f; v.w = d + 3 < D ? src[3] : 0.f;
+            reinterpret_cast<float4*>(dst)[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < tn * row; i += blockDim.x) {
+            const int nl = i / row, r = i - nl * row;
+            const int q = r / Dp, d = r - q * Dp;
+            dst[i] = d < D ? ptile[(q * TN + nl) * D + d] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+slab_unpack_kernel(const float* __restrict__ slab, float* __restrict__ x, int Q, int N, int D, int Dp, int TN) {
+    extern __shared__ float ptile[];                 // [TN][Q][Dp]
+    const int n0 = blockIdx.x * TN, tn = min(TN, N - n0);
+    const int row = Q * Dp;
+    const float* src = slab + (int64_t)n0 * row;
+    if ((row & 3) == 0 && aligned16(slab)) {
+        for (int i = threadIdx.x; i < tn * (row >> 2); i += blockDim.x)
+            reinterpret_cast<float4*>(ptile)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < tn * row; i += blockDim.x) ptile[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int run = tn * D;
+    for (int i = threadIdx.x; i < Q * run; i += blockDim.x) {
+        const int q = i / run, r = i - q * run;
+        const int nl = r / D, d = r - nl * D;
+        x[((int64_t)q * N + n0) * D + r] = ptile[(nl * Q + q) * Dp + d];
+    }
+}
+
+static int slab_tile_rows(int Q, int Dp) {
+    int tn = (int)(12288 / ((int64_t)Q * Dp));       // <= 48 KB of shared memory per block
+    if (tn > 64) tn = 64;
+    return tn < 1 ? 1 : tn;
+}
+
+int slab_pack(const float* x, float* slab, int Q, int N, int D, int Dp, cudaStream_t st) {
+    if ((int64_t)Q * N * D == 0) return TGCN_OK;
+    if (Dp == D && D > 128) return swap_axes(x, slab, Q, N, D, st);
+    const int TN = slab_tile_rows(Q, Dp);
+    const size_t smem = sizeof(float) * (size_t)Q * TN * Dp;
+    TGCN_SUPPORTED(smem <= 48 * 1024, "to_slab: Q=%d D=%d too wide for the tile kernel", Q, Dp);
+    slab_pack_kernel<<<(unsigned)ceil_div(N, TN), 256, smem, st>>>(x, slab, Q, N, D, Dp, TN);
+    TGCN_LAUNCH_CHECK("slab_pack");
+    return TGCN_OK;
+}
+
+int slab_unpack(const float* slab, float* x, int Q, int N, int D, int Dp, cudaStream_t st) {
+    if ((int64_t)Q * N * D == 0) return TGCN_OK;
+    if (Dp == D && D > 128) return swap_axes(slab, x, N, Q, D, st);
+    const int TN = slab_tile_rows(Q, Dp);
+    const size_t smem = sizeof(float) * (size_t)Q * TN * Dp;
+    TGCN_SUPPORTED(smem <= 48 * 1024, "from_slab: Q=%d D=%d too wide for the tile kernel", Q, Dp);
+    slab_unpack_kernel<<<(unsigned)ceil_div(N, TN), 256, smem, st>>>(slab, x, Q, N, D, Dp, TN);
+    TGCN_LAUNCH_CHECK("slab_unpack");
+    return TGCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // SpMM step
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) { fma4_packed(acc, w, x); }
@@ -1029,13 +1116,13 @@ extern "C" int tgcn_rowtile_plan_destroy(int64_t handle) {
 extern "C" int tgcn_to_slab(const float* x, float* slab, int Q, int N, int D, void* stream) {
     TGCN_REQUIRE(x && slab, "tgcn_to_slab: null pointer");
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0, "tgcn_to_slab: negative size");
-    return swap_axes(x, slab, Q, N, D, as_stream(stream));
+    return slab_pack(x, slab, Q, N, D, D, as_stream(stream));
 }
 
 extern "C" int tgcn_from_slab(const float* slab, float* x, int Q, int N, int D, void* stream) {
     TGCN_REQUIRE(x && slab, "tgcn_from_slab: null pointer");
     TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0, "tgcn_from_slab: negative size");
-    return swap_axes(slab, x, N, Q, D, as_stream(stream));
+    return slab_unpack(slab, x, Q, N, D, D, as_stream(stream));
 }
 
 extern "C" int tgcn_spmm_step(const int32_t* rowptr, const int32_t* col, const float* val, int N,
@@ -1047,18 +1134,14 @@ extern "C" int tgcn_spmm_step(const int32_t* rowptr, const int32_t* col, const f
     return spmm_step(rowptr, col, val, N, in, prev, out, C, alpha, beta, as_stream(stream));
 }
 
-extern "C" int tgcn_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int N,
-                               const float* x, float* stack, int Q, int D, int K, int recursion,
-                               void* stream) {
-    TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0 && K >= 1, "tgcn_cheb_basis: bad sizes Q=%d N=%d D=%d K=%d", Q, N, D, K);
-    TGCN_REQUIRE(recursion == TGCN_RECURSION_REFERENCE || recursion == TGCN_RECURSION_CHEBYSHEV,
-                 "tgcn_cheb_basis: unknown recursion %d", recursion);
-    const int64_t C = (int64_t)Q * D;
+namespace tgcn {
+// basis of x[Q,N,D] in slabs of Q*Dp columns (Dp >= D: zero padding columns, which every recursion step keeps zero)
+int cheb_basis_padded(const int32_t* rowptr, const int32_t* col, const float* val, int N, const float* x, float* stack,
+                      int Q, int D, int Dp, int K, int recursion, cudaStream_t st) {
+    const int64_t C = (int64_t)Q * Dp;
     const int64_t S = (int64_t)N * C;
-    if (S == 0) return TGCN_OK;
-    TGCN_REQUIRE(rowptr && x && stack, "tgcn_cheb_basis: null pointer");
-    cudaStream_t st = as_stream(stream);
-    TGCN_PROPAGATE(swap_axes(x, stack, Q, N, D, st));
+    if (S == 0 || D == 0) return TGCN_OK;
+    TGCN_PROPAGATE(slab_pack(x, stack, Q, N, D, Dp, st));
     for (int k = 1; k < K; ++k) {
         float* cur = stack + (int64_t)k * S;
         const float* in = stack + (int64_t)(k - 1) * S;
@@ -1069,6 +1152,18 @@ extern "C" int tgcn_cheb_basis(const int32_t* rowptr, const int32_t* col, const 
         }
     }
     return TGCN_OK;
+}
+}  // namespace tgcn
+
+extern "C" int tgcn_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int N,
+                               const float* x, float* stack, int Q, int D, int K, int recursion,
+                               void* stream) {
+    TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0 && K >= 1, "tgcn_cheb_basis: bad sizes Q=%d N=%d D=%d K=%d", Q, N, D, K);
+    TGCN_REQUIRE(recursion == TGCN_RECURSION_REFERENCE || recursion == TGCN_RECURSION_CHEBYSHEV,
+                 "tgcn_cheb_basis: unknown recursion %d", recursion);
+    if ((int64_t)Q * N * D == 0) return TGCN_OK;
+    TGCN_REQUIRE(rowptr && x && stack, "tgcn_cheb_basis: null pointer");
+    return cheb_basis_padded(rowptr, col, val, N, x, stack, Q, D, D, K, recursion, as_stream(stream));
 }
 
 extern "C" int tgcn_basis_to_reference(const float* stack, float* Xt, int Q, int N, int D, int K,
@@ -1083,15 +1178,12 @@ extern "C" int tgcn_basis_to_reference(const float* stack, float* Xt, int Q, int
     return TGCN_OK;
 }
 
-extern "C" int tgcn_cheb_adjoint(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N,
-                                 float* gstack, float* dx, int Q, int D, int K, int recursion,
-                                 void* stream) {
-    TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0 && K >= 1, "tgcn_cheb_adjoint: bad sizes");
-    const int64_t C = (int64_t)Q * D;
+namespace tgcn {
+int cheb_adjoint_padded(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N, float* gstack, float* dx,
+                        int Q, int D, int Dp, int K, int recursion, cudaStream_t st) {
+    const int64_t C = (int64_t)Q * Dp;
     const int64_t S = (int64_t)N * C;
-    if (S == 0) return TGCN_OK;
-    TGCN_REQUIRE(rowptrT && gstack && dx, "tgcn_cheb_adjoint: null pointer");
-    cudaStream_t st = as_stream(stream);
+    if (S == 0 || D == 0) return TGCN_OK;
     if (recursion == TGCN_RECURSION_REFERENCE) {
         // P_j = L P_{j-1}:  A_{K-1} = G_{K-1};  A_j = G_j + L^T A_{j+1}   (Horner), dx = A_0
         for (int j = K - 2; j >= 0; --j) {
@@ -1111,5 +1203,15 @@ extern "C" int tgcn_cheb_adjoint(const int32_t* rowptrT, const int32_t* colT, co
         }
         if (K >= 2) TGCN_PROPAGATE(spmm_step(rowptrT, colT, valT, N, gstack + S, gstack, gstack, C, 1.f, 1.f, st));
     }
-    return swap_axes(gstack, dx, N, Q, D, st);
+    return slab_unpack(gstack, dx, Q, N, D, Dp, st);
+}
+}  // namespace tgcn
+
+extern "C" int tgcn_cheb_adjoint(const int32_t* rowptrT, const int32_t* colT, const float* valT, int N,
+                                 float* gstack, float* dx, int Q, int D, int K, int recursion,
+                                 void* stream) {
+    TGCN_REQUIRE(Q >= 0 && N >= 0 && D >= 0 && K >= 1, "tgcn_cheb_adjoint: bad sizes");
+    if ((int64_t)Q * N * D == 0) return TGCN_OK;
+    TGCN_REQUIRE(rowptrT && gstack && dx, "tgcn_cheb_adjoint: null pointer");
+    return cheb_adjoint_padded(rowptrT, colT, valT, N, gstack, dx, Q, D, D, K, recursion, as_stream(stream));
 }

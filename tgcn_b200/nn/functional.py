@@ -85,16 +85,19 @@ class ChebLayerFunction(torch.autograd.Function):
         if _ROWTILE_SPMM:
             plan.ensure_rowtile_plans(rows_per_tile=_ROWTILE_SPMM)
         out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
-        stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
-        fw_bytes = int(lib.tgcn_layer_fwd_workspace(Q, N, D, G, K))
+        # slab width of the streaming kernels: D, or D padded to whole 128-byte blocks for the TMA-fed contraction
+        Dp = int(lib.tgcn_layer_slab_width(Q, N, D, G, K, engine))
+        stack = torch.empty((K, N, Q * Dp), dtype=torch.float32, device=dev)
+        fw_bytes = int(lib.tgcn_layer_fwd_workspace(Q, N, Dp, G, K))
         wmix = torch.empty((max(fw_bytes, 4) + 3) // 4, dtype=torch.float32, device=dev)   # [Wmix | engine scratch]
         with _DeviceGuard(dev):
             rc = lib.tgcn_layer_fwd(_ptr(plan.rowptr), _ptr(plan.col), _ptr(plan.val), N, _ptr(x), _ptr(w), _ptr(b),
                                     bias_mode if b is not None else _lib.BIAS_NONE, _ptr(out), _ptr(stack), _ptr(wmix),
-                                    Q, D, G, K, recursion, engine, _stream(dev))
+                                    Q, D, Dp, G, K, recursion, engine, _stream(dev))
         _lib.check(rc, "tgcn_layer_fwd")
         ctx.plan = plan
         ctx.dims = (Q, N, D, G, K)
+        ctx.Dp = Dp
         ctx.cfg = (bias_mode if b is not None else _lib.BIAS_NONE, recursion, engine)
         ctx.bias_shape = None if bias is None else tuple(bias.shape)
         ctx.w_shape = tuple(weight.shape)
@@ -115,13 +118,14 @@ class ChebLayerFunction(torch.autograd.Function):
         dW = torch.empty(ctx.w_shape, dtype=torch.float32, device=dev)
         db = torch.empty(ctx.bias_shape, dtype=torch.float32, device=dev) if bias_mode != _lib.BIAS_NONE else None
         dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev) if need_dx else None
-        gstack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev) if need_dx else None
-        ws_bytes = lib.tgcn_layer_bwd_workspace(Q, N, D, G, K)
+        Dp = ctx.Dp
+        gstack = torch.empty((K, N, Q * Dp), dtype=torch.float32, device=dev) if need_dx else None
+        ws_bytes = lib.tgcn_layer_bwd_workspace(Q, N, Dp, G, K)
         ws = torch.empty((max(int(ws_bytes), 4) + 3) // 4, dtype=torch.float32, device=dev)
         with _DeviceGuard(dev):
             rc = lib.tgcn_layer_bwd(_ptr(plan.rowptr_t), _ptr(plan.col_t), _ptr(plan.val_t), N, _ptr(dout), _ptr(stack),
                                     _ptr(wmix), _ptr(dW), _ptr(db), bias_mode, _ptr(dx), _ptr(gstack), _ptr(ws),
-                                    Q, D, G, K, recursion, engine, _stream(dev))
+                                    Q, D, Dp, G, K, recursion, engine, _stream(dev))
         _lib.check(rc, "tgcn_layer_bwd")
         return dx, dW, db, None, None, None, None
 

@@ -155,14 +155,6 @@ class _ChebBase(torch.nn.Module):
         if self._use_resident(plan, w3.shape[1], w3.shape[2], K):
             res = F_.ResidentChebFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, pool_p, relu, drop)
             return res[0] if pool_p else res
-        # streaming path: the TMA-fed tensor-core contraction (csrc/contract_tc3.cu) wants slab rows of whole 128-byte
-        # blocks (D a multiple of 32).  A D just below one (the cortical-mesh layer 1: H*F = 30) is zero-padded -- zero
-        # columns stay zero through the recursion and meet zero weight rows, so the result is unchanged.
-        D = w3.shape[1]
-        Dp = (D + 31) // 32 * 32
-        if self.engine in ("auto", "tcgen05") and Dp != D and (Dp - D) * 8 <= D:
-            x3 = torch.nn.functional.pad(x3, (0, Dp - D))
-            w3 = torch.nn.functional.pad(w3, (0, 0, 0, Dp - D))
         out = F_.ChebLayerFunction.apply(x3, w3, self.bias, plan, self._bias_mode, rec, _ENGINE[self.engine])
         if pool_p:
             out = F_.PoolFunction.apply(out, pool_p, relu, drop)[0]
