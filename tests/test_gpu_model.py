@@ -26,10 +26,19 @@ def _train_both(model, port, xs, ys, steps, lr=0.01, momentum=0.5, fc1_fused=Fal
     import copy
     from tgcn_b200.nn.head import Fc1FusedSGD
     from tgcn_b200.parallel import PeerAllreduceSGD
-    port64 = copy.deepcopy(port).double()
-    for m in port64.modules():
+    # float64 twin of the port (sparse-CSR operands cannot be deep-copied: detach them, copy, re-attach as double)
+    ops = {}
+    for name, m in port.named_modules():
         if hasattr(m, "L") and isinstance(m.L, torch.Tensor):
-            m.L = m.L.double()
+            ops[name] = m.L
+            m.L = None
+    port64 = copy.deepcopy(port).double()
+    for name, m in port.named_modules():
+        if name in ops:
+            m.L = ops[name]
+    for name, m in port64.named_modules():
+        if name in ops:
+            m.L = ops[name].to(torch.float64)
     params = list(model.parameters())
     if fc1_fused:
         model.fc1_update = Fc1FusedSGD(model.fc1.weight, lr=lr, momentum=momentum)

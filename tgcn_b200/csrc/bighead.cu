@@ -100,7 +100,7 @@ bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, fl
             float s = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) s += red[w8][ol][q];
-            partial[((int64_t)blockIdx.x * Q + q) * Hd + o0 + ol] = s;
+            partial[((int64_t)q * Hd + o0 + ol) * gridDim.x + blockIdx.x] = s;   // [Q][Hd][P]: contiguous for the reduction
         }
     }
 }
@@ -111,62 +111,59 @@ __device__ __forceinline__ float bh_warp_sum(float v) {
     return v;
 }
 
-// h = b1 + sum_p partial[p] (fixed order), BatchNorm1d statistics, ReLU, dropout: one CTA per 8 hidden features,
-// thread = (sample, feature, quarter of the partials).  Q <= 32.
-constexpr int kBhBnF = 8;
+// h = b1 + sum_p partial[q][f][p] (fixed order: lane l sums p = l, l + 32, ...; then a butterfly), BatchNorm1d
+// statistics, ReLU, dropout.  One CTA per hidden feature, one warp per sample (warps loop when Q > 8): the P partials
+// of a (sample, feature) pair are contiguous, so the reduction is a handful of coalesced loads per lane instead of a
+// chain of P dependent ones (the first version: 23 us at P = 164).  Q <= 64.
+constexpr int kBhBnMaxQ = 64;
 __global__ void __launch_bounds__(kBhThreads)
 bighead_bn_kernel(const float* __restrict__ partial, int P, const float* __restrict__ b1, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                   int training, float* __restrict__ act, float* __restrict__ xhat, float* __restrict__ invstd_out, int Q,
                   int Hd, float drop_p, uint32_t drop_seed, const uint32_t* drop_step) {
-    __shared__ float hs[32][kBhBnF];
-    __shared__ float s_mean[kBhBnF], s_inv[kBhBnF];
+    __shared__ float hs[kBhBnMaxQ];
+    __shared__ float s_mean, s_inv;
     const DropCfg drop = drop_resolve(drop_p, drop_seed, drop_step);
-    const int f0 = blockIdx.x * kBhBnF;
+    const int f = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int pair = tid >> 2; pair < Q * kBhBnF; pair += kBhThreads / 4) {
-        const int q = pair / kBhBnF, f = pair - q * kBhBnF;
-        const int sub = tid & 3;
+    const float bias = b1 ? __ldg(b1 + f) : 0.f;
+    for (int q = warp; q < Q; q += kBhThreads / 32) {
+        const float* src = partial + ((int64_t)q * Hd + f) * P;
         float s = 0.f;
-        if (f0 + f < Hd)
-            for (int p = sub; p < P; p += 4) s += __ldg(partial + ((int64_t)p * Q + q) * Hd + f0 + f);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (sub == 0) hs[q][f] = s + ((b1 && f0 + f < Hd) ? __ldg(b1 + f0 + f) : 0.f);
+        for (int p = lane; p < P; p += 32) s += __ldg(src + p);
+        s = bh_warp_sum(s);
+        if (lane == 0) hs[q] = s + bias;
     }
     __syncthreads();
-    if (warp < kBhBnF && f0 + warp < Hd) {
-        const int f = warp;
+    if (warp == 0) {
         float mean, inv;
         if (training) {
             float s = 0.f;
-            for (int q = lane; q < Q; q += 32) s += hs[q][f];
+            for (int q = lane; q < Q; q += 32) s += hs[q];
             mean = bh_warp_sum(s) / (float)Q;
             float v = 0.f;
-            for (int q = lane; q < Q; q += 32) { const float d = hs[q][f] - mean; v = fmaf(d, d, v); }
+            for (int q = lane; q < Q; q += 32) { const float d = hs[q] - mean; v = fmaf(d, d, v); }
             const float var = bh_warp_sum(v) / (float)Q;
             inv = 1.0f / sqrtf(var + eps);
             if (lane == 0 && running_mean) {
                 const float unb = Q > 1 ? var * (float)Q / (float)(Q - 1) : var;
-                running_mean[f0 + f] = (1.f - momentum) * running_mean[f0 + f] + momentum * mean;
-                running_var[f0 + f] = (1.f - momentum) * running_var[f0 + f] + momentum * unb;
+                running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * mean;
+                running_var[f] = (1.f - momentum) * running_var[f] + momentum * unb;
             }
         } else {
-            mean = running_mean[f0 + f];
-            inv = 1.0f / sqrtf(running_var[f0 + f] + eps);
+            mean = running_mean[f];
+            inv = 1.0f / sqrtf(running_var[f] + eps);
         }
-        if (lane == 0) { s_mean[f] = mean; s_inv[f] = inv; if (invstd_out) invstd_out[f0 + f] = inv; }
+        if (lane == 0) { s_mean = mean; s_inv = inv; if (invstd_out) invstd_out[f] = inv; }
     }
     __syncthreads();
-    for (int i = tid; i < Q * kBhBnF; i += kBhThreads) {
-        const int q = i / kBhBnF, f = i - q * kBhBnF;
-        if (f0 + f >= Hd) continue;
-        const float xh = (hs[q][f] - s_mean[f]) * s_inv[f];
-        const float y = fmaf(xh, gamma ? __ldg(gamma + f0 + f) : 1.f, beta ? __ldg(beta + f0 + f) : 0.f);
-        if (xhat) xhat[(int64_t)q * Hd + f0 + f] = xh;
+    for (int q = tid; q < Q; q += kBhThreads) {
+        const float xh = (hs[q] - s_mean) * s_inv;
+        const float y = fmaf(xh, gamma ? __ldg(gamma + f) : 1.f, beta ? __ldg(beta + f) : 0.f);
+        if (xhat) xhat[(int64_t)q * Hd + f] = xh;
         float a = fmaxf(y, 0.f);
-        if (drop.scale != 0.f) a = drop_apply(a, (uint64_t)((int64_t)q * Hd + f0 + f), drop);
-        act[(int64_t)q * Hd + f0 + f] = a;
+        if (drop.scale != 0.f) a = drop_apply(a, (uint64_t)((int64_t)q * Hd + f), drop);
+        act[(int64_t)q * Hd + f] = a;
     }
 }
 
@@ -333,7 +330,7 @@ int bighead_fwd(const float* x, const float* W1, const float* b1, const float* g
     const dim3 grid((unsigned)P, (unsigned)ceil_div(Hd, kBhFwdRows));
     bighead_fc1_kernel<<<grid, kBhThreads, 0, st>>>(x, W1, partial, Q, I, Hd);
     TGCN_LAUNCH_CHECK("bighead_fc1");
-    bighead_bn_kernel<<<(unsigned)ceil_div(Hd, kBhBnF), kBhThreads, 0, st>>>(partial, P, b1, gamma, beta, running_mean, running_var,
+    bighead_bn_kernel<<<(unsigned)Hd, kBhThreads, 0, st>>>(partial, P, b1, gamma, beta, running_mean, running_var,
                                                                             momentum, eps, training, act, xhat, invstd, Q, Hd,
                                                                             drop_p, drop_seed, drop_step);
     TGCN_LAUNCH_CHECK("bighead_bn");

@@ -651,6 +651,7 @@ int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias,
     const size_t wtotal = (size_t)K * p.DB * p.wunit;
     const size_t fixed = 1024 + 256;
     p.w_resident = (wtotal <= 96 * 1024) ? 1 : 0;
+    if (const char* e = getenv("TGCN_T3_WRES")) p.w_resident = (atoi(e) != 0 && wtotal <= 96 * 1024) ? 1 : 0;
     const size_t stage = 2 * (size_t)kT3Tile + (p.w_resident ? 0 : p.wunit);
     int NS = (int)((kT3SmemLimit - fixed - (p.w_resident ? wtotal : 0)) / stage);
     if (NS > kT3MaxStages) NS = kT3MaxStages;
