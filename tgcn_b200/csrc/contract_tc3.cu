@@ -28,8 +28,6 @@
 namespace tgcn {
 using namespace tc;
 
-constexpr int kT3Threads = 448;            // producer, MMA, 4 epilogue, 8 transform warps
-constexpr int kT3TransformWarp0 = 6;
 constexpr int kT3TransformWarps = 8;
 constexpr int kT3MaxStages = 6;
 constexpr uint32_t kT3Tile = 128 * 128;    // one [128 x 32 fp32] operand tile
@@ -110,17 +108,58 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& x) {
 // ------------------------------------------------------------------------------------------------
 // forward:  out[m, g] = sum_j sum_d P_j[m, d] W'_j[d, g] + bias
 // unit u = (order j, column block db) of a row tile: one [128 x 32] TMA tile of the stack
+//
+// What the first version of this kernel taught (profiles/r02/contract_tc3_notes.txt): with G = 32 filters every
+// tcgen05.mma is tiny (128 x 32 x 8: ~16 tensor-pipe cycles) and ONE issuing thread could not feed them -- its own
+// instruction stream (descriptor arithmetic, two barrier polls, 12 MMAs and a commit per unit, ~1600 cycles) was the
+// pace of the whole kernel (tensor pipe 13 % busy, DRAM 35 %, no stage-count sensitivity).  Hence:
+//   * the hi part is multiplied by [W_hi ; W_lo] in ONE MMA of N = 2 GP (the weight image stores the lo rows right
+//     behind the hi rows, so both are one K-major B tile): 2 MMAs per k-step instead of 3, columns [GP, 2 GP) of the
+//     accumulator hold hi * W_lo and are added in the epilogue;
+//   * NI issuer warps take the units round-robin, each with its own TMEM accumulator (no ordering between issuers is
+//     needed; the epilogue adds the NI partial sums in a fixed order);
+//   * the hot-loop barrier waits carry no clock reads.
 // ------------------------------------------------------------------------------------------------
+constexpr int kT3Issuers = 4;              // issuer warps 1..4 (NI <= 4 of them active)
+constexpr int kT3EpiWarp0 = 1 + kT3Issuers;
+constexpr int kT3TransformWarp0F = kT3EpiWarp0 + 4;
+constexpr int kT3ThreadsF = (kT3TransformWarp0F + kT3TransformWarps) * 32;     // 17 warps = 544 threads
+
+// bounded poll without clock reads (hot loops): ~2^28 polls, then trap
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > (1u << 28)) __trap();
+    }
+}
+
 struct Fwd3Params {
     const uint8_t* wimg;           // per unit: [hi | lo] x [GP rows x 128 B], K-major SWIZZLE_128B image
     const float* bias; int bias_mode;
     float* out;
     int M, Q, N, G, GP, K, DB;     // DB = Dp / 32 column blocks per order
     int ntiles, NS, w_resident;
+    int NI;                        // active MMA issuer warps = TMEM accumulators per row-tile buffer
+    int NSi;                       // stages owned by each issuer (NS = NI * NSi)
     uint32_t wunit;                // bytes of one weight image: 2 * GP * 128
 };
 
-__global__ void __launch_bounds__(kT3Threads, 1)
+// Stage of unit u of the CTA's ti-th row tile.  Every issuer owns its own NSi stages and barriers: a parity wait is
+// only sound for a waiter that sees EVERY phase of its barrier, and an issuer only sees the units it multiplies
+// (with one shared ring, an issuer that skips units would wait on a phase two ahead and be released by the
+// intermediate one of the same parity).  c = running count of the issuer's units.
+struct StagePos { uint32_t s, ph; };
+__device__ __forceinline__ StagePos fwd3_stage(int ti, int u, int units, int NI, int NSi) {
+    const int i = u % NI;
+    const int per_tile = (units - i + NI - 1) / NI;          // units of issuer i in one row tile
+    const uint32_t c = (uint32_t)(ti * per_tile + u / NI);
+    StagePos r;
+    r.s = (uint32_t)(i * NSi) + c % (uint32_t)NSi;
+    r.ph = (c / (uint32_t)NSi) & 1u;
+    return r;
+}
+
+__global__ void __launch_bounds__(kT3ThreadsF, 1)
 contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Params p) {
     extern __shared__ uint8_t smem_raw3[];
     uint8_t* smem = align1024_3(smem_raw3);
@@ -128,15 +167,16 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int NS = p.NS, units = p.K * p.DB;
+    const int NS = p.NS, units = p.K * p.DB, NI = p.NI;
     const uint32_t stage_bytes = 2 * kT3Tile + (p.w_resident ? 0u : p.wunit);
     uint8_t* stage0 = smem;
     uint8_t* wres = smem + (size_t)NS * stage_bytes;                  // resident weight images (w_resident)
-    const uint32_t ncols = tmem_cols_pow2(2u * (uint32_t)p.GP);
+    const uint32_t accw = (uint32_t)(NI * 2 * p.GP);                  // TMEM columns of one row-tile buffer
+    const uint32_t ncols = tmem_cols_pow2(2u * accw);
 
     if (tid == 0) {
         for (int i = 0; i < kT3MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&lo_ready[i], kT3TransformWarps); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], (uint32_t)NI); mbar_init(&acc_empty[i], 4); }
         mbar_init(&w_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmA);
@@ -156,12 +196,13 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
                 for (uint32_t off = 0; off < wtotal; off += 32768u)
                     bulk_g2s(wres + off, p.wimg + off, min(32768u, wtotal - off), &w_full);
             }
-            uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            int ti = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
                 const int m0 = tile * 128;
-                for (int u = 0; u < units; ++u, ++g) {
-                    const uint32_t s = g % (uint32_t)NS;
-                    if (g >= (uint32_t)NS) mbar_wait(&empty[s], ((g / NS) - 1) & 1);
+                for (int u = 0; u < units; ++u) {
+                    const StagePos sp = fwd3_stage(ti, u, units, NI, p.NSi);
+                    const uint32_t s = sp.s;
+                    mbar_wait_hot(&empty[s], sp.ph ^ 1u);            // first use: parity 1 passes on a fresh barrier
                     uint8_t* st = stage0 + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full[s], kT3Tile + (p.w_resident ? 0u : p.wunit));
                     const int j = u / p.DB, db = u - j * p.DB;
@@ -170,40 +211,46 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.GP, 0, 0);
+    } else if (warp < kT3EpiWarp0) {
+        // ===================== MMA issuers: issuer i takes the units u = i, i + NI, ... of every row tile =====================
+        const int i = warp - 1;
+        if (lane == 0 && i < NI) {
+            const uint32_t idesc2 = make_idesc_tf32(128, 2u * (uint32_t)p.GP, 0, 0);     // hi x [W_hi ; W_lo]
+            const uint32_t idesc1 = make_idesc_tf32(128, (uint32_t)p.GP, 0, 0);          // lo x W_hi
             if (p.w_resident) mbar_wait(&w_full, 0);
-            uint32_t g = 0, ti = 0;
+            const uint64_t desc_stage0 = make_desc_kmajor(smem_u32(stage0));
+            const uint64_t desc_w0 = make_desc_kmajor(smem_u32(p.w_resident ? wres : stage0 + 2 * kT3Tile));
+            const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), w_step = (uint64_t)(p.wunit >> 4);
+            uint32_t ti = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
                 const uint32_t a = ti & 1u;
-                if (ti >= 2) mbar_wait(&acc_empty[a], ((ti >> 1) - 1) & 1);        // the epilogue drained this buffer
+                if (ti >= 2) mbar_wait_hot(&acc_empty[a], ((ti >> 1) - 1) & 1);          // the epilogue drained this buffer
                 tcgen05_fence_after();
-                const uint32_t acc = tmem_base + a * (uint32_t)p.GP;
-                for (int u = 0; u < units; ++u, ++g) {
-                    const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
-                    mbar_wait(&full[s], ph);
-                    mbar_wait(&lo_ready[s], ph);
+                const uint32_t acc = tmem_base + a * accw + (uint32_t)(i * 2 * p.GP);
+                uint32_t fresh = 0u;                                                      // accumulate flag of the next hi MMA
+                for (int u = i; u < units; u += NI) {
+                    const StagePos sp = fwd3_stage((int)ti, u, units, NI, p.NSi);
+                    const uint32_t s = sp.s, ph = sp.ph;
+                    mbar_wait_hot(&full[s], ph);
+                    mbar_wait_hot(&lo_ready[s], ph);
                     tcgen05_fence_after();
-                    uint8_t* st = stage0 + (size_t)s * stage_bytes;
-                    const uint8_t* wu = p.w_resident ? wres + (size_t)u * p.wunit : st + 2 * kT3Tile;
-                    const uint64_t dah = make_desc_kmajor(smem_u32(st)), dal = make_desc_kmajor(smem_u32(st + kT3Tile));
-                    const uint64_t dbh = make_desc_kmajor(smem_u32(wu)), dbl = make_desc_kmajor(smem_u32(wu + p.wunit / 2));
+                    const uint64_t dah = desc_stage0 + (uint64_t)s * stage_step;          // raw tile = hi operand
+                    const uint64_t dal = dah + (uint64_t)(kT3Tile >> 4);
+                    const uint64_t dbw = p.w_resident ? desc_w0 + (uint64_t)u * w_step : desc_w0 + (uint64_t)s * stage_step;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);                   // 32 bytes along K, in 16-byte units
-                        umma_tf32(acc, dal + adv, dbh + adv, idesc, (u | ks) ? 1u : 0u);
-                        umma_tf32(acc, dah + adv, dbl + adv, idesc, 1u);
-                        umma_tf32(acc, dah + adv, dbh + adv, idesc, 1u);
+                        const uint64_t adv = (uint64_t)(ks * 2);                          // 32 bytes along K, in 16-byte units
+                        umma_tf32(acc, dah + adv, dbw + adv, idesc2, fresh);
+                        umma_tf32(acc, dal + adv, dbw + adv, idesc1, 1u);
+                        fresh = 1u;
                     }
                     umma_commit(&empty[s]);
                 }
                 umma_commit(&acc_full[a]);
             }
         }
-    } else if (warp < kT3TransformWarp0) {
-        // ===================== epilogue (warp e owns TMEM lanes [32 e', 32 e' + 32), e' = warp % 4) =====================
+    } else if (warp < kT3TransformWarp0F) {
+        // ===================== epilogue (TMEM lane quarter = warp % 4) =====================
         const int lq = warp & 3;
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
@@ -216,39 +263,41 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
             if (live) { n = m / p.Q; q = m - n * p.Q; }
             float* dst = p.out + ((int64_t)q * p.N + n) * p.G;
             const bool vec = (p.G % 4 == 0) && aligned16(p.out);
-            for (int cb = 0; cb < p.GP; cb += 32) {
-                float v[32];
-                if (p.GP - cb >= 32) {
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * (uint32_t)p.GP + (uint32_t)cb, v);
-                } else {
-                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + a * (uint32_t)p.GP + (uint32_t)cb, v);
+            for (int cb = 0; cb < p.GP; cb += 16) {                                 // GP is a multiple of 16
+                float v[16];
+                const uint32_t tcol = tmem_base + ((uint32_t)(lq * 32) << 16) + a * accw + (uint32_t)cb;
+                tmem_ld16(tcol, v);
+                for (int k = 1; k < 2 * NI; ++k) {                                 // fixed order: issuer 0 (hi*Wh+lo*Wh, hi*Wl), issuer 1, ...
+                    float w[16];
+                    tmem_ld16(tcol + (uint32_t)(k * p.GP), w);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += w[e];
                 }
-                const int ncol = min(32, p.GP - cb);
                 if (!live) continue;
                 if (p.bias_mode == TGCN_BIAS_PER_VERTEX) {
                     const float* b = p.bias + (int64_t)n * p.G + cb;
                     if (vec) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            if (i < ncol && cb + i < p.G) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(b + i));
-                                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+                        for (int e = 0; e < 16; e += 4)
+                            if (cb + e < p.G) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(b + e));
+                                v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
                             }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) v[i] += __ldg(b + i);
+                        for (int e = 0; e < 16; ++e) if (cb + e < p.G) v[e] += __ldg(b + e);
                     }
                 } else if (p.bias_mode == TGCN_BIAS_PER_FILTER) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) v[i] += __ldg(p.bias + cb + i);
+                    for (int e = 0; e < 16; ++e) if (cb + e < p.G) v[e] += __ldg(p.bias + cb + e);
                 }
                 if (vec) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        if (i < ncol && cb + i < p.G) *reinterpret_cast<float4*>(dst + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int e = 0; e < 16; e += 4)
+                        if (cb + e < p.G) *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.G) dst[cb + i] = v[i];
+                    for (int e = 0; e < 16; ++e) if (cb + e < p.G) dst[cb + e] = v[e];
                 }
             }
             tcgen05_fence_before();
@@ -257,23 +306,24 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
         }
     } else {
         // ===================== transform: lo tile from the raw (= hi) tile =====================
-        const int t = tid - kT3TransformWarp0 * 32;                   // 0..255
+        const int t = tid - kT3TransformWarp0F * 32;                  // 0..255
         const uint32_t base_u32 = smem_u32(stage0);
-        uint32_t g = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            for (int u = 0; u < units; ++u, ++g) {
-                const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
-                mbar_wait(&full[s], ph);
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+            for (int u = 0; u < units; ++u) {
+                const StagePos sp = fwd3_stage(ti, u, units, NI, p.NSi);
+                const uint32_t s = sp.s, ph = sp.ph;
+                mbar_wait_hot(&full[s], ph);
                 const uint32_t src = base_u32 + s * stage_bytes + (uint32_t)t * 16u;
                 float4 x[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
-                                 : "r"(src + (uint32_t)i * 4096u));
+                for (int e = 0; e < 4; ++e)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[e].x), "=f"(x[e].y), "=f"(x[e].z), "=f"(x[e].w)
+                                 : "r"(src + (uint32_t)e * 4096u));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 l = tf32_lo4(x[i]);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)i * 4096u), "f"(l.x), "f"(l.y),
+                for (int e = 0; e < 4; ++e) {
+                    const float4 l = tf32_lo4(x[e]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)e * 4096u), "f"(l.x), "f"(l.y),
                                  "f"(l.z), "f"(l.w) : "memory");
                 }
                 fence_proxy_async_smem();
@@ -294,32 +344,36 @@ contract_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const Fwd3Param
 // weight images through a small ring; the accumulator of order j drains (TMEM -> 16-byte stores of the slab rows)
 // while order j + 1 multiplies.
 // ------------------------------------------------------------------------------------------------
-constexpr int kX3WRing = 3;
+constexpr int kX3WRing = 4;
 
 struct BwdX3Params {
     const uint8_t* wimg;           // per (j, gb): [hi | lo] x [DP rows (d) x 128 B (32 g)], K-major SWIZZLE_128B
     float* gstack;                 // [K][M][D]
     int M, Q, N, D, DP, G, GB, K, nt;      // nt = 128 / Q vertices per tile
-    int ntiles, abufs;
+    int ntiles, abufs, NI;
     uint32_t wunit;                // bytes of one order's images: GB * 2 * DP * 128
 };
 
-__global__ void __launch_bounds__(kT3Threads, 1)
+// Issuer i multiplies the orders j = i, i + NI, ... of every row tile, alternating between its own two TMEM
+// accumulators [128 x 2 DP] (hi x [W_hi ; W_lo] in one MMA of N = 2 DP, then lo x W_hi into the first DP columns).
+__global__ void __launch_bounds__(kT3ThreadsF, 1)
 contract_bwd_x_tc3_kernel(const __grid_constant__ CUtensorMap tmD, const BwdX3Params p) {
     extern __shared__ uint8_t smem_raw3[];
     uint8_t* smem = align1024_3(smem_raw3);
-    __shared__ __align__(8) uint64_t a_full[2], a_lo[2], a_empty[2], w_full[kX3WRing], w_empty[kX3WRing], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_full[2], a_lo[2], a_empty[2], w_full[kX3WRing], w_empty[kX3WRing];
+    __shared__ __align__(8) uint64_t acc_full[kT3Issuers][2], acc_empty[kT3Issuers][2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NI = p.NI;
     const uint32_t abytes = (uint32_t)p.GB * 2u * kT3Tile;            // one A buffer: GB x [raw | lo]
     uint8_t* abase = smem;
     uint8_t* wbase = smem + (size_t)p.abufs * abytes;
-    const uint32_t ncols = tmem_cols_pow2(2u * (uint32_t)p.DP);
+    const uint32_t accw = 2u * (uint32_t)p.DP;                        // columns of one accumulator
+    const uint32_t ncols = tmem_cols_pow2(2u * (uint32_t)NI * accw);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_lo[i], kT3TransformWarps); mbar_init(&a_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
-        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_lo[i], kT3TransformWarps); mbar_init(&a_empty[i], (uint32_t)NI); }
+        for (int i = 0; i < kT3Issuers; ++i)
+            for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[i][b], 1); mbar_init(&acc_empty[i][b], 4); }
         for (int i = 0; i < kX3WRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         fence_mbar_init();
         tma_prefetch_desc(&tmD);
@@ -335,7 +389,7 @@ contract_bwd_x_tc3_kernel(const __grid_constant__ CUtensorMap tmD, const BwdX3Pa
         if (lane == 0) {
             auto load_a = [&](uint32_t ti, int tile) {
                 const uint32_t ab = ti % AB;
-                if (ti >= AB) mbar_wait(&a_empty[ab], ((ti / AB) - 1) & 1);
+                if (ti >= AB) mbar_wait_hot(&a_empty[ab], ((ti / AB) - 1) & 1);
                 mbar_arrive_expect_tx(&a_full[ab], (uint32_t)p.GB * kT3Tile);
                 for (int gb = 0; gb < p.GB; ++gb)
                     tma_load_3d(abase + (size_t)ab * abytes + (size_t)gb * 2 * kT3Tile, &tmD, gb * 32, tile * p.nt, 0, &a_full[ab]);
@@ -345,103 +399,115 @@ contract_bwd_x_tc3_kernel(const __grid_constant__ CUtensorMap tmD, const BwdX3Pa
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
                 if (AB > 1 && tile + (int)gridDim.x < p.ntiles) load_a(ti + 1, tile + gridDim.x);
                 for (int j = 0; j < p.K; ++j, ++gw) {
-                    const uint32_t ws = gw % kX3WRing;
-                    if (gw >= kX3WRing) mbar_wait(&w_empty[ws], ((gw / kX3WRing) - 1) & 1);
+                    // weight-image slots are owned per issuer (see fwd3_stage): slot and phase from the issuer's job count
+                    const StagePos wp = fwd3_stage((int)ti, j, p.K, NI, kX3WRing / NI);
+                    const uint32_t ws = wp.s;
+                    mbar_wait_hot(&w_empty[ws], wp.ph ^ 1u);
                     mbar_arrive_expect_tx(&w_full[ws], p.wunit);
                     bulk_g2s(wbase + (size_t)ws * p.wunit, p.wimg + (size_t)j * p.wunit, p.wunit, &w_full[ws]);
                 }
                 if (AB == 1 && tile + (int)gridDim.x < p.ntiles) load_a(ti + 1, tile + gridDim.x);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.DP, 0, 0);
-            const uint32_t whalf = (uint32_t)p.DP * kRowBytes;         // hi image of one (j, gb), lo follows
-            uint32_t ti = 0, gw = 0;
+    } else if (warp < kT3EpiWarp0) {
+        const int i = warp - 1;
+        if (lane == 0 && i < NI) {
+            const uint32_t idesc2 = make_idesc_tf32(128, 2u * (uint32_t)p.DP, 0, 0);
+            const uint32_t idesc1 = make_idesc_tf32(128, (uint32_t)p.DP, 0, 0);
+            const uint64_t whalf = (uint64_t)(((uint32_t)p.DP * kRowBytes) >> 4);     // hi image of one (j, gb); lo follows
+            const uint64_t desc_a0 = make_desc_kmajor(smem_u32(abase)), desc_w0 = make_desc_kmajor(smem_u32(wbase));
+            uint32_t ti = 0, cnt = 0;                                                 // cnt: jobs this issuer has done
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
                 const uint32_t ab = ti % AB, aph = (ti / AB) & 1;
-                mbar_wait(&a_full[ab], aph);
-                mbar_wait(&a_lo[ab], aph);
-                uint8_t* at = abase + (size_t)ab * abytes;
-                for (int j = 0; j < p.K; ++j, ++gw) {
-                    const uint32_t ws = gw % kX3WRing, acb = gw & 1u;
-                    mbar_wait(&w_full[ws], (gw / kX3WRing) & 1);
-                    if (gw >= 2) mbar_wait(&acc_empty[acb], ((gw >> 1) - 1) & 1);
+                mbar_wait_hot(&a_full[ab], aph);
+                mbar_wait_hot(&a_lo[ab], aph);
+                const uint64_t dat = desc_a0 + (uint64_t)ab * (uint64_t)(abytes >> 4);
+                for (int j = i; j < p.K; j += NI, ++cnt) {
+                    const StagePos wp = fwd3_stage((int)ti, j, p.K, NI, kX3WRing / NI);
+                    const uint32_t ws = wp.s, acb = cnt & 1u;
+                    mbar_wait_hot(&w_full[ws], wp.ph);
+                    if (cnt >= 2) mbar_wait_hot(&acc_empty[i][acb], ((cnt >> 1) - 1) & 1);
                     tcgen05_fence_after();
-                    const uint32_t acc = tmem_base + acb * (uint32_t)p.DP;
-                    const uint8_t* wu = wbase + (size_t)ws * p.wunit;
+                    const uint32_t acc = tmem_base + ((uint32_t)i * 2u + acb) * accw;
+                    const uint64_t dw = desc_w0 + (uint64_t)ws * (uint64_t)(p.wunit >> 4);
+                    uint32_t fresh = 0u;
                     for (int gb = 0; gb < p.GB; ++gb) {
-                        const uint64_t dah = make_desc_kmajor(smem_u32(at + (size_t)gb * 2 * kT3Tile));
-                        const uint64_t dal = make_desc_kmajor(smem_u32(at + (size_t)gb * 2 * kT3Tile + kT3Tile));
-                        const uint64_t dbh = make_desc_kmajor(smem_u32(wu + (size_t)gb * 2 * whalf));
-                        const uint64_t dbl = make_desc_kmajor(smem_u32(wu + (size_t)gb * 2 * whalf + whalf));
+                        const uint64_t dah = dat + (uint64_t)gb * (uint64_t)((2 * kT3Tile) >> 4);
+                        const uint64_t dal = dah + (uint64_t)(kT3Tile >> 4);
+                        const uint64_t dbw = dw + (uint64_t)gb * 2u * whalf;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);
-                            umma_tf32(acc, dal + adv, dbh + adv, idesc, (gb | ks) ? 1u : 0u);
-                            umma_tf32(acc, dah + adv, dbl + adv, idesc, 1u);
-                            umma_tf32(acc, dah + adv, dbh + adv, idesc, 1u);
+                            umma_tf32(acc, dah + adv, dbw + adv, idesc2, fresh);
+                            umma_tf32(acc, dal + adv, dbw + adv, idesc1, 1u);
+                            fresh = 1u;
                         }
                     }
                     umma_commit(&w_empty[ws]);
-                    umma_commit(&acc_full[acb]);
+                    umma_commit(&acc_full[i][acb]);
                 }
                 umma_commit(&a_empty[ab]);
             }
         }
-    } else if (warp < kT3TransformWarp0) {
+    } else if (warp < kT3TransformWarp0F) {
         const int lq = warp & 3;
         const int r = lq * 32 + lane;                                  // row of the tile: sample-major (q, vertex)
         const int q = r / p.nt, nl = r - q * p.nt;
         const bool vec = (p.D % 4 == 0) && aligned16(p.gstack);
-        uint32_t gw = 0;
+        uint32_t cnt[kT3Issuers] = {0u, 0u, 0u, 0u};
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const int n = tile * p.nt + nl;
             const bool live = n < p.N;
             const int64_t m = (int64_t)n * p.Q + q;
-            for (int j = 0; j < p.K; ++j, ++gw) {
-                const uint32_t acb = gw & 1u;
-                mbar_wait(&acc_full[acb], (gw >> 1) & 1);
+            for (int j = 0; j < p.K; ++j) {
+                const int i = j % NI;
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < kT3Issuers; ++k) if (k == i) { c = cnt[k]; cnt[k] = c + 1; }
+                const uint32_t acb = c & 1u;
+                mbar_wait(&acc_full[i][acb], (c >> 1) & 1);
                 tcgen05_fence_after();
                 float* dst = p.gstack + ((int64_t)j * p.M + m) * p.D;
-                for (int cb = 0; cb < p.DP; cb += 32) {
-                    float v[32];
-                    if (p.DP - cb >= 32) tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acb * (uint32_t)p.DP + (uint32_t)cb, v);
-                    else tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + acb * (uint32_t)p.DP + (uint32_t)cb, v);
+                const uint32_t tcol0 = tmem_base + ((uint32_t)(lq * 32) << 16) + ((uint32_t)i * 2u + acb) * accw;
+                for (int cb = 0; cb < p.DP; cb += 16) {
+                    float v[16], w[16];
+                    tmem_ld16(tcol0 + (uint32_t)cb, v);
+                    tmem_ld16(tcol0 + (uint32_t)(p.DP + cb), w);
                     if (!live) continue;
-                    const int ncol = min(32, p.DP - cb);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += w[e];
                     if (vec) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            if (i < ncol && cb + i < p.D) *reinterpret_cast<float4*>(dst + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int e = 0; e < 16; e += 4)
+                            if (cb + e < p.D) *reinterpret_cast<float4*>(dst + cb + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (i < ncol && cb + i < p.D) dst[cb + i] = v[i];
+                        for (int e = 0; e < 16; ++e) if (cb + e < p.D) dst[cb + e] = v[e];
                     }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acb]);
+                if (lane == 0) mbar_arrive(&acc_empty[i][acb]);
             }
         }
     } else {
-        const int t = tid - kT3TransformWarp0 * 32;
+        const int t = tid - kT3TransformWarp0F * 32;
         const uint32_t base_u32 = smem_u32(abase);
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
             const uint32_t ab = ti % AB;
-            mbar_wait(&a_full[ab], (ti / AB) & 1);
+            mbar_wait_hot(&a_full[ab], (ti / AB) & 1);
             for (int gb = 0; gb < p.GB; ++gb) {
                 const uint32_t src = base_u32 + ab * abytes + (uint32_t)gb * 2u * kT3Tile + (uint32_t)t * 16u;
                 float4 x[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
-                                 : "r"(src + (uint32_t)i * 4096u));
+                for (int e = 0; e < 4; ++e)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[e].x), "=f"(x[e].y), "=f"(x[e].z), "=f"(x[e].w)
+                                 : "r"(src + (uint32_t)e * 4096u));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 l = tf32_lo4(x[i]);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)i * 4096u), "f"(l.x), "f"(l.y),
+                for (int e = 0; e < 4; ++e) {
+                    const float4 l = tf32_lo4(x[e]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + kT3Tile + (uint32_t)e * 4096u), "f"(l.x), "f"(l.y),
                                  "f"(l.z), "f"(l.w) : "memory");
                 }
             }
@@ -461,18 +527,20 @@ contract_bwd_x_tc3_kernel(const __grid_constant__ CUtensorMap tmD, const BwdX3Pa
 // and 32-column block, a [RU x 32 fp32] TMA tile in SWIZZLE_128B_ATOM_32B layout -- the layout tcgen05 reads
 // MN-major tf32 operands in (SWIZZLE_128B_BASE32B) -- and the dOut rows of the unit arrive through a 3-D box over
 // dOut[Q][N][G] whose strides are given vertex-major, so its rows come out in the same (vertex, sample) order.
-// Four 32-wide blocks form one 128-row output tile; accumulators for all of a CTA's blocks live in TMEM for the
-// whole kernel and are written once, as a per-CTA partial that reduce_partials sums in a fixed order.
+// Four 32-wide blocks form one 128-row output tile [128 x 2 GPw] (hi^T x [dOut_hi | dOut_lo] in one MMA, lo^T x
+// dOut_hi into the first GPw columns); the output tiles are dealt to the issuer warps (tile t -> issuer t mod NI),
+// accumulate in TMEM for the whole kernel and are written once, as a per-CTA partial that reduce_partials sums in
+// a fixed order.
 // ------------------------------------------------------------------------------------------------
 struct BwdW3Params {
     float* partial;                // [P][K*D][G]
     int M, Q, N, D, G, GPw, K, DB;
     int NB;                        // 32-wide (order, column block) pairs handled per CTA (grid.y splits the rest)
     int MT;                        // output tiles per CTA = ceil(NB / 4)
-    int RU, NS, units_per_cta, total_units;
+    int RU, NS, NI, units_per_cta, total_units;
 };
 
-__global__ void __launch_bounds__(kT3Threads, 1)
+__global__ void __launch_bounds__(kT3ThreadsF, 1)
 contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD, const BwdW3Params p) {
     extern __shared__ uint8_t smem_raw3[];
     uint8_t* smem = align1024_3(smem_raw3);
@@ -481,26 +549,30 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t blk = (uint32_t)p.RU * kRowBytes;                  // one 32-wide block of RU reduction rows
     const int GBk = p.GPw / 32;
-    const uint32_t a_part = (uint32_t)p.MT * 4u * blk;                // hi (= raw) blocks of A, tile-padded
+    // hi (= raw) blocks of A.  The last output tile may own fewer than 4 blocks: its MMA then also reads the blocks that
+    // follow in the stage (finite or not, they only reach accumulator rows that are never stored), so no padding blocks
+    // are allocated.
+    const uint32_t a_part = (uint32_t)p.NB * blk;
     const uint32_t b_part = (uint32_t)GBk * blk;
     const uint32_t stage_bytes = 2u * a_part + 2u * b_part;           // [A hi | A lo | B hi | B lo]
-    const uint32_t ncols = tmem_cols_pow2((uint32_t)(p.MT * p.GPw));
+    const uint32_t accw = 2u * (uint32_t)p.GPw;
+    const uint32_t ncols = tmem_cols_pow2((uint32_t)p.MT * accw);
     const int blk0 = blockIdx.y * p.NB;                               // first (order, column block) pair of this CTA
     const int nb = min(p.NB, p.K * p.DB - blk0);
     const int u_begin = blockIdx.x * p.units_per_cta;
     const int u_end = min(p.total_units, u_begin + p.units_per_cta);
-    const int NS = p.NS;
+    const int NS = p.NS, NI = p.NI;
 
     if (tid == 0) {
-        for (int i = 0; i < kT3MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&lo_ready[i], kT3TransformWarps); mbar_init(&empty[i], 1); }
-        mbar_init(&acc_full, 1);
+        for (int i = 0; i < kT3MaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&lo_ready[i], kT3TransformWarps); mbar_init(&empty[i], (uint32_t)NI); }
+        mbar_init(&acc_full, (uint32_t)NI);
         fence_mbar_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmD);
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
-    // zero the stages once: the padding blocks of the last output tile (and filters >= G) are never written
-    for (uint32_t i = tid; i < (uint32_t)NS * stage_bytes / 16; i += kT3Threads) reinterpret_cast<float4*>(smem)[i] = make_float4(0, 0, 0, 0);
+    // zero the stages once (+ the slack a last, partly filled output tile reads behind its stage)
+    for (uint32_t i = tid; i < ((uint32_t)NS * stage_bytes + 4u * blk) / 16; i += kT3ThreadsF) reinterpret_cast<float4*>(smem)[i] = make_float4(0, 0, 0, 0);
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
@@ -513,7 +585,7 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             uint32_t g = 0;
             for (int u = u_begin; u < u_end; ++u, ++g) {
                 const uint32_t s = g % (uint32_t)NS;
-                if (g >= (uint32_t)NS) mbar_wait(&empty[s], ((g / NS) - 1) & 1);
+                if (g >= (uint32_t)NS) mbar_wait_hot(&empty[s], ((g / NS) - 1) & 1);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(nb + gblocks) * blk);
                 const int m0 = u * p.RU;
@@ -525,38 +597,35 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     tma_load_3d(st + 2 * (size_t)a_part + (size_t)gb * blk, &tmD, gb * 32, 0, m0 / p.Q, &full[s]);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.GPw, 1, 1);
+    } else if (warp < kT3EpiWarp0) {
+        const int i = warp - 1;
+        if (lane == 0 && i < NI) {
+            const uint32_t idesc2 = make_idesc_tf32(128, 2u * (uint32_t)p.GPw, 1, 1);
+            const uint32_t idesc1 = make_idesc_tf32(128, (uint32_t)p.GPw, 1, 1);
+            const uint64_t desc0 = make_desc_mnmajor(smem_u32(smem), blk);
             uint32_t g = 0;
             for (int u = u_begin; u < u_end; ++u, ++g) {
                 const uint32_t s = g % (uint32_t)NS, ph = (g / NS) & 1;
-                mbar_wait(&full[s], ph);
-                mbar_wait(&lo_ready[s], ph);
+                mbar_wait_hot(&full[s], ph);
+                mbar_wait_hot(&lo_ready[s], ph);
                 tcgen05_fence_after();
-                uint8_t* ah = smem + (size_t)s * stage_bytes;
-                uint8_t* al = ah + a_part;
-                uint8_t* bh = ah + 2 * (size_t)a_part;
-                uint8_t* bl = bh + b_part;
-                for (int t = 0; t < p.MT; ++t) {
-                    const uint32_t acc = tmem_base + (uint32_t)(t * p.GPw);
-                    const uint32_t aoff = (uint32_t)t * 4u * blk;
+                const uint64_t dst0 = desc0 + (uint64_t)s * (uint64_t)(stage_bytes >> 4);
+                const uint64_t dbh = dst0 + (uint64_t)((2u * a_part) >> 4);              // [B hi blocks | B lo blocks]: N = 2 GPw
+                for (int t = i; t < p.MT; t += NI) {
+                    const uint32_t acc = tmem_base + (uint32_t)t * accw;
+                    const uint64_t dah = dst0 + (uint64_t)(((uint32_t)t * 4u * blk) >> 4);
+                    const uint64_t dal = dah + (uint64_t)(a_part >> 4);
                     for (int ks = 0; ks < p.RU / 8; ++ks) {
-                        const uint32_t adv = (uint32_t)ks * kAtomBytes;           // next 8 reduction rows
-                        const uint64_t dah = make_desc_mnmajor(smem_u32(ah + aoff + adv), blk);
-                        const uint64_t dal = make_desc_mnmajor(smem_u32(al + aoff + adv), blk);
-                        const uint64_t dbh = make_desc_mnmajor(smem_u32(bh + adv), blk);
-                        const uint64_t dbl = make_desc_mnmajor(smem_u32(bl + adv), blk);
-                        umma_tf32(acc, dal, dbh, idesc, (g | (uint32_t)ks) ? 1u : 0u);
-                        umma_tf32(acc, dah, dbl, idesc, 1u);
-                        umma_tf32(acc, dah, dbh, idesc, 1u);
+                        const uint64_t adv = (uint64_t)(((uint32_t)ks * kAtomBytes) >> 4);   // next 8 reduction rows
+                        umma_tf32(acc, dah + adv, dbh + adv, idesc2, (g | (uint32_t)ks) ? 1u : 0u);
+                        umma_tf32(acc, dal + adv, dbh + adv, idesc1, 1u);
                     }
                 }
                 umma_commit(&empty[s]);
             }
             umma_commit(&acc_full);
         }
-    } else if (warp < kT3TransformWarp0) {
+    } else if (warp < kT3TransformWarp0F) {
         // ===================== epilogue: partial[blockIdx.x][(j, d)][g] =====================
         const int lq = warp & 3;
         float* dst_base = p.partial + (int64_t)blockIdx.x * p.K * p.D * p.G;
@@ -567,28 +636,30 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 const int b = t * 4 + lq;                                  // block of this lane quarter
                 const bool ok = b < nb;
                 float* dst = dst_base + ((int64_t)(blk0 + b) * 32 + lane) * p.G;
-                for (int cb = 0; cb < p.GPw; cb += 32) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.GPw + cb), v);
+                for (int cb = 0; cb < p.GPw; cb += 16) {
+                    float v[16], w[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)t * accw + (uint32_t)cb, v);
+                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)t * accw + (uint32_t)(p.GPw + cb), w);
                     if (ok) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (cb + i < p.G) dst[cb + i] = v[i];
+                        for (int e = 0; e < 16; ++e)
+                            if (cb + e < p.G) dst[cb + e] = v[e] + w[e];
                     }
                 }
             }
         } else {
-            for (int i = tid - 64; i < nb * 32 * p.G; i += 128) dst_base[(int64_t)blk0 * 32 * p.G + i] = 0.f;
+            const int t0 = tid - kT3EpiWarp0 * 32;
+            for (int e = t0; e < nb * 32 * p.G; e += 128) dst_base[(int64_t)blk0 * 32 * p.G + e] = 0.f;
         }
     } else {
         // ===================== transform: lo parts of the A blocks and of the dOut blocks =====================
-        const int t = tid - kT3TransformWarp0 * 32;
+        const int t = tid - kT3TransformWarp0F * 32;
         const uint32_t base_u32 = smem_u32(smem);
         const uint32_t a_f4 = (uint32_t)nb * blk / 16u, b_f4 = (uint32_t)gblocks * blk / 16u;
         uint32_t g = 0;
         for (int u = u_begin; u < u_end; ++u, ++g) {
             const uint32_t s = g % (uint32_t)NS;
-            mbar_wait(&full[s], (g / NS) & 1);
+            mbar_wait_hot(&full[s], (g / NS) & 1);
             const uint32_t st = base_u32 + s * stage_bytes;
             for (uint32_t i0 = 0; i0 < a_f4 + b_f4; i0 += 1024u) {
                 float4 x[4];
@@ -596,10 +667,10 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 bool ok[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t i = i0 + (uint32_t)k * 256u + (uint32_t)t;
-                    ok[k] = i < a_f4 + b_f4;
-                    const bool isb = i >= a_f4;
-                    off[k] = isb ? 2u * a_part + (i - a_f4) * 16u : i * 16u;
+                    const uint32_t e = i0 + (uint32_t)k * 256u + (uint32_t)t;
+                    ok[k] = e < a_f4 + b_f4;
+                    const bool isb = e >= a_f4;
+                    off[k] = isb ? 2u * a_part + (e - a_f4) * 16u : e * 16u;
                     dlt[k] = isb ? b_part : a_part;
                     if (ok[k])
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[k].x), "=f"(x[k].y), "=f"(x[k].z), "=f"(x[k].w)
@@ -658,13 +729,23 @@ int contract_fwd_tc3(const float* stack, const uint8_t* wimg, const float* bias,
     if (const char* e = getenv("TGCN_T3_NS")) { const int v = atoi(e); if (v >= 2 && v <= NS) NS = v; }
     if (NS < 2) return TGCN_OK;
     p.NS = NS;
+    // issuer warps: each owns 2 GP accumulator columns in each of the two row-tile buffers (512 TMEM columns in all)
+    int NI = 512 / (4 * GP);
+    if (NI > kT3Issuers) NI = kT3Issuers;
+    if (NI > K * p.DB) NI = K * p.DB;
+    if (const char* e = getenv("TGCN_T3_NI")) { const int v = atoi(e); if (v >= 1 && v <= NI) NI = v; }
+    if (NI > NS) NI = NS;
+    if (NI < 1) return TGCN_OK;
+    p.NI = NI;
+    p.NSi = NS / NI;
+    p.NS = NS = p.NSi * NI;
     const size_t smem = fixed + (size_t)NS * stage + (p.w_resident ? wtotal : 0);
     CUtensorMap tmA;
     TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, 128, 1,
                               CU_TENSOR_MAP_SWIZZLE_128B));
     TGCN_PROPAGATE(set_smem3(contract_fwd_tc3_kernel, smem, "contract_fwd_tc3"));
     const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
-    contract_fwd_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tmA, p);
+    contract_fwd_tc3_kernel<<<grid, kT3ThreadsF, smem, st>>>(tmA, p);
     TGCN_LAUNCH_CHECK("contract_fwd_tc3");
     *launched = 1;
     return TGCN_OK;
@@ -687,28 +768,34 @@ int contract_bwd_x_tc3(const float* dout, const uint8_t* wimg, float* gstack, in
     const size_t wring = (size_t)kX3WRing * p.wunit;
     if (fixed + wring + abytes > kT3SmemLimit) return TGCN_OK;
     p.abufs = (fixed + wring + 2 * abytes <= kT3SmemLimit) ? 2 : 1;
+    int NI = 512 / (4 * DP);                                   // two [128 x 2 DP] accumulators per issuer
+    if (NI > kT3Issuers) NI = kT3Issuers;
+    if (NI > K) NI = K;
+    if (const char* e = getenv("TGCN_T3_NI")) { const int v = atoi(e); if (v >= 1 && v <= NI) NI = v; }
+    if (NI < 1) return TGCN_OK;
+    p.NI = NI;
     const size_t smem = fixed + wring + (size_t)p.abufs * abytes;
     CUtensorMap tmD;
     TGCN_PROPAGATE(make_tmap3(&tmD, dout, (uint64_t)G, (uint64_t)N, (uint64_t)Q, (uint64_t)G * 4, (uint64_t)N * G * 4, 32, (uint32_t)p.nt,
                               (uint32_t)Q, CU_TENSOR_MAP_SWIZZLE_128B));
     TGCN_PROPAGATE(set_smem3(contract_bwd_x_tc3_kernel, smem, "contract_bwd_x_tc3"));
     const unsigned grid = (unsigned)min64(p.ntiles, kNumSMs);
-    contract_bwd_x_tc3_kernel<<<grid, kT3Threads, smem, st>>>(tmD, p);
+    contract_bwd_x_tc3_kernel<<<grid, kT3ThreadsF, smem, st>>>(tmD, p);
     TGCN_LAUNCH_CHECK("contract_bwd_x_tc3");
     *launched = 1;
     return TGCN_OK;
 }
 
-struct BwdW3Plan { bool ok; int GPw, DB, NBtot, NB, NY, MT, RU, NS, P, units_per_cta, total_units; size_t smem; };
+struct BwdW3Plan { bool ok; int GPw, DB, NBtot, NB, NY, MT, RU, NS, NI, P, units_per_cta, total_units; size_t smem; };
 
 static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
     BwdW3Plan t{};
     const int64_t M = (int64_t)Q * N;
-    if (!use_v3() || D % 32 != 0 || G < 1 || G > 256 || Q < 1 || M <= 0 || M >= (int64_t)INT32_MAX - 256) return t;
+    if (!use_v3() || D % 32 != 0 || G < 1 || G > 128 || Q < 1 || M <= 0 || M >= (int64_t)INT32_MAX - 256) return t;
     t.GPw = (G + 31) / 32 * 32;
     t.DB = D / 32;
     t.NBtot = K * t.DB;
-    const int max_tiles = 512 / t.GPw;                       // TMEM columns
+    const int max_tiles = 512 / (2 * t.GPw);                 // TMEM columns: one [128 x 2 GPw] accumulator per output tile
     if (max_tiles < 1) return t;
     t.NB = t.NBtot < 4 * max_tiles ? t.NBtot : 4 * max_tiles;
     t.NY = (t.NBtot + t.NB - 1) / t.NB;
@@ -719,13 +806,15 @@ static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
         // a unit's rows must be whole vertices (its dOut box is [ru / Q vertices] x [Q samples]) unless Q > ru
         if (ru % Q != 0) continue;
         const size_t blk = (size_t)ru * kRowBytes;
-        const size_t stage = 2 * (size_t)t.MT * 4 * blk + 2 * (size_t)(t.GPw / 32) * blk;
-        int ns = (int)((kT3SmemLimit - fixed) / stage);
+        const size_t stage = 2 * (size_t)t.NB * blk + 2 * (size_t)(t.GPw / 32) * blk;
+        int ns = (int)((kT3SmemLimit - fixed - 4 * blk) / stage);       // 4 blocks of slack behind the last stage
         if (ns > kT3MaxStages) ns = kT3MaxStages;
-        if (ns >= 2) { t.RU = ru; t.NS = ns; t.smem = fixed + (size_t)ns * stage; break; }
+        if (ns >= 2) { t.RU = ru; t.NS = ns; t.smem = fixed + (size_t)ns * stage + 4 * blk; break; }
     }
     if (t.RU == 0) return t;
     if (const char* e = getenv("TGCN_T3_NS")) { const int v = atoi(e); if (v >= 2 && v <= t.NS) t.NS = v; }
+    t.NI = t.MT < kT3Issuers ? t.MT : kT3Issuers;
+    if (const char* e = getenv("TGCN_T3_NI")) { const int v = atoi(e); if (v >= 1 && v <= t.NI) t.NI = v; }
     t.total_units = (int)ceil_div(M, t.RU);
     int64_t want = kNumSMs / t.NY;
     if (want < 1) want = 1;
@@ -750,7 +839,7 @@ int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, in
     const int64_t M = (int64_t)Q * N;
     BwdW3Params p{};
     p.partial = partial; p.M = (int)M; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GPw = t.GPw; p.K = K; p.DB = t.DB;
-    p.NB = t.NB; p.MT = t.MT; p.RU = t.RU; p.NS = t.NS; p.units_per_cta = t.units_per_cta; p.total_units = t.total_units;
+    p.NB = t.NB; p.MT = t.MT; p.RU = t.RU; p.NS = t.NS; p.NI = t.NI; p.units_per_cta = t.units_per_cta; p.total_units = t.total_units;
     CUtensorMap tmA, tmD;
     TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, (uint32_t)t.RU, 1,
                               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -759,7 +848,7 @@ int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, in
                               (uint32_t)(t.RU / Q), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     TGCN_PROPAGATE(set_smem3(contract_bwd_w_tc3_kernel, t.smem, "contract_bwd_w_tc3"));
     const dim3 grid((unsigned)t.P, (unsigned)t.NY);
-    contract_bwd_w_tc3_kernel<<<grid, kT3Threads, t.smem, st>>>(tmA, tmD, p);
+    contract_bwd_w_tc3_kernel<<<grid, kT3ThreadsF, t.smem, st>>>(tmA, tmD, p);
     TGCN_LAUNCH_CHECK("contract_bwd_w_tc3");
     *P_out = t.P;
     *launched = 1;
