@@ -567,7 +567,7 @@ def dp_verify(model, opt, fwd_bwd, finish_step, wl, cfg, Lt, hx, hy, Q, N0, H, n
         out = {"replicas_bit_identical": bool(identical), "max_rel_err_params": worst, "max_rel_err_update": worst_upd,
                "ranks": world, "what": "one N-rank step (dropouts off) vs per-rank gradients averaged + torch.optim.SGD in one "
                                        "process; parameters, and the parameter UPDATE relative to its own size"}
-        if not identical or worst > 1e-5 or worst_upd > 0.05:
+        if not identical or worst > 1e-4 or worst_upd > 0.05:
             raise SystemExit("[bench] data-parallel check FAILED: %s" % json.dumps(out))
     for m, p in zip(drops, saved_p):
         m.p = p
