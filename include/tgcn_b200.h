@@ -281,6 +281,7 @@ typedef struct tgcn_fc1_update {
     int world, rank;
     void* const* regions;
     unsigned int* state;
+    float* gather;          /* world > 1: device scratch of world * (pad4(Q*I) + pad4(Q*Hd)) floats (the peers' x / dh land here) */
 } tgcn_fc1_update_t;
 int tgcn_head_fused_update_supported(int Q, int I, int Hd);
 /* Backward of tgcn_head_fwd (training statistics): gradients of every operand from dlogp[Q,C]; dx may be NULL;
@@ -309,6 +310,20 @@ int64_t tgcn_peer_region_bytes(int64_t n, int nseg);
 int tgcn_peer_allreduce_sgd(void* const* regions_host, int world, int rank, const float* const* grads_host,
                             float* const* params_host, float* const* moms_host, const int64_t* numels_host,
                             int nseg, float lr, float momentum, unsigned int* state, void* stream);
+
+/* ---- row-partitioned graph: halo rows read from the owners over NVLink (BASELINE configs[3]) -------- */
+/* Each rank keeps its basis slabs in a region allocated with tgcn_peer_alloc and mapped by its peers (tgcn_peer_export /
+ * _import); a 256-byte zero-initialised flag line sits at byte offset flag_off[r] of rank r's region.  After producing a
+ * slab a rank calls tgcn_halo_signal (pushes its running step count to every rank's flag line); before the next
+ * recursion step it calls tgcn_halo_pull, which waits for the owners' counts and gathers the halo rows -- owner[h],
+ * row[h] = owning rank and its local row of halo row h -- from slab `slab_off[owner]` of the owner's region into `dst`
+ * [n_halo, C] with 16-byte P2P loads.  Replaces the reference's single-device dense matmul for graphs that are
+ * partitioned by rows (gcn_matmul.py:152-156).  `state`: 4 zero-initialised device uint32 per rank.  Capturable. */
+int tgcn_halo_signal(void* const* regions_host, const int64_t* flag_off_host, int world, int rank,
+                     unsigned int* state, void* stream);
+int tgcn_halo_pull(void* const* regions_host, const int64_t* slab_off_host, const int64_t* flag_off_host, int world,
+                   int rank, const int32_t* owner, const int32_t* row, int n_halo, int64_t C, float* dst,
+                   unsigned int* state, void* stream);
 
 /* ---- host-side graph preprocessing (CPU, no device work) ----------------------------------- */
 /* One level of greedy heavy-edge (Graclus-normalised) matching: replaces the pure-Python loop

@@ -74,6 +74,8 @@ SIGNATURES = {
     "tgcn_peer_close": (_i, [_p]),
     "tgcn_peer_region_bytes": (_l, [_l, _i]),
     "tgcn_peer_allreduce_sgd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _f, _f, _p, _p]),
+    "tgcn_halo_signal": (_i, [_p, _p, _i, _i, _p, _p]),
+    "tgcn_halo_pull": (_i, [_p, _p, _p, _i, _i, _p, _p, _i, _l, _p, _p, _p]),
     "tgcn_pair_one_level_f32": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
     "tgcn_pair_one_level_f64": (_i, [_p, _p, _p, _l, _p, _p, _l, _p]),
 }
@@ -88,7 +90,7 @@ class Dropout(ctypes.Structure):
 class Fc1Update(ctypes.Structure):
     """tgcn_fc1_update_t (include/tgcn_b200.h)."""
     _fields_ = [("lr", ctypes.c_float), ("momentum", ctypes.c_float), ("mom", ctypes.c_void_p), ("world", ctypes.c_int),
-                ("rank", ctypes.c_int), ("regions", ctypes.c_void_p), ("state", ctypes.c_void_p)]
+                ("rank", ctypes.c_int), ("regions", ctypes.c_void_p), ("state", ctypes.c_void_p), ("gather", ctypes.c_void_p)]
 
 
 def dropout_arg(p, seed=0, step_ptr=None):

@@ -33,13 +33,33 @@ def nvcc_path():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ for sm_100a and link the shared library. Returns its path."""
-    fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _up_to_date(fp):
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
-            if fh.read().strip() == fp:
+            return fh.read().strip() == fp
+    return False
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ for sm_100a and link the shared library. Returns its path.  Safe to call from
+    several processes at once (torchrun ranks): the build runs under an exclusive file lock and the late comers find
+    the library up to date."""
+    import fcntl
+    fp = _fingerprint()
+    if not force and _up_to_date(fp):
+        return LIB
+    lock_path = os.path.join(HERE, "csrc", ".build_lock")
+    with open(lock_path, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(fp):
                 return LIB
+            return _build_locked(fp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(fp, verbose):
     nvcc = nvcc_path()
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libtgcn_b200.so (and no prebuilt library is present)")
@@ -59,8 +79,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    link = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    link = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs + ["-cudart", "static"]
     subprocess.check_call(link)
+    os.replace(tmp, LIB)               # atomic: a concurrent loader never maps a half-written library
     with open(STAMP, "w") as fh:
         fh.write(fp)
     return LIB

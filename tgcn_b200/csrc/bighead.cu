@@ -18,6 +18,7 @@
 //                        the replicas stay bit-identical.  NVLink bytes per rank and step: (world-1) * 5.4 MB instead
 //                        of 2 * (world-1)/world * 134 MB.
 // fp32, fixed summation orders (deterministic).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tgcn {
@@ -168,11 +169,45 @@ bighead_bn_kernel(const float* __restrict__ partial, int P, const float* __restr
 }
 
 // ---- backward (+ fused SGD-momentum update, + peer exchange of the activations) ---------------------------------
+// world > 1: all ranks' [x | dh] of this step, pulled over NVLink into ONE local buffer by a plain, fully parallel copy
+// kernel (every SM has dozens of 16-byte P2P loads in flight), so that the update kernel below reads local memory only:
+// a first version read the peers' column blocks from inside the update kernel and paid an exposed ~3 us NVLink round
+// trip at the start of each of its 1308 one-per-SM CTAs.
+struct BhGatherParams {
+    const float* flat[kPeerMaxWorld];   // each rank's region base ([flat0 | flat1 | flags])
+    const unsigned int* flags;          // own flag line
+    unsigned int* step_ctr;
+    unsigned int* done_blocks;
+    float* dst;                         // [world][n_flat]
+    int64_t n_flat;
+    int world, rank;
+    unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(256)
+bighead_gather_kernel(const BhGatherParams p) {
+    const unsigned int step = *p.step_ctr;
+    if ((int)threadIdx.x < p.world) peer_wait_flag(p.flags + threadIdx.x, step + 1u, p.timeout_ns);
+    __syncthreads();
+    const int64_t par = (int64_t)(step & 1u) * p.n_flat;
+    const int64_t n4 = p.n_flat / 4, total = n4 * p.world;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n4);
+        const int64_t e = (i - (int64_t)r * n4) * 4;
+        *reinterpret_cast<float4*>(p.dst + (int64_t)r * p.n_flat + e) = ld_volatile_f4(p.flat[r] + par + e);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(p.done_blocks, 1u);
+        if (prev == gridDim.x - 1) { *p.done_blocks = 0u; *p.step_ctr = step + 1u; }
+    }
+}
+
 struct BhBwdParams {
-    const float* x[kPeerMaxWorld];      // rank r's x [Q, I]  (own rank: the local tensor or the own region)
+    const float* x[kPeerMaxWorld];      // rank r's x [Q, I]  (local memory: the own tensor, or the gathered copies)
     const float* dh[kPeerMaxWorld];     // rank r's dh [Q, Hd]
-    const unsigned int* flags;          // own flag line (slot r written by rank r), or null (world 1)
-    unsigned int* step_ctr;             // device step counter shared with the pack kernel (advanced by the last CTA), or null
+    const unsigned int* flags;          // unused (kept null): the exchange is complete before this kernel starts
+    unsigned int* step_ctr;
     unsigned int* done_blocks;
     float* W1;                          // [Hd, I]; updated in place when `mom` != null
     float* mom;                         // [Hd, I] momentum buffer, or null (plain backward)
@@ -367,27 +402,40 @@ int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* d
     } else {
         TGCN_REQUIRE(dW1, "tgcn_head_bwd: neither dW1 nor an update descriptor");
     }
-    const int S = world * Q;
+    int S = world * Q;
+    if (world == 1 && upd) { const char* e = getenv("TGCN_BH_FAKEWORLD"); const int f = e ? atoi(e) : 0; if (f > 1 && f <= kPeerMaxWorld) S = f * Q; }
     const size_t smem_stage = sizeof(float) * ((size_t)S * kBhCols + (size_t)S * p.HdP);
     const size_t smem_red = sizeof(float) * ((size_t)S * kBhCols + (size_t)8 * Q * kBhCols);
     const size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
     TGCN_SUPPORTED(smem <= 200 * 1024, "tgcn_head_bwd: world %d x batch %d x Hd %d does not fit shared memory", world, Q, Hd);
     if (world == 1) {
         p.x[0] = x; p.dh[0] = dh;
+        // timing experiment only (scripts/time_kernels.py): the arithmetic of an N-rank update on one GPU
+        static const int fake = [] { const char* e = getenv("TGCN_BH_FAKEWORLD"); return e ? atoi(e) : 0; }();
+        if (upd && fake > 1 && fake <= kPeerMaxWorld) {
+            for (int r = 1; r < fake; ++r) { p.x[r] = x; p.dh[r] = dh; }
+            p.world = fake; p.gscale = 1.0f / (float)fake;
+        }
     } else {
-        TGCN_REQUIRE(upd->regions && upd->state, "tgcn_head_bwd: world > 1 needs the peer regions and the state buffer");
-        // publish x and dh of this step in the own region, then read every rank's copy
+        TGCN_REQUIRE(upd->regions && upd->state && upd->gather, "tgcn_head_bwd: world > 1 needs the peer regions, the state and the gather buffer");
+        TGCN_REQUIRE(aligned16(upd->gather), "tgcn_head_bwd: gather buffer must be 16-byte aligned");
+        // publish x and dh of this step in the own region, pull every rank's copy into the local gather buffer
         const float* srcs[2] = {x, dh};
         const int64_t numels[2] = {(int64_t)Q * I, (int64_t)Q * Hd};
         TGCN_PROPAGATE(peer_pack_launch(upd->regions, world, rank, srcs, numels, 2, upd->state, st));
         const int64_t nx = ((int64_t)Q * I + 3) & ~(int64_t)3, nd = ((int64_t)Q * Hd + 3) & ~(int64_t)3;
-        p.n_flat = nx + nd;
+        BhGatherParams g{};
+        g.n_flat = nx + nd; g.world = world; g.rank = rank; g.timeout_ns = peer_timeout_ns();
+        for (int r = 0; r < world; ++r) g.flat[r] = reinterpret_cast<const float*>(upd->regions[r]);
+        g.flags = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(upd->regions[rank]) + 2 * g.n_flat * sizeof(float));
+        g.step_ctr = upd->state; g.done_blocks = upd->state + 2; g.dst = upd->gather;
+        const int gblocks = (int)min64(ceil_div(g.n_flat / 4 * world, 256), (int64_t)kNumSMs * 8);
+        bighead_gather_kernel<<<gblocks, 256, 0, st>>>(g);
+        TGCN_LAUNCH_CHECK("bighead_gather");
         for (int r = 0; r < world; ++r) {
-            p.x[r] = reinterpret_cast<const float*>(upd->regions[r]);
-            p.dh[r] = reinterpret_cast<const float*>(upd->regions[r]) + nx;
+            p.x[r] = upd->gather + (int64_t)r * g.n_flat;
+            p.dh[r] = upd->gather + (int64_t)r * g.n_flat + nx;
         }
-        p.flags = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(upd->regions[rank]) + 2 * p.n_flat * sizeof(float));
-        p.step_ctr = upd->state; p.done_blocks = upd->state + 2;
     }
     if (upd) return OB == 5 ? bighead_bwd_launch<5, true>(p, smem, st) : bighead_bwd_launch<8, true>(p, smem, st);
     return OB == 5 ? bighead_bwd_launch<5, false>(p, smem, st) : bighead_bwd_launch<8, false>(p, smem, st);

@@ -274,9 +274,87 @@ sgd_direct_kernel(const PeerSegs segs, int64_t n, float lr, float momentum, unsi
     }
 }
 
+// ---- halo rows of a row-partitioned slab, read straight from the owners' memory ----
+// Every rank keeps its basis slabs in an IPC-mapped region.  Before recursion step j a rank needs slab j-1's rows of the
+// vertices its rows reference but other ranks own.  halo_signal_kernel (one thread per peer) publishes "my slab is
+// complete" by pushing a step count into slot [rank] of every rank's flag line; halo_pull_kernel waits for the owners'
+// counts and copies the rows with P2P loads (16-byte, coalesced along the row) into the local extended slab.
+// Replaces index_select + NCCL send/recv per step (host-driven, several launches) by two launches without host sync.
+__global__ void halo_signal_kernel(PeerRanks ranks, unsigned int* state) {
+    const unsigned int v = state[0] + 1u;
+    __threadfence_system();
+    if ((int)threadIdx.x < ranks.world) st_release_sys(ranks.flag[threadIdx.x] + ranks.rank, v);
+    __syncthreads();
+    if (threadIdx.x == 0) state[0] = v;
+}
+
+struct HaloSrc { const float* slab[kPeerMaxWorld]; };      // slab j-1 of every rank, as mapped in this process
+
+__global__ void __launch_bounds__(256)
+halo_pull_kernel(const HaloSrc src, const PeerRanks ranks, const int* __restrict__ owner, const int* __restrict__ row,
+                 int n_halo, int V, float4* __restrict__ dst, unsigned int* state, unsigned int* done_blocks) {
+    const unsigned int expect = state[1] + 1u;
+    if ((int)threadIdx.x < ranks.world && (int)threadIdx.x != ranks.rank)
+        peer_wait_flag(ranks.flag[ranks.rank] + threadIdx.x, expect, ranks.timeout_ns);
+    __syncthreads();
+    const int64_t total = (int64_t)n_halo * V;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i / V), v = (int)(i - (int64_t)h * V);
+        const float* base = src.slab[__ldg(owner + h)] + ((int64_t)__ldg(row + h) * V + v) * 4;
+        dst[i] = ld_volatile_f4(base);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_blocks, 1u);
+        if (prev == gridDim.x - 1) { *done_blocks = 0u; state[1] = expect; }
+    }
+}
+
 }  // namespace tgcn
 
 using namespace tgcn;
+
+// regions_host[r]: rank r's slab region as mapped here; flag_off_host[r]: byte offset of its flag line (256 B, zeroed);
+// state: 4 device uint32 of this rank (zeroed): [0] signals sent, [1] pulls done, [2] block counter
+extern "C" int tgcn_halo_signal(void* const* regions_host, const int64_t* flag_off_host, int world, int rank,
+                                unsigned int* state, void* stream) {
+    TGCN_REQUIRE(regions_host && flag_off_host && state, "tgcn_halo_signal: null pointer");
+    TGCN_SUPPORTED(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "tgcn_halo_signal: world %d rank %d", world, rank);
+    PeerRanks ranks{};
+    ranks.world = world; ranks.rank = rank; ranks.timeout_ns = peer_timeout_ns();
+    for (int r = 0; r < world; ++r)
+        ranks.flag[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[r]) + flag_off_host[r]);
+    halo_signal_kernel<<<1, 32, 0, as_stream(stream)>>>(ranks, state);
+    TGCN_LAUNCH_CHECK("halo_signal");
+    return TGCN_OK;
+}
+
+// dst[h, :] = slab_{owner[h]}[row[h], :] for the n_halo halo rows (C floats each, C % 4 == 0); slab_off_host[r]: element
+// offset of the wanted slab inside rank r's region.  Waits until every peer has signalled once more than this rank has pulled.
+extern "C" int tgcn_halo_pull(void* const* regions_host, const int64_t* slab_off_host, const int64_t* flag_off_host, int world,
+                              int rank, const int32_t* owner, const int32_t* row, int n_halo, int64_t C, float* dst,
+                              unsigned int* state, void* stream) {
+    TGCN_REQUIRE(regions_host && slab_off_host && flag_off_host && state, "tgcn_halo_pull: null pointer");
+    TGCN_SUPPORTED(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "tgcn_halo_pull: world %d rank %d", world, rank);
+    TGCN_REQUIRE(C % 4 == 0 && aligned16(dst), "tgcn_halo_pull: rows must be whole 16-byte vectors");
+    TGCN_REQUIRE(n_halo == 0 || (owner && row && dst), "tgcn_halo_pull: null halo tables");
+    HaloSrc src{};
+    PeerRanks ranks{};
+    ranks.world = world; ranks.rank = rank; ranks.timeout_ns = peer_timeout_ns();
+    for (int r = 0; r < world; ++r) {
+        TGCN_REQUIRE(regions_host[r] && (slab_off_host[r] % 4) == 0, "tgcn_halo_pull: bad region / slab offset for rank %d", r);
+        src.slab[r] = reinterpret_cast<const float*>(regions_host[r]) + slab_off_host[r];
+        ranks.flag[r] = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(regions_host[r]) + flag_off_host[r]);
+    }
+    const int V = (int)(C / 4);
+    int64_t blocks = ceil_div((int64_t)n_halo * V, 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
+    halo_pull_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, ranks, owner, row, n_halo, V, reinterpret_cast<float4*>(dst),
+                                                                     state, state + 2);
+    TGCN_LAUNCH_CHECK("halo_pull");
+    return TGCN_OK;
+}
 
 // ---- peer regions -------------------------------------------------------------------------------------------
 extern "C" int tgcn_peer_alloc(int64_t bytes, void** ptr_out) {

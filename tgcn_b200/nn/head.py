@@ -36,6 +36,7 @@ class Fc1FusedSGD:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = weight.device
         self.state = None
+        self.gather = None
         self._regions_c = None
         self._regions = []
         self._batch = None
@@ -66,6 +67,8 @@ class Fc1FusedSGD:
         dist.barrier(group=self.group)
         self._regions_c = (ctypes.c_void_p * self.world)(*self._regions)
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
+        nflat = ((Q * I + 3) // 4 * 4) + ((Q * Hd + 3) // 4 * 4)
+        self.gather = torch.empty(self.world * nflat, dtype=torch.float32, device=self.device)
         self._batch = Q
 
     def supported(self, Q):
@@ -77,7 +80,8 @@ class Fc1FusedSGD:
         """ctypes tgcn_fc1_update_t for one backward call (kept alive by the caller for the duration of the call)."""
         return _lib.Fc1Update(self.lr, self.momentum, self.mom.data_ptr(), self.world, self.rank,
                               None if self._regions_c is None else ctypes.cast(self._regions_c, ctypes.c_void_p),
-                              None if self.state is None else self.state.data_ptr())
+                              None if self.state is None else self.state.data_ptr(),
+                              None if self.gather is None else self.gather.data_ptr())
 
 
 class _HeadFunction(torch.autograd.Function):

@@ -394,14 +394,18 @@ class RowPartitionedLayer:
     use, as in the reference models where the input does not require grad)."""
 
     def __init__(self, L_csr, K, D, G, rank=0, world=1, device=None, recursion=0, engine=0, group=None,
-                 rows_per_tile=0, rowtile_pad=1):
+                 rows_per_tile=0, rowtile_pad=1, halo="auto"):
         """rows_per_tile = 4 or 8: register the row-tile plan of this rank's rows (register-tiled SpMM kernel,
         include/tgcn_b200.h `tgcn_rowtile_plan_create`) when the row order has locality; 0: per-entry kernels.
-        rowtile_pad: see csr.make_rowtile_plan."""
+        rowtile_pad: see csr.make_rowtile_plan.
+        halo: "peer" = the basis slabs live in IPC-mapped regions and the halo rows are read from their owners with
+        P2P loads inside a gather kernel (tgcn_halo_signal / tgcn_halo_pull: no host round trip, no NCCL);
+        "nccl" = index_select + grouped NCCL send/recv per step; "auto" = peer on CUDA with world > 1."""
         from . import _lib
         self.lib = _lib.load()
         self.K, self.D, self.G = K, D, G
         self.rank, self.world, self.group = rank, world, group
+        self.halo_mode = halo
         self.recursion, self.engine = recursion, engine
         self.device = torch.device(device if device is not None else "cuda")
         self.plan = RowPartition(L_csr, rank, world)
@@ -417,6 +421,17 @@ class RowPartitionedLayer:
         self.val = torch.tensor(pl.val, device=dev)
         self.send_idx_dev = [None if (i is None or len(i) == 0) else torch.as_tensor(i, device=dev) for i in pl.send_idx]
         self._bufs = {}
+        self._peer = None
+        if world > 1 and self.halo_mode in ("auto", "peer") and self.device.type == "cuda":
+            import numpy as np
+            starts = np.array([b[0] for b in pl.bounds] + [pl.n_global])
+            owner = (np.searchsorted(starts, pl.halo_ids, side="right") - 1).astype(np.int32)
+            row = (pl.halo_ids - starts[owner]).astype(np.int32)
+            self.halo_owner = torch.as_tensor(owner, device=dev)
+            self.halo_row = torch.as_tensor(row, device=dev)
+            self.halo_mode = "peer"
+        elif self.halo_mode == "auto":
+            self.halo_mode = "nccl"
         self.rowtile = None
         if rows_per_tile:
             from .csr import make_rowtile_plan
@@ -436,7 +451,8 @@ class RowPartitionedLayer:
             dev = self.device
             C = Q * D
             f32 = dict(dtype=torch.float32, device=dev)
-            b = dict(stack=torch.zeros((K, n, C), **f32), out=torch.empty((Q, n, G), **f32),
+            stack = self._peer_stack(Q) if self.halo_mode == "peer" else torch.zeros((K, n, C), **f32)
+            b = dict(stack=stack, out=torch.empty((Q, n, G), **f32),
                      dout=torch.zeros((Q, n, G), **f32), bias=torch.zeros((n, G), **f32), xext=torch.zeros((Q, n, D), **f32),
                      wmix=torch.empty((K, D, G), **f32), dwmix=torch.empty((K, D, G), **f32),
                      scr=torch.empty(max(int(lib.tgcn_contract_fwd_scratch(Q, n, D, G, K)), 16) // 4 + 64, **f32),
@@ -445,10 +461,62 @@ class RowPartitionedLayer:
             self._bufs[Q] = b
         return b
 
-    def _halo(self, slab_ext):
-        if self.world == 1 or self.plan.n_halo == 0:
+    def _peer_stack(self, Q):
+        """The basis stack [K, n_ext, C] of this rank inside an IPC-mapped region (+ a 256-byte flag line), mapped by every
+        peer.  Collective (all ranks allocate together)."""
+        import ctypes
+        import numpy as np
+        from . import _lib
+        lib = self.lib
+        C = Q * self.D
+        nfl = self.K * self.n_ext * C
+        flag_off = (nfl * 4 + 255) // 256 * 256
+        own = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tgcn_peer_alloc(flag_off + 256, ctypes.byref(own)), "tgcn_peer_alloc")
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.tgcn_peer_export(own, handle), "tgcn_peer_export")
+            info = [None] * self.world
+            dist.all_gather_object(info, (bytes(handle), self.n_ext, flag_off), group=self.group)
+            regions = []
+            for r in range(self.world):
+                if r == self.rank:
+                    regions.append(own.value)
+                else:
+                    ptr = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(info[r][0])
+                    _lib.check(lib.tgcn_peer_import(buf, ctypes.byref(ptr)), "tgcn_peer_import")
+                    regions.append(ptr.value)
+        dist.barrier(group=self.group)
+        # a torch view of the own region (the library keeps ownership of the allocation for the process lifetime)
+        iface = {"shape": (self.K, self.n_ext, C), "typestr": "<f4", "data": (own.value, False), "version": 3}
+        holder = type("PeerRegion", (), {"__cuda_array_interface__": iface})()
+        stack = torch.as_tensor(holder, device=self.device)
+        self._peer = dict(regions=(ctypes.c_void_p * self.world)(*regions),
+                          flag_off=(ctypes.c_int64 * self.world)(*[i[2] for i in info]),
+                          slab_elems=[i[1] * C for i in info], holder=holder, Q=Q,
+                          state=torch.zeros(4, dtype=torch.int32, device=self.device))
+        return stack
+
+    def _halo(self, slab_ext, j=None):
+        if self.world == 1:
             return
         pl = self.plan
+        if self.halo_mode != "peer" and pl.n_halo == 0:
+            return
+        if self.halo_mode == "peer":
+            import ctypes
+            from . import _lib
+            pr = self._peer
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            offs = (ctypes.c_int64 * self.world)(*[j * e for e in pr["slab_elems"]])
+            _lib.check(self.lib.tgcn_halo_signal(pr["regions"], pr["flag_off"], self.world, self.rank, pr["state"].data_ptr(), st),
+                       "tgcn_halo_signal")
+            if pl.n_halo:          # a rank without halo rows still signals: its peers read ITS rows
+                _lib.check(self.lib.tgcn_halo_pull(pr["regions"], offs, pr["flag_off"], self.world, self.rank,
+                                                   self.halo_owner.data_ptr(), self.halo_row.data_ptr(), pl.n_halo, slab_ext.shape[1],
+                                                   slab_ext[self.n_own:].data_ptr(), pr["state"].data_ptr(), st), "tgcn_halo_pull")
+            return
         ops, keep, off = [], [], 0
         for q in range(pl.world):
             cnt = pl.recv_cnt[q]
@@ -477,7 +545,7 @@ class RowPartitionedLayer:
         b["xext"][:, :self.n_own] = x_own
         _lib.check(lib.tgcn_to_slab(b["xext"].data_ptr(), b["stack"][0].data_ptr(), Q, n, D, st), "tgcn_to_slab")
         for j in range(1, K):
-            self._halo(b["stack"][j - 1])
+            self._halo(b["stack"][j - 1], j - 1)
             prev = None
             alpha, beta = 1.0, 0.0
             if self.recursion == 1 and j >= 2:
