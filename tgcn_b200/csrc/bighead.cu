@@ -25,7 +25,7 @@ namespace tgcn {
 
 constexpr int kBhThreads = 256;
 constexpr int kBhFwdCols = 1024;      // columns per CTA of the forward (8 warps x 32 lanes x float4)
-constexpr int kBhFwdRows = 16;        // W1 rows per CTA of the forward
+constexpr int kBhFwdRows = 25;        // W1 rows per CTA of the forward (Hd = 200 -> 8 row groups: 164 x 8 CTAs = 2.95 waves of 3 CTAs/SM)
 constexpr int kBhCols = 128;          // columns per CTA of the backward (32 lanes x float4)
 
 // Sum each of the 8 per-lane values over the 32 lanes of the warp with 9 shuffles (recursive halving): afterwards
@@ -76,12 +76,11 @@ bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, fl
     for (int q = 0; q < 8; ++q)
         xq[q] = (ok && q < Q) ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)q * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int qsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int b0 = 0; b0 < rows; b0 += 8) {
         float4 w[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int ol = half * 8 + r;
+            const int ol = b0 + r;
             w[r] = (ok && ol < rows) ? __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)(o0 + ol) * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
@@ -91,7 +90,7 @@ bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, fl
             for (int q = 0; q < 8; ++q)
                 v[q] = fmaf(w[r].x, xq[q].x, fmaf(w[r].y, xq[q].y, fmaf(w[r].z, xq[q].z, w[r].w * xq[q].w)));
             const float tot = warp_reduce8(v, lane);
-            if ((lane & 3) == 0) red[warp][half * 8 + r][qsel] = tot;
+            if ((lane & 3) == 0 && b0 + r < rows) red[warp][b0 + r][qsel] = tot;
         }
     }
     __syncthreads();
@@ -228,8 +227,9 @@ bighead_bwd_kernel(const BhBwdParams p) {
     extern __shared__ __align__(16) float bsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Q = p.Q, I = p.I, Hd = p.Hd, HdP = p.HdP, S = p.world * Q;
-    float* xs = bsm;                                    // [S][128]
-    float* dhs = bsm + (size_t)S * kBhCols;             // [S][HdP]
+    const int SP = (S + 3) & ~3;                        // sample slots padded to whole float4 (zero rows)
+    float* xs = bsm;                                    // [SP][128]
+    float* dhs = bsm + (size_t)SP * kBhCols;            // [HdP][SP]: dh transposed, so a row tile reads 4 samples per LDS.128
     const int64_t i0 = (int64_t)blockIdx.x * kBhCols;
     const int64_t icol = i0 + lane * 4;
     const bool ok = icol < I;
@@ -242,27 +242,27 @@ bighead_bwd_kernel(const BhBwdParams p) {
         __syncthreads();
     }
     // stage every rank's x column block and dh (P2P loads for the peers; volatile: written by another device this step)
-    for (int t = tid; t < S * 32; t += kBhThreads) {
+    for (int t = tid; t < SP * 32; t += kBhThreads) {
         const int sq = t >> 5, l = t & 31;
         const int r = sq / Q, q = sq - r * Q;
         const int64_t c = i0 + l * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < I) v = ld_volatile_f4(p.x[r] + par + (int64_t)q * I + c);
+        if (sq < S && c < I) v = ld_volatile_f4(p.x[r] + par + (int64_t)q * I + c);
         reinterpret_cast<float4*>(xs)[t] = v;
     }
-    for (int t = tid; t < S * HdP; t += kBhThreads) {
-        const int sq = t / HdP, f = t - sq * HdP;
+    for (int t = tid; t < SP * HdP; t += kBhThreads) {
+        const int sq = t / HdP, f = t - sq * HdP;        // coalesced global read along f
         const int r = sq / Q, q = sq - r * Q;
         float v = 0.f;
-        if (f < Hd) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p.dh[r] + par + (int64_t)q * Hd + f) : "memory");
-        dhs[t] = v;
+        if (sq < S && f < Hd) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p.dh[r] + par + (int64_t)q * Hd + f) : "memory");
+        dhs[f * SP + sq] = v;
     }
     __syncthreads();
 
     float4 dxa[QN];
 #pragma unroll
     for (int q = 0; q < QN; ++q) dxa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* dh_own = dhs + (size_t)p.rank * Q * HdP;
+    const int own0 = p.rank * Q;                        // this rank's sample slots (dx uses the local dh only)
     const float4* xs4 = reinterpret_cast<const float4*>(xs);
     const int ntiles = (Hd + OB - 1) / OB;
     for (int tile = warp; tile < ntiles; tile += 8) {
@@ -277,28 +277,25 @@ bighead_bwd_kernel(const BhBwdParams p) {
         float4 g[OB];
 #pragma unroll
         for (int j = 0; j < OB; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sq = 0; sq < S; ++sq) {                     // rank-major, then sample: the same order on every rank
-            const float4 xv = xs4[sq * 32 + lane];
-            const float* dr = dhs + (size_t)sq * HdP + o0;   // o0 + OB <= HdP (HdP is padded to a multiple of OB)
+        for (int sq = 0; sq < SP; sq += 4) {                 // rank-major, then sample: the same order on every rank
+            const float4 x0 = xs4[(sq + 0) * 32 + lane], x1 = xs4[(sq + 1) * 32 + lane];
+            const float4 x2 = xs4[(sq + 2) * 32 + lane], x3 = xs4[(sq + 3) * 32 + lane];
 #pragma unroll
             for (int j = 0; j < OB; ++j) {
-                const float d = dr[j];
-                g[j].x = fmaf(d, xv.x, g[j].x); g[j].y = fmaf(d, xv.y, g[j].y);
-                g[j].z = fmaf(d, xv.z, g[j].z); g[j].w = fmaf(d, xv.w, g[j].w);
+                const float4 d = *reinterpret_cast<const float4*>(dhs + (size_t)(o0 + j) * SP + sq);   // warp broadcast
+                fma4_packed(g[j], d.x, x0);
+                fma4_packed(g[j], d.y, x1);
+                fma4_packed(g[j], d.z, x2);
+                fma4_packed(g[j], d.w, x3);
             }
         }
         if (p.dx) {
 #pragma unroll
-            for (int q = 0; q < QN; ++q) {
-                if (q < Q) {
-                    const float* dr = dh_own + (size_t)q * HdP + o0;
+            for (int j = 0; j < OB; ++j) {
+                const float* dr = dhs + (size_t)(o0 + j) * SP + own0;
 #pragma unroll
-                    for (int j = 0; j < OB; ++j) {
-                        const float d = dr[j];
-                        dxa[q].x = fmaf(d, w[j].x, dxa[q].x); dxa[q].y = fmaf(d, w[j].y, dxa[q].y);
-                        dxa[q].z = fmaf(d, w[j].z, dxa[q].z); dxa[q].w = fmaf(d, w[j].w, dxa[q].w);
-                    }
-                }
+                for (int q = 0; q < QN; ++q)
+                    if (q < Q) fma4_packed(dxa[q], dr[q], w[j]);
             }
         }
 #pragma unroll
@@ -404,8 +401,9 @@ int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* d
     }
     int S = world * Q;
     if (world == 1 && upd) { const char* e = getenv("TGCN_BH_FAKEWORLD"); const int f = e ? atoi(e) : 0; if (f > 1 && f <= kPeerMaxWorld) S = f * Q; }
-    const size_t smem_stage = sizeof(float) * ((size_t)S * kBhCols + (size_t)S * p.HdP);
-    const size_t smem_red = sizeof(float) * ((size_t)S * kBhCols + (size_t)8 * Q * kBhCols);
+    const int SP = (S + 3) & ~3;
+    const size_t smem_stage = sizeof(float) * ((size_t)SP * kBhCols + (size_t)SP * p.HdP);
+    const size_t smem_red = sizeof(float) * ((size_t)SP * kBhCols + (size_t)8 * Q * kBhCols);
     const size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
     TGCN_SUPPORTED(smem <= 200 * 1024, "tgcn_head_bwd: world %d x batch %d x Hd %d does not fit shared memory", world, Q, Hd);
     if (world == 1) {

@@ -55,7 +55,8 @@ prep_wimg_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int K, 
         uint8_t* base = img + u * 2 * (int64_t)rowsP * kRowBytes;
         const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)c);
         *reinterpret_cast<float*>(base + off) = h;
-        *reinterpret_cast<float*>(base + (int64_t)rowsP * kRowBytes + off) = v - h;
+        // the lo part is rounded to tf32 as well: the tensor core would otherwise truncate it (a biased error)
+        *reinterpret_cast<float*>(base + (int64_t)rowsP * kRowBytes + off) = tf32_hi(v - h);
     }
 }
 
@@ -81,7 +82,7 @@ template <int VEC>
 __device__ __forceinline__ void store_split_vec(uint8_t* hi, uint8_t* lo, uint32_t off, const float* x) {
     float h[VEC], l[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = x[i] - h[i]; }
+    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = tf32_hi(x[i] - h[i]); }
     if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);

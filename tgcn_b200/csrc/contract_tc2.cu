@@ -49,7 +49,7 @@ template <int VEC>
 __device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t off, const float* x) {
     float h[VEC], l[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = x[i] - h[i]; }
+    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = tf32_hi(x[i] - h[i]); }
     if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
@@ -78,7 +78,7 @@ template <int VEC>
 __device__ __forceinline__ void split_store_u32(uint32_t hi, uint32_t lo, const float* x) {
     float h[VEC], l[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = x[i] - h[i]; }
+    for (int i = 0; i < VEC; ++i) { h[i] = tf32_hi(x[i]); l[i] = tf32_hi(x[i] - h[i]); }
     if constexpr (VEC == 4) {
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");

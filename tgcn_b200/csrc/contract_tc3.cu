@@ -95,14 +95,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// lo part of a float4 of fp32 values under the tensor core's tf32 read (upper 19 bits): x - trunc(x), exact in fp32
+// lo part of a float4 of fp32 values under the tensor core's tf32 read (upper 19 bits): x - trunc(x) is exact in fp32
+// (13 significant bits); it is then ROUNDED to tf32 here, because the tensor core would truncate it -- truncation errors
+// all point toward zero and add up linearly over the 10^4..10^5 terms of a weight gradient, rounding errors do not
+// (the whole-model training test caught the difference: tests/test_gpu_model.py).
+__device__ __forceinline__ float tf32_lo1(float x) {
+    return tf32_hi(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
 __device__ __forceinline__ float4 tf32_lo4(const float4& x) {
-    float4 r;
-    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-    return r;
+    return make_float4(tf32_lo1(x.x), tf32_lo1(x.y), tf32_lo1(x.z), tf32_lo1(x.w));
 }
 
 // ------------------------------------------------------------------------------------------------

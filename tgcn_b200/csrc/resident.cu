@@ -216,7 +216,7 @@ static ResSmemFwd res_fwd_smem(int N, int64_t E, int DP, int GP, int K, bool csr
 __device__ __forceinline__ void store_image4(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& r) {
     float4 h, l;
     h.x = tf32_hi(r.x); h.y = tf32_hi(r.y); h.z = tf32_hi(r.z); h.w = tf32_hi(r.w);
-    l.x = r.x - h.x; l.y = r.y - h.y; l.z = r.z - h.z; l.w = r.w - h.w;
+    l.x = tf32_hi(r.x - h.x); l.y = tf32_hi(r.y - h.y); l.z = tf32_hi(r.z - h.z); l.w = tf32_hi(r.w - h.w);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
 }

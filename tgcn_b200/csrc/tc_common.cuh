@@ -172,7 +172,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void store_split(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float x) {
     const float h = tf32_hi(x);
     *reinterpret_cast<float*>(tile_hi + off) = h;
-    *reinterpret_cast<float*>(tile_lo + off) = x - h;
+    *reinterpret_cast<float*>(tile_lo + off) = tf32_hi(x - h);   // rounded, not left to the tensor core to truncate
 }
 
 }  // namespace tc
