@@ -213,132 +213,160 @@ struct BhBwdParams {
     float* dW1;                         // [Hd, I] gradient output of the plain backward, or null
     float* dx;                          // [Q, I] or null
     int world, rank, Q, I, Hd, HdP;
-    int64_t n_flat;                     // elements of one flat buffer of a region: the step's buffer starts at (step & 1) * n_flat
+    int RW;                             // rows of W1 per warp (even; kBhBwdWarps * RW >= Hd)
+    int64_t n_flat;                     // unused (kept for layout stability of the struct)
     float lr, momentum, gscale;
     unsigned long long timeout_ns;
 };
 
-// One CTA = 128 columns of W1, all Hd rows: warp w takes the row tiles w, w + 8, ... of OB rows; lane = one float4 column.
-// Shared memory: xs [S][128] (S = world * Q rows of all ranks), dhs [S][HdP]; dhs is re-used for the cross-warp
-// reduction of dx.  QN = register tile of the dx accumulators (Q <= QN).
-template <int OB, int QN, bool kUpdate>
-__global__ void __launch_bounds__(kBhThreads, 1)
+// One CTA = 128 columns of W1, all Hd rows; lane = one float4 column, warp w = rows [w RW, (w + 1) RW) in tiles of
+// OB = 10 rows.  The accumulators are packed over ROW PAIRS -- {g[2p][c], g[2p+1][c]} in one 64-bit register -- so the
+// coefficient pairs {dh[s][2p], dh[s][2p+1]} come straight out of shared memory as the first operand of fma.rn.f32x2
+// and only the four components of x need a duplicating move: 5 LDS.64 + 1 LDS.128 + 4 MOV + 20 FFMA2 per sample for
+// 40 multiply-adds (a first version with scalar FFMA and an in-kernel repack spent 1.2 instructions per multiply-add;
+// at 8 ranks = 64 samples per weight that arithmetic was +180 us per step).  dx uses the same trick over SAMPLE pairs.
+// Shared memory: xs [SP][128] (SP = world * Q sample slots), dhs [SP][HdP] (row pairs contiguous), dho [HdP][QN] (this
+// rank's dh, sample pairs contiguous); dhs is re-used for the cross-warp reduction of dx.
+constexpr int kBhBwdWarps = 10;
+constexpr int kBhBwdThreads = kBhBwdWarps * 32;
+constexpr int kBhOB = 10;
+
+__device__ __forceinline__ unsigned long long dup2(float v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+template <int QN, bool kUpdate>
+__global__ void __launch_bounds__(kBhBwdThreads, 1)
 bighead_bwd_kernel(const BhBwdParams p) {
     extern __shared__ __align__(16) float bsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Q = p.Q, I = p.I, Hd = p.Hd, HdP = p.HdP, S = p.world * Q;
-    const int SP = (S + 3) & ~3;                        // sample slots padded to whole float4 (zero rows)
+    const int SP = (S + 3) & ~3;
     float* xs = bsm;                                    // [SP][128]
-    float* dhs = bsm + (size_t)SP * kBhCols;            // [HdP][SP]: dh transposed, so a row tile reads 4 samples per LDS.128
+    float* dhs = bsm + (size_t)SP * kBhCols;            // [SP][HdP]
+    float* dho = dhs + (size_t)SP * HdP;                // [HdP][QN]
     const int64_t i0 = (int64_t)blockIdx.x * kBhCols;
     const int64_t icol = i0 + lane * 4;
     const bool ok = icol < I;
-    unsigned int step = 0;
-    int64_t par = 0;
-    if (p.flags) {
-        step = *p.step_ctr;
-        par = (int64_t)(step & 1u) * p.n_flat;
-        if (tid < p.world) peer_wait_flag(p.flags + tid, step + 1u, p.timeout_ns);
-        __syncthreads();
-    }
-    // stage every rank's x column block and dh (P2P loads for the peers; volatile: written by another device this step)
-    for (int t = tid; t < SP * 32; t += kBhThreads) {
+    for (int t = tid; t < SP * 32; t += kBhBwdThreads) {
         const int sq = t >> 5, l = t & 31;
         const int r = sq / Q, q = sq - r * Q;
         const int64_t c = i0 + l * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sq < S && c < I) v = ld_volatile_f4(p.x[r] + par + (int64_t)q * I + c);
+        if (sq < S && c < I) v = __ldg(reinterpret_cast<const float4*>(p.x[r] + (int64_t)q * I + c));
         reinterpret_cast<float4*>(xs)[t] = v;
     }
-    for (int t = tid; t < SP * HdP; t += kBhThreads) {
-        const int sq = t / HdP, f = t - sq * HdP;        // coalesced global read along f
+    for (int t = tid; t < SP * HdP; t += kBhBwdThreads) {
+        const int sq = t / HdP, f = t - sq * HdP;
         const int r = sq / Q, q = sq - r * Q;
-        float v = 0.f;
-        if (sq < S && f < Hd) asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p.dh[r] + par + (int64_t)q * Hd + f) : "memory");
-        dhs[f * SP + sq] = v;
+        dhs[t] = (sq < S && f < Hd) ? __ldg(p.dh[r] + (int64_t)q * Hd + f) : 0.f;
+    }
+    for (int t = tid; t < HdP * QN; t += kBhBwdThreads) {
+        const int f = t / QN, q = t - f * QN;
+        dho[t] = (q < Q && f < Hd) ? __ldg(p.dh[p.rank] + (int64_t)q * Hd + f) : 0.f;
     }
     __syncthreads();
 
-    float4 dxa[QN];
+    unsigned long long dxa[QN / 2][4];                  // {dx[2qp][c], dx[2qp+1][c]}
 #pragma unroll
-    for (int q = 0; q < QN; ++q) dxa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int own0 = p.rank * Q;                        // this rank's sample slots (dx uses the local dh only)
+    for (int qp = 0; qp < QN / 2; ++qp)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dxa[qp][c] = 0ull;
     const float4* xs4 = reinterpret_cast<const float4*>(xs);
-    const int ntiles = (Hd + OB - 1) / OB;
-    for (int tile = warp; tile < ntiles; tile += 8) {
-        const int o0 = tile * OB;
-        float4 w[OB], m[OB];
+    const int RW = p.RW;                                // rows per warp (even)
+    const int row_end = min(Hd, (warp + 1) * RW);
+    for (int o0 = warp * RW; o0 < row_end; o0 += kBhOB) {
+        float4 w[kBhOB], m[kBhOB];
 #pragma unroll
-        for (int j = 0; j < OB; ++j) {
-            const bool live = ok && o0 + j < Hd;
+        for (int j = 0; j < kBhOB; ++j) {
+            const bool live = ok && o0 + j < row_end;
             w[j] = live ? *reinterpret_cast<const float4*>(p.W1 + (int64_t)(o0 + j) * I + icol) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (kUpdate) m[j] = live ? *reinterpret_cast<const float4*>(p.mom + (int64_t)(o0 + j) * I + icol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float4 g[OB];
+        unsigned long long g[kBhOB / 2][4];
 #pragma unroll
-        for (int j = 0; j < OB; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sq = 0; sq < SP; sq += 4) {                 // rank-major, then sample: the same order on every rank
-            const float4 x0 = xs4[(sq + 0) * 32 + lane], x1 = xs4[(sq + 1) * 32 + lane];
-            const float4 x2 = xs4[(sq + 2) * 32 + lane], x3 = xs4[(sq + 3) * 32 + lane];
+        for (int jp = 0; jp < kBhOB / 2; ++jp)
 #pragma unroll
-            for (int j = 0; j < OB; ++j) {
-                const float4 d = *reinterpret_cast<const float4*>(dhs + (size_t)(o0 + j) * SP + sq);   // warp broadcast
-                fma4_packed(g[j], d.x, x0);
-                fma4_packed(g[j], d.y, x1);
-                fma4_packed(g[j], d.z, x2);
-                fma4_packed(g[j], d.w, x3);
+            for (int c = 0; c < 4; ++c) g[jp][c] = 0ull;
+        for (int sq = 0; sq < S; ++sq) {                     // rank-major, then sample: the same order on every rank
+            const float4 xv = xs4[sq * 32 + lane];
+            const unsigned long long xx[4] = {dup2(xv.x), dup2(xv.y), dup2(xv.z), dup2(xv.w)};
+            const unsigned long long* dr = reinterpret_cast<const unsigned long long*>(dhs + (size_t)sq * HdP + o0);   // o0 even, HdP even
+#pragma unroll
+            for (int jp = 0; jp < kBhOB / 2; ++jp) {
+                const unsigned long long d2 = dr[jp];        // {dh[sq][o0 + 2 jp], dh[sq][o0 + 2 jp + 1]}: warp broadcast
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ffma2(g[jp][c], d2, xx[c]);
             }
         }
         if (p.dx) {
 #pragma unroll
-            for (int j = 0; j < OB; ++j) {
-                const float* dr = dhs + (size_t)(o0 + j) * SP + own0;
+            for (int j = 0; j < kBhOB; ++j) {
+                const unsigned long long ww[4] = {dup2(w[j].x), dup2(w[j].y), dup2(w[j].z), dup2(w[j].w)};
+                const unsigned long long* dq = reinterpret_cast<const unsigned long long*>(dho + (size_t)(o0 + j) * QN);
 #pragma unroll
-                for (int q = 0; q < QN; ++q)
-                    if (q < Q) fma4_packed(dxa[q], dr[q], w[j]);
+                for (int qp = 0; qp < QN / 2; ++qp) {
+                    const unsigned long long d2 = dq[qp];    // {dh[2qp][o], dh[2qp+1][o]} of this rank
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ffma2(dxa[qp][c], d2, ww[c]);
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < OB; ++j) {
-            if (!(ok && o0 + j < Hd)) continue;
-            const int64_t off = (int64_t)(o0 + j) * I + icol;
-            if (kUpdate) {
-                float4 mm, ww;
-                mm.x = fmaf(p.momentum, m[j].x, g[j].x * p.gscale); mm.y = fmaf(p.momentum, m[j].y, g[j].y * p.gscale);
-                mm.z = fmaf(p.momentum, m[j].z, g[j].z * p.gscale); mm.w = fmaf(p.momentum, m[j].w, g[j].w * p.gscale);
-                ww.x = fmaf(-p.lr, mm.x, w[j].x); ww.y = fmaf(-p.lr, mm.y, w[j].y);
-                ww.z = fmaf(-p.lr, mm.z, w[j].z); ww.w = fmaf(-p.lr, mm.w, w[j].w);
-                *reinterpret_cast<float4*>(p.mom + off) = mm;
-                *reinterpret_cast<float4*>(p.W1 + off) = ww;
-            } else {
-                *reinterpret_cast<float4*>(p.dW1 + off) = g[j];
+        for (int jp = 0; jp < kBhOB / 2; ++jp) {
+            float ga[4], gb[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) unpack2(g[jp][c], ga[c], gb[c]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * jp + h;
+                if (!(ok && o0 + j < row_end)) continue;
+                const float* gg = h ? gb : ga;
+                const int64_t off = (int64_t)(o0 + j) * I + icol;
+                if (kUpdate) {
+                    float4 mm, wn;
+                    mm.x = fmaf(p.momentum, m[j].x, gg[0] * p.gscale); mm.y = fmaf(p.momentum, m[j].y, gg[1] * p.gscale);
+                    mm.z = fmaf(p.momentum, m[j].z, gg[2] * p.gscale); mm.w = fmaf(p.momentum, m[j].w, gg[3] * p.gscale);
+                    wn.x = fmaf(-p.lr, mm.x, w[j].x); wn.y = fmaf(-p.lr, mm.y, w[j].y);
+                    wn.z = fmaf(-p.lr, mm.z, w[j].z); wn.w = fmaf(-p.lr, mm.w, w[j].w);
+                    *reinterpret_cast<float4*>(p.mom + off) = mm;
+                    *reinterpret_cast<float4*>(p.W1 + off) = wn;
+                } else {
+                    *reinterpret_cast<float4*>(p.dW1 + off) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+                }
             }
         }
     }
     if (p.dx) {
-        __syncthreads();                                    // dhs is dead: re-use it for the cross-warp reduction of dx
-        float4* red = reinterpret_cast<float4*>(dhs);       // [8 warps][Q][32 lanes]
+        __syncthreads();                                    // dhs / dho are dead: re-use them for the cross-warp reduction of dx
+        float4* red = reinterpret_cast<float4*>(dhs);       // [warps][Q][32 lanes]
 #pragma unroll
-        for (int q = 0; q < QN; ++q)
-            if (q < Q) red[(warp * Q + q) * 32 + lane] = dxa[q];
+        for (int qp = 0; qp < QN / 2; ++qp) {
+            float a[4], b[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) unpack2(dxa[qp][c], a[c], b[c]);
+            if (2 * qp < Q) red[(warp * Q + 2 * qp) * 32 + lane] = make_float4(a[0], a[1], a[2], a[3]);
+            if (2 * qp + 1 < Q) red[(warp * Q + 2 * qp + 1) * 32 + lane] = make_float4(b[0], b[1], b[2], b[3]);
+        }
         __syncthreads();
-        for (int t = tid; t < Q * 32; t += kBhThreads) {
+        for (int t = tid; t < Q * 32; t += kBhBwdThreads) {
             const int q = t >> 5, l = t & 31;
-            float4 s = red[(0 * Q + q) * 32 + l];
+            float4 s4 = red[(0 * Q + q) * 32 + l];
 #pragma unroll
-            for (int w8 = 1; w8 < 8; ++w8) {
+            for (int w8 = 1; w8 < kBhBwdWarps; ++w8) {
                 const float4 v = red[(w8 * Q + q) * 32 + l];
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
             }
             const int64_t c = i0 + l * 4;
-            if (c < I) *reinterpret_cast<float4*>(p.dx + (int64_t)q * I + c) = s;
-        }
-    }
-    if (p.step_ctr) {                                       // the last CTA advances the step (buffers alternate with its parity)
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int prev = atomicAdd(p.done_blocks, 1u);
-            if (prev == gridDim.x - 1) { *p.done_blocks = 0u; *p.step_ctr = step + 1u; }
+            if (c < I) *reinterpret_cast<float4*>(p.dx + (int64_t)q * I + c) = s4;
         }
     }
 }
@@ -369,14 +397,14 @@ int bighead_fwd(const float* x, const float* W1, const float* b1, const float* g
     return TGCN_OK;
 }
 
-template <int OB, bool kUpdate>
+template <bool kUpdate>
 static int bighead_bwd_launch(const BhBwdParams& p, size_t smem, cudaStream_t st) {
-    auto kern = bighead_bwd_kernel<OB, 8, kUpdate>;
+    auto kern = bighead_bwd_kernel<8, kUpdate>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "tgcn_head_bwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
-    kern<<<(unsigned)ceil_div(p.I, kBhCols), kBhThreads, smem, st>>>(p);
+    kern<<<(unsigned)ceil_div(p.I, kBhCols), kBhBwdThreads, smem, st>>>(p);
     TGCN_LAUNCH_CHECK("bighead_bwd");
     return TGCN_OK;
 }
@@ -388,9 +416,10 @@ int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* d
                  "tgcn_head_bwd: x / W1 / dW1 / dx must be 16-byte aligned");
     const int world = upd ? upd->world : 1, rank = upd ? upd->rank : 0;
     TGCN_SUPPORTED(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "tgcn_head_bwd: world %d rank %d", world, rank);
-    const int OB = (Hd % 5 == 0) ? 5 : 8;
     BhBwdParams p{};
-    p.world = world; p.rank = rank; p.Q = Q; p.I = I; p.Hd = Hd; p.HdP = (int)ceil_div(Hd, OB) * OB;
+    p.world = world; p.rank = rank; p.Q = Q; p.I = I; p.Hd = Hd;
+    p.RW = ((int)ceil_div(Hd, kBhBwdWarps) + 1) & ~1;                 // even: row pairs never straddle two warps
+    p.HdP = kBhBwdWarps * p.RW + kBhOB;                               // a warp's last tile may read (zero) rows past its range
     p.W1 = W1; p.dW1 = dW1; p.dx = dx;
     p.timeout_ns = peer_timeout_ns();
     if (upd) {
@@ -402,8 +431,8 @@ int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* d
     int S = world * Q;
     if (world == 1 && upd) { const char* e = getenv("TGCN_BH_FAKEWORLD"); const int f = e ? atoi(e) : 0; if (f > 1 && f <= kPeerMaxWorld) S = f * Q; }
     const int SP = (S + 3) & ~3;
-    const size_t smem_stage = sizeof(float) * ((size_t)SP * kBhCols + (size_t)SP * p.HdP);
-    const size_t smem_red = sizeof(float) * ((size_t)SP * kBhCols + (size_t)8 * Q * kBhCols);
+    const size_t smem_stage = sizeof(float) * ((size_t)SP * kBhCols + (size_t)SP * p.HdP + (size_t)p.HdP * 8);
+    const size_t smem_red = sizeof(float) * ((size_t)SP * kBhCols + (size_t)kBhBwdWarps * Q * kBhCols);
     const size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
     TGCN_SUPPORTED(smem <= 200 * 1024, "tgcn_head_bwd: world %d x batch %d x Hd %d does not fit shared memory", world, Q, Hd);
     if (world == 1) {
@@ -435,8 +464,8 @@ int bighead_bwd(const float* dh, const float* x, float* W1, float* dW1, float* d
             p.dh[r] = upd->gather + (int64_t)r * g.n_flat + nx;
         }
     }
-    if (upd) return OB == 5 ? bighead_bwd_launch<5, true>(p, smem, st) : bighead_bwd_launch<8, true>(p, smem, st);
-    return OB == 5 ? bighead_bwd_launch<5, false>(p, smem, st) : bighead_bwd_launch<8, false>(p, smem, st);
+    if (upd) return bighead_bwd_launch<true>(p, smem, st);
+    return bighead_bwd_launch<false>(p, smem, st);
 }
 
 }  // namespace tgcn
