@@ -70,30 +70,14 @@ int tgcn_device_supported(void);
  * capture counts once) */
 long long tgcn_launch_count(void);
 /* Kernel-variant selection for tests and sweeps (also readable from the environment as TGCN_<KEY>):
- * "SPMM_PIPE" = blocks per SM of the persistent, software-pipelined SpMM kernel (0 = plain kernel),
- * "SPMM_TILE" = rows per block of the row-tiled SpMM kernel (0 = off), "SPMM_STAGED" = use registered row-block
- * plans (1), "RES_TC" = contraction of the resident forward kernel on tcgen05 with 3xTF32 operands and TMEM
- * accumulators (1) or on the fp32 FFMA pipe (0, the default: measured faster at the resident shapes), "RES_ENT" =
- * keep each thread's CSR entries in registers across the K steps of the resident forward (bit-identical; 0 default:
- * at 768 threads the register budget spills and the variant measured 55.8 us against 49.5 us), "SPMM_RTILE" = use
- * registered row-tile plans (1; 4/5/6/8 = the build for that many blocks per SM; 16 = SM-contiguous block mapping,
- * measured 4 % slower, kept as a recorded experiment; 0 = off).  The other SpMM variants are bit-identical; RES_TC changes the contraction's rounding (<= 5e-6). */
+ * "SPMM_PIPE" = blocks per SM of the persistent, software-pipelined per-entry SpMM kernel (0 = plain kernel),
+ * "SPMM_CSM" = stage the CSR entries of a row block in shared memory (per-entry kernel), "SPMM_RTILE" = use
+ * registered row-tile plans (1; 4/5/6/8 = the build for that many blocks per SM; 0 = off), "RES_TC" = contraction of
+ * the resident forward kernel on tcgen05 with 3xTF32 operands and TMEM accumulators (1) or on the fp32 FFMA pipe (0,
+ * the default: measured faster at the resident shapes), "RES_ENT" = keep each thread's CSR entries in registers
+ * across the K steps of the resident forward (bit-identical; 0 default).  The per-entry SpMM variants are
+ * bit-identical with each other; RES_TC changes the contraction's rounding (<= 5e-6). */
 int tgcn_set_tuning(const char* key, int value);
-
-/* ---- row-block plans (the "plan_create/destroy" of SURVEY 8b) --------------------------------- */
-/* For graphs with locality in their row order (meshes in coarsening order), tgcn_spmm_step and everything
- * built on it stage the DISTINCT source rows of each block of RB consecutive rows in shared memory by bulk
- * copies and gather from there ("SPMM_STAGED" tuning key, on by default whenever a plan is registered).
- * tgcn_block_plan_host computes the plan arrays on the host (blk_rows_host == NULL: size query; at most `cap`
- * rows are staged per block, the remaining entries are gathered from global memory); upload
- * them and register them with tgcn_plan_create, keyed by the device address of the CSR `col` array they
- * belong to.  The arrays stay owned by the caller and must outlive the plan.  Results are bit-identical
- * with and without a plan. */
-int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB, int cap,
-                             int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host);
-int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
-                         const uint16_t* lcol_dev, int RB, int maxd);
-int tgcn_plan_destroy(int64_t handle);
 
 /* ---- row-tile plans: register-tiled SpMM ("SPMM_RTILE" tuning key, on whenever a plan is registered) ---- */
 /* A thread of the row-tile kernel owns one float4 column of R consecutive rows (R = 4 or 8) and loads every DISTINCT

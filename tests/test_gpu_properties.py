@@ -110,12 +110,10 @@ def test_batch_sharding_invariance():
     assert float((lay.bias.grad - gb).abs().max() / gb.abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("variant", [("SPMM_PIPE", 4), ("SPMM_PIPE", 1), ("SPMM_TILE", 32), ("SPMM_TILE", 16),
-                                     ("SPMM_WARPROW", 8), ("SPMM_WARPROW", 1),
-                                     ("SPMM_CSM", 4), ("SPMM_CSM", 6), ("SPMM_CSM", 8)])
+@pytest.mark.parametrize("variant", [("SPMM_PIPE", 4), ("SPMM_PIPE", 1), ("SPMM_CSM", 4), ("SPMM_CSM", 6), ("SPMM_CSM", 8)])
 @pytest.mark.parametrize("has_prev", [False, True])
 def test_spmm_variants_are_bit_identical(variant, has_prev):
-    """The persistent pipelined and the row-tiled SpMM kernels keep the per-row summation order of the plain
+    """The persistent pipelined and the staged-CSR SpMM kernels keep the per-row summation order of the plain
     kernel: bit-identical outputs on a ragged graph (empty rows, rows longer than one batch)."""
     from tgcn_b200 import _lib
     from tgcn_b200.csr import build_csr
@@ -138,13 +136,12 @@ def test_spmm_variants_are_bit_identical(variant, has_prev):
         assert rc == 0, _lib.last_error()
         return out
     try:
-        assert lib.tgcn_set_tuning(b"SPMM_PIPE", 0) == 0 and lib.tgcn_set_tuning(b"SPMM_TILE", 0) == 0
-        assert lib.tgcn_set_tuning(b"SPMM_WARPROW", 0) == 0 and lib.tgcn_set_tuning(b"SPMM_CSM", 0) == 0
+        assert lib.tgcn_set_tuning(b"SPMM_PIPE", 0) == 0 and lib.tgcn_set_tuning(b"SPMM_CSM", 0) == 0
         base = run()
         assert lib.tgcn_set_tuning(variant[0].encode(), variant[1]) == 0
         got = run()
     finally:
-        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+        for key in (b"SPMM_PIPE", b"SPMM_CSM"):
             lib.tgcn_set_tuning(key, -1)
     assert torch.equal(base, got)
     assert lib.tgcn_set_tuning(b"NOPE", 1) == -1
@@ -180,51 +177,15 @@ def test_spmm_staged_csr_dense_rows_fall_back_to_global_entries(u, C):
         assert rc == 0, _lib.last_error()
         return out
     try:
-        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+        for key in (b"SPMM_PIPE", b"SPMM_CSM"):
             assert lib.tgcn_set_tuning(key, 0) == 0
         base = run()
         assert lib.tgcn_set_tuning(b"SPMM_CSM", u) == 0
         got = run()
     finally:
-        for key in (b"SPMM_PIPE", b"SPMM_TILE", b"SPMM_WARPROW", b"SPMM_CSM"):
+        for key in (b"SPMM_PIPE", b"SPMM_CSM"):
             lib.tgcn_set_tuning(key, -1)
     assert torch.equal(base, got)
-
-
-@pytest.mark.parametrize("rb,cap", [(4, 65534), (16, 65534), (64, 65534), (16, 12), (32, 3)])   # small caps: global-gather fallback
-@pytest.mark.parametrize("C", [72, 300])           # 300 floats = 75 float4: two column strips
-def test_row_block_staged_spmm_is_bit_identical(rb, cap, C):
-    """tgcn_plan_create + the staged SpMM kernel (distinct source rows of a row block bulk-copied into shared
-    memory) against the plain kernel on the same operands: bit-identical, with and without `prev`."""
-    from tgcn_b200 import _lib
-    from tgcn_b200.csr import build_csr
-    from conftest import csr_from, load_golden
-    lib = _lib.load()
-    L = csr_from(load_golden("graph_grid28_k8_seed0.npz"), "L_0")     # coarsening order: locality + empty (fake) rows
-    n = L.shape[0]
-    rng = np.random.default_rng(1)
-    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
-    prev = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-
-    def run(plan, with_prev):
-        out = torch.full((n, C), float("nan"), device="cuda")
-        rc = lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), n, x.data_ptr(),
-                                prev.data_ptr() if with_prev else None, out.data_ptr(), C, 2.0, -1.0, st)
-        assert rc == 0, _lib.last_error()
-        return out
-    plain = build_csr(L, torch.device("cuda"))
-    staged = build_csr(L, torch.device("cuda"))
-    info = staged.ensure_block_plans(rows_per_block=rb, min_gain=0.0, cap=cap)
-    assert info and info[0][2]["max_distinct"] <= cap
-    for with_prev in (False, True):
-        assert torch.equal(run(plain, with_prev), run(staged, with_prev))
-    # the tuning key switches the staged path off without touching the plan
-    try:
-        lib.tgcn_set_tuning(b"SPMM_STAGED", 0)
-        assert torch.equal(run(plain, False), run(staged, False))
-    finally:
-        lib.tgcn_set_tuning(b"SPMM_STAGED", -1)
 
 
 @pytest.mark.parametrize("R", [4, 8])

@@ -50,38 +50,3 @@ def test_pack_rejects_bad_arguments_and_handles_empty_rows():
     assert lib.tgcn_pack_csr_host(rp.ctypes.data, None, None, 6, 3, None, None) == -1
     assert lib.tgcn_resident_pack_classes(64, 384, 15, 0) == 2      # 4 float4 per row -> rows alternate bank halves
     assert lib.tgcn_resident_pack_classes(64, 96, 32, 0) == 1       # 128-byte rows: no conflicts to avoid
-
-
-def test_block_plan_host_matches_numpy():
-    lib = _lib.load()
-    m = sp.random(103, 103, density=0.08, random_state=2, format="csr", dtype=np.float32)
-    m.sort_indices()
-    rp = m.indptr.astype(np.int32); c = m.indices.astype(np.int32)
-    for rb in (1, 7, 16):
-        nb = -(-103 // rb)
-        blk_ptr = np.zeros(nb + 1, np.int32); blk_rows = np.zeros(c.size, np.int32); lcol = np.zeros(c.size, np.uint16)
-        maxd = np.zeros(1, np.int32)
-        total = lib.tgcn_block_plan_host(rp.ctypes.data, c.ctypes.data, 103, rb, 65534, blk_ptr.ctypes.data, blk_rows.ctypes.data,
-                                         lcol.ctypes.data, maxd.ctypes.data)
-        assert total == blk_ptr[-1]
-        for b in range(nb):
-            e0, e1 = rp[b * rb], rp[min(103, (b + 1) * rb)]
-            ref = np.unique(c[e0:e1])
-            got = blk_rows[blk_ptr[b]:blk_ptr[b + 1]]
-            assert np.array_equal(got, ref)
-            assert np.array_equal(got[lcol[e0:e1]], c[e0:e1])       # local ids point back at the original columns
-        assert maxd[0] == np.diff(blk_ptr).max()
-    assert lib.tgcn_block_plan_host(None, None, 5, 4, 10, None, None, None, None) == -1
-    # a cap below the block's distinct count: the most referenced rows stay, the rest get the 0xFFFF sentinel
-    nb = -(-103 // 16)
-    blk_ptr = np.zeros(nb + 1, np.int32); blk_rows = np.zeros(c.size, np.int32); lcol = np.zeros(c.size, np.uint16)
-    maxd = np.zeros(1, np.int32)
-    total = lib.tgcn_block_plan_host(rp.ctypes.data, c.ctypes.data, 103, 16, 5, blk_ptr.ctypes.data, blk_rows.ctypes.data,
-                                     lcol.ctypes.data, maxd.ctypes.data)
-    assert maxd[0] <= 5 and total == blk_ptr[-1] and np.diff(blk_ptr).max() <= 5
-    for b in range(nb):
-        e0, e1 = rp[b * 16], rp[min(103, (b + 1) * 16)]
-        got = blk_rows[blk_ptr[b]:blk_ptr[b + 1]]
-        staged = lcol[e0:e1] != 0xFFFF
-        assert np.array_equal(got[lcol[e0:e1][staged]], c[e0:e1][staged])
-        assert not np.isin(c[e0:e1][~staged], got).any()

@@ -28,9 +28,6 @@ SIGNATURES = {
     "tgcn_device_supported": (_i, []),
     "tgcn_launch_count": (ctypes.c_longlong, []),
     "tgcn_set_tuning": (_i, [ctypes.c_char_p, _i]),
-    "tgcn_block_plan_host": (_l, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
-    "tgcn_plan_create": (_l, [_p, _i, _p, _p, _p, _i, _i]),
-    "tgcn_plan_destroy": (_i, [_l]),
     "tgcn_rowtile_plan_host": (_l, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "tgcn_rowtile_plan_create": (_l, [_p, _i, _i, _i, _p, _p, _p]),
     "tgcn_rowtile_plan_destroy": (_i, [_l]),

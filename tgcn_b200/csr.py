@@ -14,7 +14,7 @@ class LaplacianCSR:
     """int32 CSR of L and of L^T resident on one CUDA device."""
 
     __slots__ = ("n", "nnz", "rowptr", "col", "val", "rowptr_t", "col_t", "val_t", "symmetric", "device",
-                 "_host", "_packed", "_lock", "_blocks", "_rowtiles")
+                 "_host", "_packed", "_lock", "_rowtiles")
 
     def __init__(self, n, rowptr, col, val, rowptr_t, col_t, val_t, symmetric, device):
         self.n, self.nnz = n, int(col.numel())
@@ -25,51 +25,13 @@ class LaplacianCSR:
         self._host = None          # (crow, col, val, crow_t, col_t, val_t) as int32/float32 numpy, for packing
         self._packed = {}
         self._lock = threading.Lock()
-        self._blocks = None        # row-block plans of the streaming SpMM: list of (handle, tensors kept alive, stats)
-        self._rowtiles = None      # row-tile plans (register-tiled SpMM): same shape of list
+        self._rowtiles = None      # row-tile plans (register-tiled SpMM): list of (handle, tensors kept alive, stats)
 
     def _host_arrays(self):
         if self._host is None:
             self._host = tuple(np.ascontiguousarray(t.cpu().numpy()) for t in
                                (self.rowptr, self.col, self.val, self.rowptr_t, self.col_t, self.val_t))
         return self._host
-
-    def ensure_block_plans(self, rows_per_block=16, min_gain=1.3, cap=65534):
-        """Row-block plans for the streaming SpMM kernels (include/tgcn_b200.h, tgcn_plan_create): built once
-        per device for L (and L^T when it differs) and registered with the library when the graph's row order
-        has enough locality (gathers / distinct source rows per block >= min_gain).  Idempotent."""
-        if self._blocks is not None:
-            return self._blocks
-        with self._lock:
-            if self._blocks is not None:
-                return self._blocks
-            from . import _lib
-            lib = _lib.load()
-            host = self._host_arrays()
-            made = []
-            variants = [(host[0], host[1], self.col)]
-            if not self.symmetric:
-                variants.append((host[3], host[4], self.col_t))
-            for rp, c, col_dev in variants:
-                if self.n < 1 or c.size == 0:
-                    continue
-                nb = (self.n + rows_per_block - 1) // rows_per_block
-                blk_ptr = np.zeros(nb + 1, dtype=np.int32)
-                blk_rows = np.zeros(max(c.size, 1), dtype=np.int32)
-                lcol = np.zeros(max(c.size, 1), dtype=np.uint16)
-                maxd = np.zeros(1, dtype=np.int32)
-                total = int(lib.tgcn_block_plan_host(rp.ctypes.data, c.ctypes.data, self.n, rows_per_block, cap, blk_ptr.ctypes.data,
-                                                     blk_rows.ctypes.data, lcol.ctypes.data, maxd.ctypes.data))
-                if total <= 0 or c.size / total < min_gain:
-                    continue
-                dev_arrays = (torch.from_numpy(blk_ptr).to(self.device), torch.from_numpy(blk_rows[:total].copy()).to(self.device),
-                              torch.from_numpy(lcol.view(np.int16)).to(self.device))
-                h = int(lib.tgcn_plan_create(col_dev.data_ptr(), self.n, dev_arrays[0].data_ptr(), dev_arrays[1].data_ptr(),
-                                             dev_arrays[2].data_ptr(), rows_per_block, int(maxd[0])))
-                if h >= 0:
-                    made.append((h, dev_arrays, {"gain": c.size / total, "max_distinct": int(maxd[0])}))
-            self._blocks = made
-        return self._blocks
 
     def ensure_rowtile_plans(self, rows_per_tile=8, min_gain=1.5, pad=1):
         """Row-tile plans for the register-tiled SpMM kernel (include/tgcn_b200.h, tgcn_rowtile_plan_create): built
@@ -94,11 +56,6 @@ class LaplacianCSR:
 
     def __del__(self):
         try:
-            if self._blocks:
-                from . import _lib
-                lib = _lib.load()
-                for h, _, _ in self._blocks:
-                    lib.tgcn_plan_destroy(h)
             if self._rowtiles:
                 from . import _lib
                 lib = _lib.load()

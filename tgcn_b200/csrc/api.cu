@@ -18,11 +18,11 @@ int set_error(int code, const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static const char* const kTuneNames[kTuneCount] = {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC", "RES_ENT", "SPMM_WARPROW", "SPMM_CSM", "SPMM_RTILE"};
-// SPMM_PIPE: persistent pipelined SpMM, 4 blocks per SM; SPMM_STAGED applies only to operands with a registered plan
-static const int kTuneDefaults[kTuneCount] = {0, 4, 1, 0, 0, 0, 106, 1};
-static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
-static_assert(kTuneCount == 8, "update the tuning tables");
+static const char* const kTuneNames[kTuneCount] = {"SPMM_PIPE", "RES_TC", "RES_ENT", "SPMM_CSM", "SPMM_RTILE"};
+// SPMM_PIPE: persistent pipelined SpMM, 4 blocks per SM
+static const int kTuneDefaults[kTuneCount] = {4, 0, 0, 106, 1};
+static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+static_assert(kTuneCount == 5, "update the tuning tables");
 
 int tuning_value(int key) {
     int v = g_tune[key].load(std::memory_order_relaxed);
@@ -47,10 +47,10 @@ unsigned long long peer_timeout_ns() {
 }
 }  // namespace tgcn
 
-// Select a kernel variant at run time (tests, sweeps): key in {"SPMM_TILE", "SPMM_PIPE", "SPMM_STAGED", "RES_TC", "RES_ENT", "SPMM_WARPROW", "SPMM_CSM", "SPMM_RTILE"};
-// returns 0, or -1 for an unknown key.  RES_TC = 1: contraction of the resident forward kernel on tcgen05 (3xTF32).  SPMM_PIPE = blocks per SM of the persistent pipelined SpMM kernel (0: one-thread-per-float4 kernel);
-// SPMM_TILE = rows per block of the row-tiled SpMM kernel (0: off); SPMM_CSM = blocks per SM (4, 5, 6, 8) the block-staged-CSR SpMM
-// kernel is compiled for (0: off; 100 + b, the default 106: only for slabs of 96 MB or more).
+// Select a kernel variant at run time (tests, sweeps): key in {"SPMM_PIPE", "RES_TC", "RES_ENT", "SPMM_CSM", "SPMM_RTILE"};
+// returns 0, or -1 for an unknown key.  RES_TC = 1: contraction of the resident forward kernel on tcgen05 (3xTF32).  SPMM_PIPE = blocks per
+// SM of the persistent pipelined SpMM kernel (0: one-thread-per-float4 kernel); SPMM_CSM = blocks per SM (4, 5, 6, 8) the block-staged-CSR
+// SpMM kernel is compiled for (0: off; 100 + b, the default 106: only for slabs of 96 MB or more); SPMM_RTILE = use registered row-tile plans.
 extern "C" int tgcn_set_tuning(const char* key, int value) {
     for (int i = 0; i < tgcn::kTuneCount; ++i)
         if (key && strcmp(key, tgcn::kTuneNames[i]) == 0) {

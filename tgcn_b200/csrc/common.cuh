@@ -21,7 +21,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 void count_launch();
 
 // Run-time tuning knobs (tgcn_set_tuning / environment TGCN_<NAME> read once); -1 = built-in default.
-enum TuneKey { kTuneSpmmTile = 0, kTuneSpmmPipe = 1, kTuneSpmmStaged = 2, kTuneResTc = 3, kTuneResEnt = 4, kTuneSpmmWarpRow = 5, kTuneSpmmCsm = 6, kTuneSpmmRtile = 7, kTuneCount = 8 };
+enum TuneKey { kTuneSpmmPipe = 0, kTuneResTc = 1, kTuneResEnt = 2, kTuneSpmmCsm = 3, kTuneSpmmRtile = 4, kTuneCount = 5 };
 int tuning_value(int key);
 
 }  // namespace tgcn

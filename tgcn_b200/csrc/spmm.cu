@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <utility>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -205,55 +206,6 @@ spmm_step_vec4_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
     out[idx] = r;
 }
 
-// Tiled variant: a block owns RB consecutive rows x one 128-byte column strip (8 float4 = one cache line per
-// gathered neighbour row).  Rows that are consecutive in the coarsening order are graph neighbours, so the
-// lines a block gathers are shared between its rows and are served from L1 instead of L2; blocks of the
-// same strip run back to back (blockIdx.x fastest), so a strip's N x 128 B working set stays in L2.
-// Same per-row summation order as spmm_step_vec4_kernel: results are bit-identical.
-template <bool kHasPrev, int RB>
-__global__ void __launch_bounds__(RB * 8)
-spmm_step_tile_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
-                      const float* __restrict__ val, int N, const float4* __restrict__ in,
-                      const float4* prev, float4* out, int V, float alpha, float beta) {
-    const int v = blockIdx.y * 8 + (threadIdx.x & 7);
-    const int row = blockIdx.x * RB + (threadIdx.x >> 3);
-    if (row >= N || v >= V) return;
-    int e = __ldg(rowptr + row);
-    const int e1 = __ldg(rowptr + row + 1);
-    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-    for (; e + 4 <= e1; e += 4) {
-        const int c0 = __ldg(col + e), c1 = __ldg(col + e + 1), c2 = __ldg(col + e + 2), c3 = __ldg(col + e + 3);
-        const float w0 = __ldg(val + e), w1 = __ldg(val + e + 1), w2 = __ldg(val + e + 2), w3 = __ldg(val + e + 3);
-        const float4 x0 = __ldg(in + (int64_t)c0 * V + v);
-        const float4 x1 = __ldg(in + (int64_t)c1 * V + v);
-        const float4 x2 = __ldg(in + (int64_t)c2 * V + v);
-        const float4 x3 = __ldg(in + (int64_t)c3 * V + v);
-        fma4(acc0, w0, x0);
-        fma4(acc1, w1, x1);
-        fma4(acc0, w2, x2);
-        fma4(acc1, w3, x3);
-    }
-    for (; e < e1; ++e) {
-        const int c0 = __ldg(col + e);
-        const float w0 = __ldg(val + e);
-        fma4(acc0, w0, __ldg(in + (int64_t)c0 * V + v));
-    }
-    float4 r;
-    r.x = alpha * (acc0.x + acc1.x);
-    r.y = alpha * (acc0.y + acc1.y);
-    r.z = alpha * (acc0.z + acc1.z);
-    r.w = alpha * (acc0.w + acc1.w);
-    const int64_t idx = (int64_t)row * V + v;
-    if (kHasPrev) {
-        const float4 p = prev[idx];
-        r.x = fmaf(beta, p.x, r.x);
-        r.y = fmaf(beta, p.y, r.y);
-        r.z = fmaf(beta, p.z, r.z);
-        r.w = fmaf(beta, p.w, r.w);
-    }
-    out[idx] = r;
-}
-
 // Persistent, software-pipelined variant.  With ~6 stored entries per row (meshes) a thread of the plain
 // kernel spends its life in a chain of three dependent round trips (row bounds -> (col,val) -> gathers) and the
 // gathers are in flight for only one of them.  Here a thread owns one float4 column of a strided set of rows
@@ -329,167 +281,6 @@ spmm_step_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
         out[idx] = r;
         if (!has_next) break;
         row = nrow; e = ne; e1 = ne1;
-    }
-}
-
-// Warp-per-row variant.  In the kernels above every lane re-loads the row's (col, val) pairs (broadcast loads that
-// still occupy the L1 pipe: at 12 entries per row they are 26 of a warp's 38 load instructions).  Here a warp
-// owns whole rows: the lanes load 32 entries of the row with ONE coalesced load each for col and val, the entries
-// are broadcast with shuffles, and the loads that reach memory are only the gathers -- each lane accumulates
-// NV = ceil(V / 32) float4 of the row.  Same summation order as spmm_step_vec4_kernel (full groups of four entries
-// alternate two accumulators, the tail goes to the first): bit-identical.
-template <bool kHasPrev, int NV>
-__global__ void __launch_bounds__(256)
-spmm_step_warprow_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
-                         const float* __restrict__ val, int N, const float4* __restrict__ in,
-                         const float4* prev, float4* out, int V, float alpha, float beta) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    const unsigned full = 0xffffffffu;
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < N; row += gridDim.x * wpb) {
-        int e0 = 0, e1 = 0;
-        if (lane < 2) e0 = __ldg(rowptr + row + lane);
-        e1 = __shfl_sync(full, e0, 1);
-        e0 = __shfl_sync(full, e0, 0);
-        const int len = e1 - e0;
-        const int full4 = len & ~3;                         // entries in complete groups of four
-        float4 a0[NV], a1[NV];
-#pragma unroll
-        for (int u = 0; u < NV; ++u) { a0[u] = make_float4(0.f, 0.f, 0.f, 0.f); a1[u] = a0[u]; }
-        for (int base = 0; base < len; base += 32) {
-            const int cnt = min(32, len - base);
-            int mc = 0;
-            float mw = 0.f;
-            if (lane < cnt) { mc = __ldg(col + e0 + base + lane); mw = __ldg(val + e0 + base + lane); }
-            int k = 0;
-            for (; k + 4 <= cnt && base + k + 4 <= full4; k += 4) {
-                int c[4];
-                float w[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { c[t] = __shfl_sync(full, mc, k + t); w[t] = __shfl_sync(full, mw, k + t); }
-                float4 x[4][NV];
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-#pragma unroll
-                    for (int u = 0; u < NV; ++u)
-                        if (u * 32 + lane < V) x[t][u] = __ldg(in + (int64_t)c[t] * V + u * 32 + lane);
-#pragma unroll
-                for (int u = 0; u < NV; ++u)
-                    if (u * 32 + lane < V) {
-                        fma4(a0[u], w[0], x[0][u]);
-                        fma4(a1[u], w[1], x[1][u]);
-                        fma4(a0[u], w[2], x[2][u]);
-                        fma4(a1[u], w[3], x[3][u]);
-                    }
-            }
-            for (; k < cnt; ++k) {                           // tail of the row (< 4 entries), or a group split by the 32-chunk
-                const int c = __shfl_sync(full, mc, k);
-                const float w = __shfl_sync(full, mw, k);
-                const bool in_full = base + k < full4;       // position inside a complete group: alternate accumulators
-                const bool odd = ((base + k) & 1) != 0;
-#pragma unroll
-                for (int u = 0; u < NV; ++u)
-                    if (u * 32 + lane < V) {
-                        const float4 x = __ldg(in + (int64_t)c * V + u * 32 + lane);
-                        if (in_full && odd) fma4(a1[u], w, x); else fma4(a0[u], w, x);
-                    }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NV; ++u) {
-            const int v = u * 32 + lane;
-            if (v >= V) continue;
-            float4 r;
-            r.x = alpha * (a0[u].x + a1[u].x);
-            r.y = alpha * (a0[u].y + a1[u].y);
-            r.z = alpha * (a0[u].z + a1[u].z);
-            r.w = alpha * (a0[u].w + a1[u].w);
-            const int64_t idx = (int64_t)row * V + v;
-            if (kHasPrev) {
-                const float4 q = prev[idx];
-                r.x = fmaf(beta, q.x, r.x);
-                r.y = fmaf(beta, q.y, r.y);
-                r.z = fmaf(beta, q.z, r.z);
-                r.w = fmaf(beta, q.w, r.w);
-            }
-            out[idx] = r;
-        }
-    }
-}
-
-// Row-block staged variant (graphs with locality, e.g. the coarsening order of a mesh: siblings, cousins, ...
-// are consecutive rows).  A block owns RB consecutive rows; the DISTINCT source rows its entries reference
-// (precomputed on the host: tgcn_block_plan_host) are copied once into shared memory by 1-D bulk copies
-// (cp.async.bulk, one per source row, completion on an mbarrier) and every gather is then served from shared
-// memory through block-local column ids.  L2 -> SM traffic drops from nnz/N slabs to (distinct rows per
-// block)/RB slabs per step (mesh32k: 4.66 -> 1.87).  Same per-row summation order: bit-identical results.
-struct StagedParams {
-    const int* rowptr; const unsigned short* lcol; const float* val; const int* col;
-    const int* blk_ptr; const int* blk_rows;
-    const float4* in; const float4* prev; float4* out;
-    int N, RB, V, SW;          // SW = float4 per staged row (column strip width)
-    float alpha, beta;
-};
-
-template <bool kHasPrev>
-__global__ void __launch_bounds__(256)
-spmm_step_staged_kernel(const StagedParams p) {
-    extern __shared__ __align__(16) unsigned char st_smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(st_smem);
-    float4* stage = reinterpret_cast<float4*>(st_smem + 16);
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int s0 = blockIdx.y * p.SW;
-    const int sw = min(p.SW, p.V - s0);
-    const int d0 = __ldg(p.blk_ptr + b), nd = __ldg(p.blk_ptr + b + 1) - d0;
-    if (tid == 0) {
-        tc::mbar_init(bar, 1);
-        tc::fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid < 32) {
-        if (tid == 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nd * (uint32_t)sw * 16u);
-        __syncwarp();
-        for (int d = tid; d < nd; d += 32)
-            tc::bulk_g2s(stage + (size_t)d * p.SW, p.in + (int64_t)__ldg(p.blk_rows + d0 + d) * p.V + s0, (uint32_t)sw * 16u, bar);
-    }
-    tc::mbar_wait(bar, 0);
-    const int row0 = b * p.RB;
-    const int rows = min(p.RB, p.N - row0);
-    for (int i = tid; i < rows * sw; i += blockDim.x) {
-        const int r = i / sw, v = i - r * sw;
-        const int row = row0 + r;
-        int e = __ldg(p.rowptr + row);
-        const int e1 = __ldg(p.rowptr + row + 1);
-        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-        // local id 0xFFFF: the source row was not among the block's staged rows (plan cap): gather it from global memory
-        auto fetch = [&](int ee) -> float4 {
-            const int lc = __ldg(p.lcol + ee);
-            if (lc != 0xFFFF) return stage[lc * p.SW + v];
-            return __ldg(p.in + (int64_t)__ldg(p.col + ee) * p.V + s0 + v);
-        };
-        for (; e + 4 <= e1; e += 4) {
-            const float w0 = __ldg(p.val + e), w1 = __ldg(p.val + e + 1), w2 = __ldg(p.val + e + 2), w3 = __ldg(p.val + e + 3);
-            const float4 x0 = fetch(e), x1 = fetch(e + 1), x2 = fetch(e + 2), x3 = fetch(e + 3);
-            fma4(acc0, w0, x0);
-            fma4(acc1, w1, x1);
-            fma4(acc0, w2, x2);
-            fma4(acc1, w3, x3);
-        }
-        for (; e < e1; ++e) fma4(acc0, __ldg(p.val + e), fetch(e));
-        float4 r4;
-        r4.x = p.alpha * (acc0.x + acc1.x);
-        r4.y = p.alpha * (acc0.y + acc1.y);
-        r4.z = p.alpha * (acc0.z + acc1.z);
-        r4.w = p.alpha * (acc0.w + acc1.w);
-        const int64_t idx = (int64_t)row * p.V + s0 + v;
-        if (kHasPrev) {
-            const float4 q = p.prev[idx];
-            r4.x = fmaf(p.beta, q.x, r4.x);
-            r4.y = fmaf(p.beta, q.y, r4.y);
-            r4.z = fmaf(p.beta, q.z, r4.z);
-            r4.w = fmaf(p.beta, q.w, r4.w);
-        }
-        p.out[idx] = r4;
     }
 }
 
@@ -622,11 +413,7 @@ __device__ __forceinline__ void rtile_load_w(const float* w, int64_t s, unsigned
 constexpr int kRtCap = 768;        // staged (tile, source) pairs per block: 3 KB of ids + 768*R*4 bytes of coefficients
 constexpr int kRtMaxTiles = 32;
 
-// kRemap (experiment, "SPMM_RTILE" = 16): block b works on tile group (b mod 148) * per + b / 148, so the blocks that are
-// resident on one SM together, and the ones that follow them there, own ADJACENT tile groups and find each other's source
-// rows in that SM's L1.  Measured 4 % SLOWER than the identity mapping on the 1M-vertex graph (bit-identical output;
-// profiles/r01/spmm_variants.txt): kept only as the recorded negative result, never selected by default.
-template <bool kHasPrev, int R, int MINB, bool kRemap = false>
+template <bool kHasPrev, int R, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
                        int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
@@ -637,15 +424,7 @@ spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__
     constexpr int U = R == 4 ? 4 : 2;          // sources in flight per thread
     const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
     const int tid = ty * V + tx, nthr = V * TY;
-    int t0;
-    if constexpr (kRemap) {
-        int group = (int)blockIdx.x;
-        const int per = (int)gridDim.x / kNumSMs;          // a bijection on [0, per * 148); the remainder keeps its index
-        if (group < per * kNumSMs) group = (group % kNumSMs) * per + group / kNumSMs;
-        t0 = group * TY;
-    } else {
-        t0 = blockIdx.x * TY;
-    }
+    const int t0 = blockIdx.x * TY;
     const int nt = min(TY, ntiles - t0);
     for (int i = tid; i <= nt; i += nthr) s_tp[i] = __ldg(tile_ptr + t0 + i);
     __syncthreads();
@@ -722,27 +501,22 @@ spmm_step_rtile_kernel(const int* __restrict__ tile_ptr, const int* __restrict__
     }
 }
 
-struct RowTilePlan { const void* key; const int* tile_ptr; const int* src; const float* w; int R, N, n_src_rows; bool live; };
+// ---- row-tile plan registry: plans are created by the host side once per CSR operand and looked up by (device,
+// device address of the operand's `col` array, N).  The owner (csr.LaplacianCSR / parallel.RowPartitionedLayer) keeps the
+// `col` tensor alive for as long as the plan is registered and destroys the plan before releasing it, so an address can
+// never be matched after its allocation was recycled.  The lookup is lock-free while no plan exists.
+struct RowTilePlan { const void* key; int device; const int* tile_ptr; const int* src; const float* w; int R, N, n_src_rows; bool live; };
 static std::mutex g_rt_mu;
 static std::vector<RowTilePlan> g_rt_plans;
+static std::atomic<int> g_rt_live{0};
 
 static bool find_rowtile_plan(const void* col, int N, RowTilePlan* out) {
+    if (g_rt_live.load(std::memory_order_acquire) == 0) return false;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
     std::lock_guard<std::mutex> lk(g_rt_mu);
     for (const RowTilePlan& rp : g_rt_plans)
-        if (rp.live && rp.key == col && rp.N == N) { *out = rp; return true; }
-    return false;
-}
-
-// ---- block-plan registry: plans are created by the host side once per CSR operand and looked up by the
-// device address of its `col` array (the plan's arrays stay owned by the caller)
-struct BlockPlan { const void* key; const int* blk_ptr; const int* blk_rows; const unsigned short* lcol; int RB, maxd, N; bool live; };
-static std::mutex g_plan_mu;
-static std::vector<BlockPlan> g_plans;
-
-static bool find_plan(const void* col, int N, BlockPlan* out) {
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (const BlockPlan& bp : g_plans)
-        if (bp.live && bp.key == col && bp.N == N) { *out = bp; return true; }
+        if (rp.live && rp.key == col && rp.N == N && rp.device == dev) { *out = rp; return true; }
     return false;
 }
 
@@ -770,28 +544,8 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
     if (N == 0 || C == 0) return TGCN_OK;
     TGCN_REQUIRE(in != out, "spmm_step: `in` must not alias `out`");
     const bool vec = (C % 4 == 0) && aligned16(in) && aligned16(out) && (prev == nullptr || aligned16(prev));
-    BlockPlan bp;
-    if (vec && tuning_value(kTuneSpmmStaged) != 0 && find_plan(col, N, &bp)) {
-        const int V = (int)(C / 4);
-        const int SW = V <= 64 ? V : 64;
-        const size_t smem = 16 + (size_t)bp.maxd * SW * 16;
-        if (smem <= 160 * 1024 && ceil_div(V, SW) <= 65535) {
-            StagedParams sp{rowptr, bp.lcol, val, col, bp.blk_ptr, bp.blk_rows, (const float4*)in, (const float4*)prev, (float4*)out,
-                            N, bp.RB, V, SW, alpha, beta};
-            const dim3 grid((unsigned)ceil_div(N, bp.RB), (unsigned)ceil_div(V, SW));
-            auto kern = prev ? spmm_step_staged_kernel<true> : spmm_step_staged_kernel<false>;
-            if (smem > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                if (e != cudaSuccess) return set_error(TGCN_ERR_CUDA, "spmm_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            }
-            kern<<<grid, 256, smem, st>>>(sp);
-            TGCN_LAUNCH_CHECK("spmm_step");
-            return TGCN_OK;
-        }
-    }
     // register-tiled row-tile kernel: whenever a row-tile plan is registered for this operand ("SPMM_RTILE": 0 = off,
-    // 1 = on with the default occupancy, 4/5/6/8 = compiled for that many blocks per SM, 16 = default occupancy with the
-    // experimental SM-contiguous block mapping)
+    // 1 = on with the default occupancy, 4/5/6/8 = compiled for that many blocks per SM)
     RowTilePlan rt;
     const int rt_mode = tuning_value(kTuneSpmmRtile);
     if (vec && rt_mode != 0 && C / 4 <= 256 && find_rowtile_plan(col, N, &rt) &&
@@ -809,23 +563,13 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             else spmm_step_rtile_kernel<false, RR, MB><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
                                                                               (float4*)out, V, ntiles, alpha, beta); \
         } while (0)
-#define TGCN_SPMM_RT_REMAP(RR, MB)                                                                                  \
-        do {                                                                                                        \
-            if (prev) spmm_step_rtile_kernel<true, RR, MB, true><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
-                                                                                        (const float4*)prev, (float4*)out, V, ntiles, alpha, beta); \
-            else spmm_step_rtile_kernel<false, RR, MB, true><<<blocks, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
-                                                                                    (float4*)out, V, ntiles, alpha, beta); \
-        } while (0)
-        if (rt_mode >= 16) {                                    // experimental SM-contiguous block mapping
-            if (rt.R == 8) TGCN_SPMM_RT_REMAP(8, 3); else TGCN_SPMM_RT_REMAP(4, 4);
-        } else if (rt.R == 8) {
+        if (rt.R == 8) {
             if (rt_mode >= 4 && rt_mode != 8) TGCN_SPMM_RT(8, 4); else TGCN_SPMM_RT(8, 3);
         } else {
             if (rt_mode >= 8) TGCN_SPMM_RT(4, 8); else if (rt_mode == 6) TGCN_SPMM_RT(4, 6);
             else if (rt_mode == 5) TGCN_SPMM_RT(4, 5); else TGCN_SPMM_RT(4, 4);
         }
 #undef TGCN_SPMM_RT
-#undef TGCN_SPMM_RT_REMAP
         TGCN_LAUNCH_CHECK("spmm_step");
         return TGCN_OK;
     }
@@ -856,26 +600,6 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         TGCN_LAUNCH_CHECK("spmm_step");
         return TGCN_OK;
     }
-    const int warprow = tuning_value(kTuneSpmmWarpRow);       // blocks per SM of the warp-per-row kernel (0 = off)
-    if (vec && warprow > 0 && C / 4 <= 128) {
-        const int V = (int)(C / 4);
-        const int NV = (V + 31) / 32;
-        int64_t blocks = (int64_t)kNumSMs * warprow;
-        const int64_t need = ceil_div(N, 8);
-        if (blocks > need) blocks = need;
-#define TGCN_SPMM_WR(NVV)                                                                                           \
-        do {                                                                                                        \
-            if (prev) spmm_step_warprow_kernel<true, NVV><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
-                                                                                           (const float4*)prev, (float4*)out, V, alpha, beta); \
-            else spmm_step_warprow_kernel<false, NVV><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
-                                                                                        (float4*)out, V, alpha, beta); \
-        } while (0)
-        if (NV == 1) TGCN_SPMM_WR(1); else if (NV == 2) TGCN_SPMM_WR(2); else if (NV == 3) TGCN_SPMM_WR(3); else TGCN_SPMM_WR(4);
-#undef TGCN_SPMM_WR
-        TGCN_LAUNCH_CHECK("spmm_step");
-        return TGCN_OK;
-    }
-    const int tile_rb = tuning_value(kTuneSpmmTile);
     const int pipe_bps = tuning_value(kTuneSpmmPipe);      // blocks per SM of the persistent kernel (0 = off)
     if (vec && pipe_bps > 0 && C / 4 <= 4096) {
         const int V = (int)(C / 4);
@@ -892,22 +616,7 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             return TGCN_OK;
         }
     }
-    if (vec && tile_rb > 0 && C / 4 >= 8 && ceil_div(C / 4, 8) <= 65535) {
-        const int V = (int)(C / 4);
-        const dim3 grid((unsigned)ceil_div(N, tile_rb), (unsigned)ceil_div(V, 8));
-#define TGCN_SPMM_TILE(RB)                                                                                         \
-        do {                                                                                                       \
-            if (prev) spmm_step_tile_kernel<true, RB><<<grid, RB * 8, 0, st>>>(rowptr, col, val, N, (const float4*)in, \
-                                                                                (const float4*)prev, (float4*)out, V, alpha, beta); \
-            else spmm_step_tile_kernel<false, RB><<<grid, RB * 8, 0, st>>>(rowptr, col, val, N, (const float4*)in, nullptr, \
-                                                                            (float4*)out, V, alpha, beta);          \
-        } while (0)
-        if (tile_rb == 16) TGCN_SPMM_TILE(16);
-        else if (tile_rb == 64) TGCN_SPMM_TILE(64);
-        else if (tile_rb == 128) TGCN_SPMM_TILE(128);
-        else TGCN_SPMM_TILE(32);
-#undef TGCN_SPMM_TILE
-    } else if (vec) {
+    if (vec) {
         const int V = (int)(C / 4);
         const int64_t total = (int64_t)N * V;
         const unsigned blocks = (unsigned)ceil_div(total, 256);
@@ -972,75 +681,6 @@ using namespace tgcn;
 // At most `cap` rows are staged per block (the most referenced ones); entries whose source row is not staged get
 // the local id 0xFFFF and are gathered from global memory by the kernel.  Returns the total number of staged
 // (block, source row) pairs, or -1 on bad arguments.  *maxd_host receives the largest per-block count (<= cap).
-extern "C" int64_t tgcn_block_plan_host(const int32_t* rowptr_host, const int32_t* col_host, int N, int RB, int cap,
-                                        int32_t* blk_ptr_host, int32_t* blk_rows_host, uint16_t* lcol_host, int32_t* maxd_host) {
-    if (N < 0 || RB < 1 || !rowptr_host || cap < 1 || cap > 65534) return -1;
-    const int nb = (int)ceil_div(N, RB);
-    int64_t total = 0;
-    int maxd = 0;
-    std::vector<int32_t> tmp, keep;
-    std::vector<std::pair<int32_t, int32_t>> cnt;
-    for (int b = 0; b < nb; ++b) {
-        const int r0 = b * RB, r1 = (int)min64((int64_t)N, (int64_t)r0 + RB);
-        const int e0 = rowptr_host[r0], e1 = rowptr_host[r1];
-        tmp.assign(col_host + e0, col_host + e1);
-        std::sort(tmp.begin(), tmp.end());
-        // distinct source rows with their reference counts; when there are more than `cap`, the most referenced stay
-        cnt.clear();
-        for (size_t i = 0; i < tmp.size();) {
-            size_t j = i;
-            while (j < tmp.size() && tmp[j] == tmp[i]) ++j;
-            cnt.push_back({-(int32_t)(j - i), tmp[i]});
-            i = j;
-        }
-        if ((int)cnt.size() > cap) { std::sort(cnt.begin(), cnt.end()); cnt.resize(cap); }
-        keep.clear();
-        for (const auto& c : cnt) keep.push_back(c.second);
-        std::sort(keep.begin(), keep.end());
-        if (blk_ptr_host) blk_ptr_host[b] = (int32_t)total;
-        if (blk_rows_host) std::copy(keep.begin(), keep.end(), blk_rows_host + total);
-        if (lcol_host)
-            for (int e = e0; e < e1; ++e) {
-                const auto it = std::lower_bound(keep.begin(), keep.end(), col_host[e]);
-                lcol_host[e] = (it != keep.end() && *it == col_host[e]) ? (uint16_t)(it - keep.begin()) : (uint16_t)0xFFFF;
-            }
-        total += (int64_t)keep.size();
-        if ((int)keep.size() > maxd) maxd = (int)keep.size();
-    }
-    if (blk_ptr_host) blk_ptr_host[nb] = (int32_t)total;
-    if (maxd_host) *maxd_host = maxd;
-    return total;
-}
-
-// Register / drop a block plan for the CSR operand whose column array lives at device address `col_dev`.
-// All arrays are device pointers owned by the caller and must outlive the plan.  Returns a handle >= 0.
-extern "C" int64_t tgcn_plan_create(const int32_t* col_dev, int N, const int32_t* blk_ptr_dev, const int32_t* blk_rows_dev,
-                                    const uint16_t* lcol_dev, int RB, int maxd) {
-    if (!col_dev || !blk_ptr_dev || !blk_rows_dev || !lcol_dev || RB < 1 || maxd < 0 || N < 1) {
-        set_error(TGCN_ERR_INVALID, "tgcn_plan_create: bad arguments");
-        return -1;
-    }
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (size_t i = 0; i < g_plans.size(); ++i)
-        if (!g_plans[i].live) { g_plans[i] = BlockPlan{col_dev, blk_ptr_dev, blk_rows_dev, lcol_dev, RB, maxd, N, true}; return (int64_t)i; }
-    g_plans.push_back(BlockPlan{col_dev, blk_ptr_dev, blk_rows_dev, lcol_dev, RB, maxd, N, true});
-    return (int64_t)g_plans.size() - 1;
-}
-
-extern "C" int tgcn_plan_destroy(int64_t handle) {
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    if (handle < 0 || handle >= (int64_t)g_plans.size() || !g_plans[handle].live)
-        return set_error(TGCN_ERR_INVALID, "tgcn_plan_destroy: unknown handle %lld", (long long)handle);
-    g_plans[handle].live = false;
-    return TGCN_OK;
-}
-
-// Host-side row-tile plan for spmm_step_rtile_kernel: per tile of R consecutive rows (R = 4 or 8) the distinct source
-// rows in ascending order, each with its R coefficients (row-major inside the tile, 0 where absent; duplicate (row,
-// col) entries are summed in CSR order).  tile_ptr_host[ceil(N/R)+1]; src_host / w_host: capacity = nnz sources
-// (w: nnz*R floats) without padding -- use the size query; both NULL: size query.  pad >= 1: every non-empty tile's
-// run is padded to a multiple of `pad` entries with zero-coefficient repeats of its last source (1 = no padding).
-// Returns the total number of (tile, source) pairs including the padding, -1 on bad arguments.
 extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
                                           int R, int pad, int32_t* tile_ptr_host, int32_t* src_host, float* w_host) {
     if (N < 0 || (R != 4 && R != 8) || pad < 1 || pad > 16 || !rowptr_host || (rowptr_host[N] > 0 && (!col_host || !val_host))) return -1;
@@ -1097,8 +737,11 @@ extern "C" int64_t tgcn_rowtile_plan_create(const int32_t* col_dev, int N, int n
         set_error(TGCN_ERR_INVALID, "tgcn_rowtile_plan_create: bad arguments");
         return -1;
     }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }     // the plan belongs to the current device
     std::lock_guard<std::mutex> lk(g_rt_mu);
-    const RowTilePlan np{col_dev, tile_ptr_dev, src_dev, w_dev, R, N, n_src_rows, true};
+    const RowTilePlan np{col_dev, dev, tile_ptr_dev, src_dev, w_dev, R, N, n_src_rows, true};
+    g_rt_live.fetch_add(1, std::memory_order_release);
     for (size_t i = 0; i < g_rt_plans.size(); ++i)
         if (!g_rt_plans[i].live) { g_rt_plans[i] = np; return (int64_t)i; }
     g_rt_plans.push_back(np);
@@ -1110,6 +753,7 @@ extern "C" int tgcn_rowtile_plan_destroy(int64_t handle) {
     if (handle < 0 || handle >= (int64_t)g_rt_plans.size() || !g_rt_plans[handle].live)
         return set_error(TGCN_ERR_INVALID, "tgcn_rowtile_plan_destroy: unknown handle %lld", (long long)handle);
     g_rt_plans[handle].live = false;
+    g_rt_live.fetch_sub(1, std::memory_order_release);
     return TGCN_OK;
 }
 

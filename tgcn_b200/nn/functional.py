@@ -7,11 +7,7 @@ import torch
 from .. import _lib
 
 
-# Row-block staged SpMM (csr.LaplacianCSR.ensure_block_plans): measured on B200 it moves 2.5x less L2 -> SM
-# traffic on the cortical mesh but is not faster than the plain kernel (profiles/r01/spmm_variants.txt), so
-# plans are only built on request (TGCN_SPMM_STAGED=1).
 import os as _os
-_STAGED_SPMM = _os.environ.get("TGCN_SPMM_STAGED", "0") not in ("", "0")
 # Register-tiled SpMM (csr.LaplacianCSR.ensure_rowtile_plans): TGCN_SPMM_ROWTILE=4|8 builds row-tile plans for every
 # streaming layer whose row order has locality (measured: 1M-vertex geometric graph 636 -> 535 us per recursion step,
 # cortical mesh 31 -> 28 us).  Opt-in because its summation order differs from the per-entry kernels' (results agree
@@ -80,8 +76,6 @@ class ChebLayerFunction(torch.autograd.Function):
         x = x.contiguous()
         w = weight.contiguous()
         b = None if bias is None else bias.contiguous()
-        if _STAGED_SPMM:
-            plan.ensure_block_plans()    # row-block staging of the SpMM when the row order has locality
         if _ROWTILE_SPMM:
             plan.ensure_rowtile_plans(rows_per_tile=_ROWTILE_SPMM)
         out = torch.empty((Q, N, G), dtype=torch.float32, device=dev)
@@ -282,8 +276,6 @@ def cheb_basis(x, plan, K, recursion=_lib.RECURSION_REFERENCE, reference_layout=
     Q, N, D = x.shape
     dev = x.device
     x = x.contiguous()
-    if _STAGED_SPMM:
-        plan.ensure_block_plans()
     if _ROWTILE_SPMM:
         plan.ensure_rowtile_plans(rows_per_tile=_ROWTILE_SPMM)
     stack = torch.empty((K, N, Q * D), dtype=torch.float32, device=dev)
