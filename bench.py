@@ -575,6 +575,13 @@ def dp_verify(model, opt, fwd_bwd, finish_step, wl, cfg, Lt, hx, hy, Q, N0, H, n
     return out
 
 
+def _rtile_kernel_name(R):
+    """Which row-tile SpMM kernel the library launches (csrc/spmm.cu dispatch on the SPMM_RTILE tuning value)."""
+    mode = int(os.environ.get("TGCN_SPMM_RTILE", "-1") or -1)
+    mode = 2 if mode < 0 else mode
+    return "spmm_step_rtile_pipe_kernel" if (mode == 3 or (mode == 2 and R == 4)) else "spmm_step_rtile_kernel"
+
+
 def measure_roofline(lib, model, Q, H, dev, flush_buf):
     """Roofline of the dominant kernel of layer 1 on the workload's own operand shapes, timed LIVE with CUDA events.
 
@@ -630,7 +637,8 @@ def measure_roofline(lib, model, Q, H, dev, flush_buf):
     per_launch_ms = _time_graph(steps, reps, flush_buf) / (K - 1)
     bytes_per_launch = algorithmic_step_bytes(N, C, plan.nnz, has_prev=False)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-    kname = "spmm_step_rtile_kernel" if getattr(plan, "_rowtiles", None) else "spmm_step_pipe_kernel"
+    tiles = getattr(plan, "_rowtiles", None)
+    kname = _rtile_kernel_name(tiles[0][2]["rows_per_tile"]) if tiles else "spmm_step_pipe_kernel"
     return {"bound": "hbm", "kernel": kname + " (layer-1 recursion step; K-1 launches per layer forward)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": _ncu_traffic(kname, "N%d_C%d" % (N, C)),
@@ -738,7 +746,7 @@ def run_rgg(args, rank, world, local):
         per = _time_graph(spmm_steps, 5, None) / (K - 1)
         nbytes = 2 * 4 * n_own * C + 8 * int(layer.col.numel()) + 4 * (n_own + 1)
         ach = nbytes / (per * 1e-3) / 1e9
-        kname = "spmm_step_rtile_kernel" if layer.rowtile else "spmm_step_csm_kernel"
+        kname = _rtile_kernel_name(args.rowtile) if layer.rowtile else "spmm_step_csm_kernel"
         roof = {"bound": "hbm", "kernel": kname + " (recursion step on this rank's rows, 2S+E bytes; slabs exceed L2)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": _ncu_traffic(kname, "N%d_C%d" % (n_own, C)), "bytes_per_launch": int(nbytes),

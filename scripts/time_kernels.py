@@ -23,7 +23,18 @@ SHAPES = {  # Q, N, D, G, K
 }
 
 
+PLAIN = False     # --plain: direct launches instead of CUDA-graph replays (for ncu: -k <kernel> -s 2 -c 1)
+
+
 def time_graph(fn, reps, flush):
+    if PLAIN:
+        tot = 0.0
+        for r in range(3 + reps):
+            flush.fill_(float(r))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            tot += a.elapsed_time(b) if r >= 3 else 0.0
+        return tot / reps * 1e3
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -71,7 +82,7 @@ def contract(lib, name, reps, flush):
         print("contract %-8s %-6s Q=%d N=%d D=%d G=%d K=%d  %8.1f us  %7.0f GB/s" % (name, label, Q, N, D, G, K, us, nbytes / us / 1e3), flush=True)
 
 
-def spmm(lib, name, reps, flush, rowtile):
+def spmm(lib, name, reps, flush, rowtile, mode=-1):
     from tgcn_b200 import workloads as wl
     from tgcn_b200.csr import build_csr
     Q, N, D, G, K = SHAPES[name]
@@ -91,8 +102,16 @@ def spmm(lib, name, reps, flush, rowtile):
     def step():
         assert lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), N, a.data_ptr(), None, b.data_ptr(), C, 1.0, 0.0, st()) == 0, _lib.last_error()
         assert lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), N, b.data_ptr(), None, a.data_ptr(), C, 1.0, 0.0, st()) == 0
+    lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
     us = time_graph(step, reps, flush) / 2
+
+    def chain():          # the recursion as the layer runs it: 8 dependent steps, each reading what the last one wrote
+        for _ in range(4):
+            step()
+    us_chain = time_graph(chain, reps, flush) / 8
+    lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
     nbytes = 2 * 4.0 * N * C + 8.0 * plan.nnz + 4.0 * (N + 1)
+    print("spmm     %-8s rowtile=%d mode=%d chain-of-8 %8.1f us/step  %7.0f GB/s (%.1f %%)" % (name, rowtile, mode, us_chain, nbytes / us_chain / 1e3, nbytes / us_chain / 1e3 / 65.408))
     print("spmm     %-8s rowtile=%d N=%d C=%d nnz=%d  %8.1f us  %7.0f GB/s  (%.1f %% of 6540.8)" % (name, rowtile, N, C, plan.nnz, us, nbytes / us / 1e3, nbytes / us / 1e3 / 65.408), flush=True)
 
 
@@ -121,7 +140,11 @@ def main():
     ap.add_argument("--shapes", default="mesh1,mesh2")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--rowtile", default="0,4")
+    ap.add_argument("--rtmodes", default="-1", help="SPMM_RTILE tuning values to time (1 one-shot, 2/3 persistent)")
+    ap.add_argument("--plain", action="store_true", help="direct launches, no CUDA graph (use under ncu)")
     args = ap.parse_args()
+    global PLAIN
+    PLAIN = args.plain
     lib = _lib.load()
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
     for name in args.shapes.split(","):
@@ -129,7 +152,8 @@ def main():
             contract(lib, name, args.reps, flush)
         if "spmm" in args.what:
             for rt in args.rowtile.split(","):
-                spmm(lib, name, args.reps, flush, int(rt))
+                for mode in ([int(m) for m in args.rtmodes.split(",")] if int(rt) else [-1]):
+                    spmm(lib, name, args.reps, flush, int(rt), mode)
     if "head" in args.what:
         head(lib, args.reps, flush)
 

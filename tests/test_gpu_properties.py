@@ -237,12 +237,60 @@ def test_register_tiled_spmm_matches_plain_kernel(R, C):
             assert not torch.equal(got, torch.full_like(got, float("nan")))
             assert float((got - base).abs().max()) <= 1e-5 * scale
             assert float(np.abs(got.double().cpu().numpy() - ref).max()) <= 1e-4 * scale
+    # the persistent, plan-prefetching builds keep the summation order of the one-shot row-tile kernel: bit-identical
+    try:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", 1)
+        one_shot = [run(tiled, True, tr) for tr in (False, True)]
+        for mode in (2, 3):
+            lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
+            for tr in (False, True):
+                assert torch.equal(run(tiled, True, tr), one_shot[tr])
+    finally:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
     # the tuning key switches the register-tiled path off without touching the plan: bit-identical to plain again
     try:
         lib.tgcn_set_tuning(b"SPMM_RTILE", 0)
         assert torch.equal(run(plain, True), run(tiled, True))
     finally:
         lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
+
+
+@pytest.mark.parametrize("R", [4, 8])
+@pytest.mark.parametrize("C", [72, 256])
+def test_persistent_rowtile_spmm_many_groups_per_block(R, C):
+    """The persistent row-tile kernel with more tile groups than resident blocks (every block walks several groups,
+    prefetching the next plan while it gathers): bit-identical to the one-shot row-tile kernel, 1e-4 of fp64."""
+    from tgcn_b200 import _lib, synth
+    from tgcn_b200.csr import build_csr
+    import scipy.sparse as sp
+    lib = _lib.load()
+    n = 60001
+    A = synth.rgg_adjacency(n, seed=3)[0]
+    L = sp.csr_matrix(A, dtype=np.float32)
+    plan = build_csr(L, torch.device("cuda"))
+    info = plan.ensure_rowtile_plans(rows_per_tile=R, min_gain=0.0)
+    assert info
+    rng = np.random.default_rng(R * C)
+    x = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    prev = torch.tensor(rng.standard_normal((n, C)).astype(np.float32), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(with_prev):
+        out = torch.full((n, C), float("nan"), device="cuda")
+        rc = lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), n, x.data_ptr(),
+                                prev.data_ptr() if with_prev else None, out.data_ptr(), C, 2.0, -1.0, st)
+        assert rc == 0, _lib.last_error()
+        return out
+    try:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", 1)
+        base = [run(False), run(True)]
+        for mode in (2, 3):
+            lib.tgcn_set_tuning(b"SPMM_RTILE", mode)
+            assert torch.equal(run(False), base[0]) and torch.equal(run(True), base[1])
+    finally:
+        lib.tgcn_set_tuning(b"SPMM_RTILE", -1)
+    ref = 2.0 * (sp.csr_matrix(L, dtype=np.float64) @ x.double().cpu().numpy()) - prev.double().cpu().numpy()
+    assert float(np.abs(base[1].double().cpu().numpy() - ref).max()) <= 1e-4 * float(np.abs(ref).max())
 
 
 def test_register_tiled_spmm_through_the_layer():

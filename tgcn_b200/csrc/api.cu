@@ -20,7 +20,7 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static const char* const kTuneNames[kTuneCount] = {"SPMM_PIPE", "RES_TC", "RES_ENT", "SPMM_CSM", "SPMM_RTILE"};
 // SPMM_PIPE: persistent pipelined SpMM, 4 blocks per SM
-static const int kTuneDefaults[kTuneCount] = {4, 0, 0, 106, 1};
+static const int kTuneDefaults[kTuneCount] = {4, 0, 0, 106, 2};
 static std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}};
 static_assert(kTuneCount == 5, "update the tuning tables");
 
