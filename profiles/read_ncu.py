@@ -16,6 +16,14 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+        'l1tex__m_l1tex2xbar_write_bytes.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'launch__waves_per_multiprocessor', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
+        'launch__shared_mem_per_block_static', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed',
         'smsp__cycles_active.avg', 'sm__cycles_elapsed.max']
 
 

@@ -25,7 +25,7 @@ namespace tgcn {
 
 constexpr int kBhThreads = 256;
 constexpr int kBhFwdCols = 1024;      // columns per CTA of the forward (8 warps x 32 lanes x float4)
-constexpr int kBhFwdRows = 25;        // W1 rows per CTA of the forward (Hd = 200 -> 8 row groups: 164 x 8 CTAs = 2.95 waves of 3 CTAs/SM)
+constexpr int kBhFwdRows = 20;        // W1 rows per CTA of the forward (Hd = 200 -> 10 row groups: 164 x 10 CTAs = 3.7 waves of 3 CTAs/SM)
 constexpr int kBhCols = 128;          // columns per CTA of the backward (32 lanes x float4)
 
 // Sum each of the 8 per-lane values over the 32 lanes of the warp with 9 shuffles (recursive halving): afterwards
@@ -61,8 +61,16 @@ __device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
     return v[0];
 }
 
-// grid (ceil(I / 1024), ceil(Hd / 16)); block 256.  Q <= 8; I % 4 == 0.
-__global__ void __launch_bounds__(kBhThreads)
+// grid (ceil(I / 1024), ceil(Hd / 20)); block 256.  Q <= 8; I % 4 == 0.
+// The 20 weight rows of a CTA are read in 5 batches of 4 rows, double-buffered in registers: the loads of batch b+1 are
+// issued before batch b is multiplied and reduced, so every warp keeps 2 KB of the weight stream in flight all the
+// time (80 registers, 3 CTAs per SM).  (First version: 25 rows in batches of 8 -- the 4th batch held one real row and
+// seven predicated ones -- loaded and then consumed in turn: 59.6 us for the 134 MB stream = 36 % of the measured HBM
+// peak, stall reason long scoreboard, profiles/r02/ncu_bighead_fc1.txt.)
+constexpr int kBhFwdBatch = 4;
+static_assert(kBhFwdRows % kBhFwdBatch == 0, "row batches must tile the CTA's rows");
+
+__global__ void __launch_bounds__(kBhThreads, 3)
 bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, float* __restrict__ partial, int Q, int I,
                    int Hd) {
     __shared__ float red[8][kBhFwdRows][8];
@@ -71,26 +79,35 @@ bighead_fc1_kernel(const float* __restrict__ x, const float* __restrict__ W1, fl
     const bool ok = i < I;
     const int o0 = blockIdx.y * kBhFwdRows;
     const int rows = min(kBhFwdRows, Hd - o0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* wcol = W1 + (int64_t)o0 * I + i;
+    float4 w[2][kBhFwdBatch];
+#pragma unroll
+    for (int r = 0; r < kBhFwdBatch; ++r)
+        w[0][r] = (ok && r < rows) ? __ldg(reinterpret_cast<const float4*>(wcol + (int64_t)r * I)) : zero4;
     float4 xq[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-        xq[q] = (ok && q < Q) ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)q * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xq[q] = (ok && q < Q) ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)q * I + i)) : zero4;
     const int qsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    for (int b0 = 0; b0 < rows; b0 += 8) {
-        float4 w[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int ol = b0 + r;
-            w[r] = (ok && ol < rows) ? __ldg(reinterpret_cast<const float4*>(W1 + (int64_t)(o0 + ol) * I + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < kBhFwdRows / kBhFwdBatch; ++b) {
+        if (b + 1 < kBhFwdRows / kBhFwdBatch) {
+#pragma unroll
+            for (int r = 0; r < kBhFwdBatch; ++r) {
+                const int ol = (b + 1) * kBhFwdBatch + r;
+                w[(b + 1) & 1][r] = (ok && ol < rows) ? __ldg(reinterpret_cast<const float4*>(wcol + (int64_t)ol * I)) : zero4;
+            }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kBhFwdBatch; ++r) {
+            const float4 wr = w[b & 1][r];
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                v[q] = fmaf(w[r].x, xq[q].x, fmaf(w[r].y, xq[q].y, fmaf(w[r].z, xq[q].z, w[r].w * xq[q].w)));
+                v[q] = fmaf(wr.x, xq[q].x, fmaf(wr.y, xq[q].y, fmaf(wr.z, xq[q].z, wr.w * xq[q].w)));
             const float tot = warp_reduce8(v, lane);
-            if ((lane & 3) == 0 && b0 + r < rows) red[warp][b0 + r][qsel] = tot;
+            if ((lane & 3) == 0 && b * kBhFwdBatch + r < rows) red[warp][b * kBhFwdBatch + r][qsel] = tot;
         }
     }
     __syncthreads();

@@ -8,18 +8,28 @@
 //     order copied shared -> shared once per unit;
 //   * the eight transform warps also ran the epilogue, so the MMA pipe drained at every tile boundary (one TMEM
 //     accumulator).
-// Here (requires slab rows padded to a multiple of 32 floats -- `Dp`, the layer pads D = 30 -> 32):
-//   warp 0      producer   one elected lane: a TMA tensor copy per (row tile, order, 32-column block) lands a
-//                          [128 x 32 fp32] tile in SWIZZLE_128B layout.  kind::tf32 reads the upper 19 bits of each
-//                          fp32, so this tile IS the "hi" operand -- no hi pass at all;
-//   warps 6-13  transform  lo = x - trunc_tf32(x), element-wise at the SAME swizzled offsets (LDS.128 -> 3 ALU ->
-//                          STS.128, conflict-free, no address arithmetic), then a proxy fence;
-//   warp 1      MMA        one lane issues the 3xTF32 products (lo*Wh, hi*Wl, hi*Wh) for the 4 k-steps of the tile
-//                          and commits the stage back to the producer; accumulators alternate between TWO TMEM
-//                          buffers, so the next row tile's MMAs start while the epilogue drains the previous one;
-//   warps 2-5   epilogue   tcgen05.ld (one TMEM lane quarter per warp), bias, stores.
-// The weight images (hi | lo, K-major SWIZZLE_128B, built once per call by prep_wimg_kernel) stay resident in shared
-// memory when they fit (cortical mesh layer 1: 80 KB), else they are streamed with their tile (1-D bulk copy, L2 hits).
+// Here (requires slab rows padded to a multiple of 32 floats -- `Dp`, the layer pads D = 30 -> 32); 17 warps per CTA:
+//   warp 0       producer   one elected lane: a TMA tensor copy per (row tile, order, 32-column block) lands a
+//                           [128 x 32 fp32] tile in SWIZZLE_128B layout.  kind::tf32 reads the upper 19 bits of each
+//                           fp32, so this tile IS the "hi" operand -- no hi pass at all;
+//   warps 9-16   transform  lo = rna_tf32(x - trunc_tf32(x)), element-wise at the SAME swizzled offsets (LDS.128 ->
+//                           ALU -> STS.128, conflict-free, no address arithmetic), then a proxy fence;
+//   warps 1-4    MMA        up to four ISSUER warps, each with its own TMEM accumulators and its own ring of stages
+//                           (units are dealt round-robin; a waiter on an mbarrier must see every phase, so rings are
+//                           never shared).  One issuer thread spent ~1600 cycles per unit on the descriptor / MMA /
+//                           commit instruction stream of twelve N = 32 MMAs while the tensor pipe sat at 13 % -- the
+//                           single issuer WAS the bottleneck (profiles/r02/contract_tc3_notes.txt), hence several of
+//                           them, and the products hi*Wh and hi*Wl fused into ONE MMA of N = 2*GP against the
+//                           side-by-side image [Wh | Wl] (the epilogue adds the two halves), plus lo*Wh: 8 MMAs per
+//                           tile instead of 12.  Accumulators alternate between TWO TMEM buffers per issuer, so the
+//                           next row tile's MMAs start while the epilogue drains the previous one;
+//   warps 5-8    epilogue   tcgen05.ld (one TMEM lane quarter per warp) in 16-column chunks, bias, stores.
+// The weight images (K-major SWIZZLE_128B, built once per call by prep_wimg_kernel) stay resident in shared memory
+// when they fit (cortical mesh layer 1: 80 KB), else they are streamed with their tile (1-D bulk copy, L2 hits).
+// bwd_x is the same pipeline with dOut as the TMA-fed operand (3-D box over [Q][N][G]) and W^T images in per-issuer
+// slots; bwd_w feeds BOTH operands by TMA as MN-major tiles (SWIZZLE_128B_ATOM_32B tensor maps = the UMMA
+// SWIZZLE_128B_BASE32B layout), deals the (D x G) output tiles to the issuers and writes per-CTA partials that
+// reduce_partials_kernel sums in a fixed order.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"

@@ -79,9 +79,18 @@ slab_pack_kernel(const float* __restrict__ x, float* __restrict__ slab, int Q, i
     extern __shared__ float ptile[];                 // [Q][TN][D]
     const int n0 = blockIdx.x * TN, tn = min(TN, N - n0);
     const int run = tn * D;
-    for (int i = threadIdx.x; i < Q * run; i += blockDim.x) {
-        const int q = i / run, r = i - q * run;
-        ptile[q * TN * D + r] = __ldg(x + ((int64_t)q * N + n0) * D + r);
+    if ((run & 3) == 0 && ((TN * D) & 3) == 0 && (((int64_t)N * D) & 3) == 0 && aligned16(x)) {
+        const int run4 = run >> 2;                    // every sample's run starts on a 16-byte boundary
+        for (int i = threadIdx.x; i < Q * run4; i += blockDim.x) {
+            const int q = i / run4, r = i - q * run4;
+            reinterpret_cast<float4*>(ptile + q * TN * D)[r] =
+                __ldg(reinterpret_cast<const float4*>(x + ((int64_t)q * N + n0) * D) + r);
+        }
+    } else {
+        for (int i = threadIdx.x; i < Q * run; i += blockDim.x) {
+            const int q = i / run, r = i - q * run;
+            ptile[q * TN * D + r] = __ldg(x + ((int64_t)q * N + n0) * D + r);
+        }
     }
     __syncthreads();
     const int row = Q * Dp;
@@ -128,7 +137,11 @@ slab_unpack_kernel(const float* __restrict__ slab, float* __restrict__ x, int Q,
 }
 
 static int slab_tile_rows(int Q, int Dp) {
-    int tn = (int)(12288 / ((int64_t)Q * Dp));       // <= 48 KB of shared memory per block
+    // ~16 KB tiles: several blocks per SM overlap their load and store phases (a 48 KB tile measured 43.6 us on the
+    // 40 MB mesh layer-1 input); never fewer than 8 rows while 48 KB allow it, so the per-sample runs stay long
+    const int cap = (int)(12288 / ((int64_t)Q * Dp));
+    int tn = (int)(4096 / ((int64_t)Q * Dp));
+    if (tn < 8) tn = cap < 8 ? cap : 8;
     if (tn > 64) tn = 64;
     return tn < 1 ? 1 : tn;
 }
@@ -515,7 +528,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool kHasPrev, int R, int MINB>
+template <bool kHasPrev, int R, int MINB, int U>
 __global__ void __launch_bounds__(256, MINB)
 spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
                             int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
@@ -524,7 +537,6 @@ spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restr
     __shared__ __align__(16) float s_w[2][CAP * R];
     __shared__ int s_src[2][CAP];
     __shared__ int s_tp[3][kRtMaxTiles + 1];
-    constexpr int U = R == 4 ? 4 : 2;
     const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
     const int tid = ty * V + tx, nthr = V * TY;
     const int stride = gridDim.x;
@@ -568,16 +580,17 @@ spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restr
                 int j = 0;
                 for (; j + U <= cnt; j += U) {
                     int c[U];
-                    unsigned long long wv[U][R / 2];
                     float4 x[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) c[u] = sp[j + u] * V;
 #pragma unroll
                     for (int u = 0; u < U; ++u) x[u] = __ldg(inv + c[u]);
 #pragma unroll
-                    for (int u = 0; u < U; ++u) rtile_load_w<R>(wp, j + u, wv[u]);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) rtile_apply<R>(a, x[u], wv[u]);
+                    for (int u = 0; u < U; ++u) {          // coefficients from shared memory just in time
+                        unsigned long long wv[R / 2];
+                        rtile_load_w<R>(wp, j + u, wv);
+                        rtile_apply<R>(a, x[u], wv);
+                    }
                 }
                 for (; j < cnt; ++j) {
                     unsigned long long wv[R / 2];
@@ -686,19 +699,19 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         } while (0)
         // 2 (the default): persistent, plan-prefetching build for R = 4 (mesh layer 1: 23.1 -> 20.2 us per step inside
         // the training step, 1M-vertex geometric graph 529 -> 485 us; R = 8 measured slower that way and keeps the
-        // one-shot kernel); 3: persistent for both R, one more block per SM at R = 4
+        // one-shot kernel) with 8 gathers in flight per thread; 3: persistent for both R, 4 gathers in flight at R = 4
         if ((rt_mode == 2 && rt.R == 4) || rt_mode == 3) {
-            const int per_sm = rt.R == 8 ? 3 : (rt_mode == 3 ? 5 : 4);
+            const int per_sm = rt.R == 8 ? 3 : 4;
             const int ngroups = (int)blocks;
             const unsigned pgrid = (unsigned)min64(ngroups, (int64_t)kNumSMs * per_sm);
-#define TGCN_SPMM_RTP(RR, MB)                                                                                       \
+#define TGCN_SPMM_RTP(RR, MB, UU)                                                                                       \
             do {                                                                                                    \
-                if (prev) spmm_step_rtile_pipe_kernel<true, RR, MB><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
+                if (prev) spmm_step_rtile_pipe_kernel<true, RR, MB, UU><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
                                                                                           (const float4*)prev, (float4*)out, V, ntiles, ngroups, alpha, beta); \
-                else spmm_step_rtile_pipe_kernel<false, RR, MB><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
+                else spmm_step_rtile_pipe_kernel<false, RR, MB, UU><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
                                                                                       (float4*)out, V, ntiles, ngroups, alpha, beta); \
             } while (0)
-            if (rt.R == 8) TGCN_SPMM_RTP(8, 3); else if (rt_mode == 3) TGCN_SPMM_RTP(4, 5); else TGCN_SPMM_RTP(4, 4);
+            if (rt.R == 8) TGCN_SPMM_RTP(8, 3, 2); else if (rt_mode == 3) TGCN_SPMM_RTP(4, 4, 4); else TGCN_SPMM_RTP(4, 4, 8);
 #undef TGCN_SPMM_RTP
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
