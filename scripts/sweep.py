@@ -6,6 +6,13 @@ For every point it times, on one B200 and through the C-ABI (CUDA events, CUDA-g
   * contract: tgcn_contract_fwd    (tcgen05 3xTF32 when the tiles cover the shape)  -- flops 2 Q N K D G
   * resident: tgcn_resident_layer_fwd (whole layer in one launch) when the per-sample slab fits in shared memory
 and writes one CSV line per point.   python scripts/sweep.py > profiles/r01/sweep.csv
+
+`--train` sweeps the TRAINING step of one layer instead (forward + backward + SGD through the public module API,
+whichever engine `engine="auto"` picks) and runs on 1..8 GPUs:
+    python scripts/sweep.py --train [--quick]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/sweep.py --train --quick
+With N ranks every rank steps its own batch of Q samples (weak scaling) and the weight / bias gradients are averaged and
+applied by the fused peer-memory optimizer (tgcn_b200.parallel.PeerAllreduceSGD); the time is the max over ranks.
 """
 import os
 import sys
@@ -35,7 +42,62 @@ def time_graph(fn, flush, reps=5):
     return tot / reps * 1e3          # microseconds
 
 
+def train_sweep(quick):
+    """One layer's training step over the (graph, Q, K, T) grid; CSV on rank 0."""
+    import torch.distributed as dist
+    from tgcn_b200.nn.gcn import TGCNCheb_H
+    from tgcn_b200.parallel import PeerAllreduceSGD
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    graphs = {"hcp360": wl.hcp_parcellation()[2][0], "mesh32k": wl.cortical_mesh()[2][0]}
+    Ks = [3, 10, 25] if quick else [3, 5, 8, 10, 15, 20, 25]
+    Ts = [5, 30] if quick else [5, 10, 15, 30, 60]
+    if rank == 0:
+        print("graph,N,gpus,Q_per_gpu,K,T,G,engine,step_us,samples_per_s")
+    for gname, L in graphs.items():
+        N = L.shape[0]
+        for Q in ((8, 64) if gname == "hcp360" else (8,)):
+            for K in Ks:
+                for T in Ts:
+                    G = 32
+                    if 4.0 * N * Q * T * K > 12e9:
+                        continue
+                    torch.manual_seed(1)                      # identical replicas
+                    layer = TGCNCheb_H(L, 1, G, K, T).to(dev)
+                    opt = PeerAllreduceSGD(list(layer.parameters()), lr=0.01, momentum=0.5)
+                    torch.manual_seed(100 + rank)
+                    x = torch.randn(Q, N, T, device=dev)
+                    dout = torch.randn(Q, N, G, device=dev)
+
+                    def step():
+                        for p_ in layer.parameters():
+                            p_.grad = None
+                        layer(x).backward(dout)
+                        opt.step()
+                    us = time_graph(step, flush)
+                    t = torch.tensor([us], device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    if rank == 0:
+                        print("%s,%d,%d,%d,%d,%d,%d,%s,%.1f,%.0f" % (gname, N, world, Q, K, T, G, layer.last_engine if hasattr(layer, "last_engine") else "auto",
+                                                                    float(t), world * Q / float(t) * 1e6), flush=True)
+                    del opt, layer
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)            # see DESIGN.md section 6 (teardown with captured graphs)
+
+
 def main():
+    if "--train" in sys.argv:
+        return train_sweep("--quick" in sys.argv)
     lib = _lib.load()
     dev = torch.device("cuda")
     flush = torch.empty(64 * 1024 * 1024, device=dev)

@@ -528,12 +528,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool kHasPrev, int R, int MINB, int U>
-__global__ void __launch_bounds__(256, MINB)
+template <bool kHasPrev, int R, int MINB, int U, int BT>
+__global__ void __launch_bounds__(BT, MINB)
 spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restrict__ src, const float* __restrict__ w,
                             int N, const float4* __restrict__ in, const float4* prev, float4* out, int V, int ntiles,
                             int ngroups, float alpha, float beta) {
-    constexpr int CAP = R == 8 ? 512 : kRtCap;      // two plan buffers within the 48 KB of static shared memory
+    constexpr int CAP = BT == 128 ? 384 : (R == 8 ? 512 : kRtCap);      // two plan buffers within the 48 KB of static shared memory
     __shared__ __align__(16) float s_w[2][CAP * R];
     __shared__ int s_src[2][CAP];
     __shared__ int s_tp[3][kRtMaxTiles + 1];
@@ -699,19 +699,23 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
         } while (0)
         // 2 (the default): persistent, plan-prefetching build for R = 4 (mesh layer 1: 23.1 -> 20.2 us per step inside
         // the training step, 1M-vertex geometric graph 529 -> 485 us; R = 8 measured slower that way and keeps the
-        // one-shot kernel) with 8 gathers in flight per thread; 3: persistent for both R, 4 gathers in flight at R = 4
+        // one-shot kernel) with 8 gathers in flight per thread; 3: persistent for both R, 128-thread blocks at R = 4
         if ((rt_mode == 2 && rt.R == 4) || rt_mode == 3) {
-            const int per_sm = rt.R == 8 ? 3 : 4;
-            const int ngroups = (int)blocks;
+            // mode 3 at R = 4: blocks of 128 threads, 8 per SM -- the per-iteration block barrier spans 4 warps, not 8
+            const bool small = rt_mode == 3 && rt.R == 4 && V <= 128;
+            const int TYp = small ? 128 / V : TY;
+            const int per_sm = rt.R == 8 ? 3 : (small ? 8 : 4);
+            const int ngroups = (int)ceil_div(ntiles, TYp);
             const unsigned pgrid = (unsigned)min64(ngroups, (int64_t)kNumSMs * per_sm);
-#define TGCN_SPMM_RTP(RR, MB, UU)                                                                                       \
+            const dim3 bdp((unsigned)V, (unsigned)TYp);
+#define TGCN_SPMM_RTP(RR, MB, UU, BB)                                                                                   \
             do {                                                                                                    \
-                if (prev) spmm_step_rtile_pipe_kernel<true, RR, MB, UU><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
+                if (prev) spmm_step_rtile_pipe_kernel<true, RR, MB, UU, BB><<<pgrid, bdp, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
                                                                                           (const float4*)prev, (float4*)out, V, ntiles, ngroups, alpha, beta); \
-                else spmm_step_rtile_pipe_kernel<false, RR, MB, UU><<<pgrid, bd, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
+                else spmm_step_rtile_pipe_kernel<false, RR, MB, UU, BB><<<pgrid, bdp, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
                                                                                       (float4*)out, V, ntiles, ngroups, alpha, beta); \
             } while (0)
-            if (rt.R == 8) TGCN_SPMM_RTP(8, 3, 2); else if (rt_mode == 3) TGCN_SPMM_RTP(4, 4, 4); else TGCN_SPMM_RTP(4, 4, 8);
+            if (rt.R == 8) TGCN_SPMM_RTP(8, 3, 2, 256); else if (small) TGCN_SPMM_RTP(4, 8, 8, 128); else TGCN_SPMM_RTP(4, 4, 8, 256);
 #undef TGCN_SPMM_RTP
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
