@@ -42,6 +42,9 @@ def time_graph(fn, flush, reps=5):
     return tot / reps * 1e3          # microseconds
 
 
+STEPS_PER_REPLAY = 8
+
+
 def train_sweep(quick):
     """One layer's training step over the (graph, Q, K, T) grid; CSV on rank 0."""
     import torch.distributed as dist
@@ -80,7 +83,13 @@ def train_sweep(quick):
                             p_.grad = None
                         layer(x).backward(dout)
                         opt.step()
-                    us = time_graph(step, flush)
+
+                    def steps():              # several steps per replay: the ranks' launch skew is paid once, not per step
+                        for _ in range(STEPS_PER_REPLAY):
+                            step()
+                    if world > 1:
+                        dist.barrier()
+                    us = time_graph(steps, flush) / STEPS_PER_REPLAY
                     t = torch.tensor([us], device=dev)
                     if world > 1:
                         dist.all_reduce(t, op=dist.ReduceOp.MAX)

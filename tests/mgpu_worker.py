@@ -100,6 +100,74 @@ def check_partitioned_layer(rank, world, dev):
     return part.plan.n_halo
 
 
+def check_halo_modes(rank, world, dev):
+    """E. halo rows pulled over NVLink peer memory (tgcn_halo_signal / tgcn_halo_pull) == halo rows exchanged by NCCL
+    send/recv: forward, dW and db bit for bit."""
+    L, _ = wl.random_geometric(n=20000, mean_degree=10.0, seed=4)
+    n = L.shape[0]
+    Q, D, G, K = 2, 32, 32, 6
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(Q, n, D, generator=g).to(dev)
+    W = (torch.randn(K, D, G, generator=g) * 0.2).to(dev)
+    bias = torch.randn(n, G, generator=g).to(dev)
+    dout = torch.randn(Q, n, G, generator=g).to(dev)
+    res = []
+    for mode in ("peer", "nccl"):
+        part = RowPartitionedLayer(L, K, D, G, rank=rank, world=world, device=dev, halo=mode)
+        lo, hi = part.plan.lo, part.plan.hi
+        for _ in range(2):                                         # twice: the step flags / buffer parity advance
+            out = part.forward(x[:, lo:hi].contiguous(), W, bias[lo:hi].contiguous()).clone()
+            dW, db = part.backward(dout[:, lo:hi].contiguous())
+        res.append((out, dW.clone(), db.clone()))
+        torch.cuda.synchronize()
+        dist.barrier()
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b), "peer-memory halo differs from the NCCL halo"
+    return part.plan.n_halo
+
+
+def check_fc1_exchange(rank, world, dev):
+    """F. large head with the fused fc1 update, data parallel by ACTIVATION exchange (csrc/bighead.cu) == plain autograd
+    on this rank's shard + allreduce(AVG) of the fc1 gradient + torch.optim.SGD; replicas bit-identical."""
+    import torch.nn as nn
+    from tgcn_b200.nn.head import Fc1FusedSGD, fused_head
+    Q, I, Hd, C = 4, 16384, 200, 6
+    torch.manual_seed(5)
+    mods = [nn.Linear(I, Hd).to(dev), nn.BatchNorm1d(Hd).to(dev), nn.Linear(Hd, C).to(dev)]
+    ref = [nn.Linear(I, Hd).to(dev), nn.BatchNorm1d(Hd).to(dev), nn.Linear(Hd, C).to(dev)]
+    for m, r in zip(mods, ref):
+        r.load_state_dict(m.state_dict())
+        m.train(); r.train()
+    upd = Fc1FusedSGD(mods[0].weight, lr=0.05, momentum=0.5, batch=Q)
+    opt = torch.optim.SGD([ref[0].weight], lr=0.05, momentum=0.5)
+    g = torch.Generator(device=dev).manual_seed(200 + rank)        # different samples per rank
+    worst = 0.0
+    for it in range(4):
+        x = torch.randn(Q, I, device=dev, generator=g)
+        y = torch.randint(0, C, (Q,), device=dev, generator=g)
+        F.nll_loss(fused_head(x, *mods, fc1_update=upd), y).backward()
+        assert mods[0].weight.grad is None
+        h = F.relu(ref[1](ref[0](x)))
+        F.nll_loss(F.log_softmax(ref[2](h), dim=1), y).backward()
+        dist.all_reduce(ref[0].weight.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        # the other parameters are not stepped here: copy them so both sides stay comparable, and clear the gradients
+        for m, r in zip(mods, ref):
+            for pm, pr in zip(m.parameters(), r.parameters()):
+                if pm is not mods[0].weight:
+                    pm.grad = None
+                pr.grad = None
+        torch.cuda.synchronize()
+        upd_mag = float((ref[0].weight - mods[0].weight).abs().max() / ref[0].weight.abs().max())
+        worst = max(worst, upd_mag)
+    assert worst < 1e-5, worst
+    mine = mods[0].weight.detach().reshape(-1)
+    others = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(others, mine)
+    assert all(torch.equal(o, mine) for o in others), "fc1 replicas diverged"
+    return worst
+
+
 def check_peer_sgd(rank, world, dev):
     """D. fused peer-memory allreduce + SGD == NCCL allreduce (mean) + torch SGD, and the replicas stay identical."""
     torch.manual_seed(3)                                           # same initial parameters on every rank
@@ -184,15 +252,25 @@ def main():
     rank, world, local = init_distributed("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if os.environ.get("MGPU_ONLY") == "peer":                     # second run of the test: TGCN_PEER_TWOSHOT=1 in the environment
+        pe = check_peer_sgd(rank, world, dev)
+        po = check_peer_sgd_overlap(rank, world, dev)
+        dist.barrier()
+        if rank == 0:
+            print("MGPU_PEER_OK world=%d peer_sgd_err=%.2e peer_overlap_err=%.2e" % (world, pe, po))
+        dist.destroy_process_group()
+        return
     e = check_dp(rank, world, dev)
     h = check_halo(rank, world, dev)
     h2 = check_partitioned_layer(rank, world, dev)
+    h3 = check_halo_modes(rank, world, dev)
+    fe = check_fc1_exchange(rank, world, dev)
     pe = check_peer_sgd(rank, world, dev)
     po = check_peer_sgd_overlap(rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d peer_sgd_err=%.2e peer_overlap_err=%.2e"
-              % (world, e, h, h2, pe, po))
+        print("MGPU_OK world=%d dp_err=%.2e halo_rows=%d layer_halo_rows=%d halo_modes_rows=%d fc1_exchange_err=%.2e peer_sgd_err=%.2e peer_overlap_err=%.2e"
+              % (world, e, h, h2, h3, fe, pe, po))
     dist.destroy_process_group()
 
 

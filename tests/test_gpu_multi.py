@@ -21,6 +21,18 @@ def test_data_parallel_and_halo_exchange_two_gpus():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_shot_peer_exchange_two_gpus():
+    """The reduce-scatter + pushed all-gather variant of the peer exchange (default from 4 ranks and 2 MB up), forced on
+    at world 2: same result as NCCL average + torch.optim.SGD, replicas bit-identical, also under the early/late overlap."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    env = dict(os.environ, TGCN_PEER_TWOSHOT="1", MGPU_ONLY="peer")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MGPU_PEER_OK world=2" in out.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_layers_under_torch_dataparallel():
     """the layers must also work under torch.nn.DataParallel (the reference's own multi-GPU mode,
     pytorch_hcp_tgcn.py:271-272): replicas run in threads, one per device, each with its own CSR operand."""

@@ -816,9 +816,11 @@ static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
     t.NB = (t.NBtot + t.NY - 1) / t.NY;                      // balance the y groups
     t.MT = (t.NB + 3) / 4;
     const size_t fixed = 1024 + 256;
+    int ru_max = 32;                                          // TGCN_T3_RU: experiment knob (rows per unit <= value)
+    if (const char* e = getenv("TGCN_T3_RU")) { const int v = atoi(e); if (v >= 8) ru_max = v; }
     for (int ru : {32, 16, 8}) {
         // a unit's rows must be whole vertices (its dOut box is [ru / Q vertices] x [Q samples]) unless Q > ru
-        if (ru % Q != 0) continue;
+        if (ru % Q != 0 || ru > ru_max) continue;
         const size_t blk = (size_t)ru * kRowBytes;
         const size_t stage = 2 * (size_t)t.NB * blk + 2 * (size_t)(t.GPw / 32) * blk;
         int ns = (int)((kT3SmemLimit - fixed - 4 * blk) / stage);       // 4 blocks of slack behind the last stage
