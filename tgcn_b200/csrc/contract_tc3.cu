@@ -549,6 +549,7 @@ struct BwdW3Params {
     int NB;                        // 32-wide (order, column block) pairs handled per CTA (grid.y splits the rest)
     int MT;                        // output tiles per CTA = ceil(NB / 4)
     int RU, NS, NI, units_per_cta, total_units;
+    int fused_a;                   // the NB blocks of a unit are NB orders of one column block: ONE tensor copy with a box of NB orders
 };
 
 __global__ void __launch_bounds__(kT3ThreadsF, 1)
@@ -600,9 +601,13 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(nb + gblocks) * blk);
                 const int m0 = u * p.RU;
-                for (int b = 0; b < nb; ++b) {
-                    const int gbk = blk0 + b, j = gbk / p.DB, db = gbk - j * p.DB;
-                    tma_load_3d(st + (size_t)b * blk, &tmA, db * 32, m0, j, &full[s]);
+                if (p.fused_a) {
+                    tma_load_3d(st, &tmA, 0, m0, blk0, &full[s]);          // box [32 x RU x NB orders] lands as NB consecutive blocks
+                } else {
+                    for (int b = 0; b < nb; ++b) {
+                        const int gbk = blk0 + b, j = gbk / p.DB, db = gbk - j * p.DB;
+                        tma_load_3d(st + (size_t)b * blk, &tmA, db * 32, m0, j, &full[s]);
+                    }
                 }
                 for (int gb = 0; gb < gblocks; ++gb)
                     tma_load_3d(st + 2 * (size_t)a_part + (size_t)gb * blk, &tmD, gb * 32, 0, m0 / p.Q, &full[s]);
@@ -856,9 +861,14 @@ int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, in
     BwdW3Params p{};
     p.partial = partial; p.M = (int)M; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GPw = t.GPw; p.K = K; p.DB = t.DB;
     p.NB = t.NB; p.MT = t.MT; p.RU = t.RU; p.NS = t.NS; p.NI = t.NI; p.units_per_cta = t.units_per_cta; p.total_units = t.total_units;
+    // One tensor copy per unit for the A operand when a unit's blocks are the K orders of a single column block (D = 32): the
+    // producer thread issued 10 + 1 copies per unit before, and the per-unit time hardly depended on the unit's size (RU = 32 /
+    // 16 / 8: 2.35 / 1.82 / 1.67 us per unit, profiles/r02/contract_tc3_notes.txt) -- the copy ISSUE was the pace of the kernel.
+    static const bool fuse_ok = [] { const char* e = getenv("TGCN_T3_FUSEA"); return !(e && e[0] == '0'); }();
+    p.fused_a = (fuse_ok && t.DB == 1 && t.NY == 1 && t.NB == K && K <= 256) ? 1 : 0;
     CUtensorMap tmA, tmD;
-    TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, (uint32_t)t.RU, 1,
-                              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, (uint32_t)t.RU,
+                              p.fused_a ? (uint32_t)K : 1u, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     // dOut[Q][N][G] addressed vertex-major: dimension 1 = sample (stride N*G), dimension 2 = vertex (stride G)
     TGCN_PROPAGATE(make_tmap3(&tmD, dout, (uint64_t)G, (uint64_t)Q, (uint64_t)N, (uint64_t)N * G * 4, (uint64_t)G * 4, 32, (uint32_t)Q,
                               (uint32_t)(t.RU / Q), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));

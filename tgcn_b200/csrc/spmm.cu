@@ -554,6 +554,12 @@ spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restr
         float4* ws = reinterpret_cast<float4*>(s_w[buf]);
         for (int i = tid; i < n * (R / 4); i += nthr) cp_async16(ws + i, wg + i);
     };
+    // Programmatic dependent launch (the host launches this kernel with the stream-serialization attribute): let the next
+    // kernel of the stream -- the next recursion step -- be scheduled as this grid's blocks retire, and fetch this block's
+    // first plan (static data) before waiting for the previous step's output: launch latency, ramp and the two dependent
+    // plan loads of the prologue overlap the previous step's tail.  Every read of `in` / `prev` and every write of `out`
+    // comes after griddepcontrol.wait.  (Both instructions are no-ops under a plain launch.)
+    asm volatile("griddepcontrol.launch_dependents;");
     fetch_tp(g, 0);
     fetch_tp(g + stride, 1);
     cp_async_wait_all();
@@ -561,6 +567,7 @@ spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restr
     fetch_plan(0, 0);
     cp_async_wait_all();
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const float4* inv = in + tx;
     for (int it = 0; g < ngroups; g += stride, ++it) {
         const int cur = it % 3, nxt = (it + 1) % 3, buf = it & 1;
@@ -633,6 +640,23 @@ spmm_step_rtile_pipe_kernel(const int* __restrict__ tile_ptr, const int* __restr
         cp_async_wait_all();
         __syncthreads();
     }
+}
+
+// Launch with programmatic stream serialization (see the kernel's prologue); TGCN_SPMM_PDL=0 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+static void launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("TGCN_SPMM_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in TGCN_LAUNCH_CHECK
 }
 
 // ---- row-tile plan registry: plans are created by the host side once per CSR operand and looked up by (device,
@@ -710,10 +734,10 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             const dim3 bdp((unsigned)V, (unsigned)TYp);
 #define TGCN_SPMM_RTP(RR, MB, UU, BB)                                                                                   \
             do {                                                                                                    \
-                if (prev) spmm_step_rtile_pipe_kernel<true, RR, MB, UU, BB><<<pgrid, bdp, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, \
-                                                                                          (const float4*)prev, (float4*)out, V, ntiles, ngroups, alpha, beta); \
-                else spmm_step_rtile_pipe_kernel<false, RR, MB, UU, BB><<<pgrid, bdp, 0, st>>>(rt.tile_ptr, rt.src, rt.w, N, (const float4*)in, nullptr, \
-                                                                                      (float4*)out, V, ntiles, ngroups, alpha, beta); \
+                if (prev) launch_dependent(spmm_step_rtile_pipe_kernel<true, RR, MB, UU, BB>, dim3(pgrid), bdp, st, rt.tile_ptr, rt.src, rt.w, N, \
+                                           (const float4*)in, (const float4*)prev, (float4*)out, V, ntiles, ngroups, alpha, beta); \
+                else launch_dependent(spmm_step_rtile_pipe_kernel<false, RR, MB, UU, BB>, dim3(pgrid), bdp, st, rt.tile_ptr, rt.src, rt.w, N, \
+                                      (const float4*)in, (const float4*)nullptr, (float4*)out, V, ntiles, ngroups, alpha, beta); \
             } while (0)
             if (rt.R == 8) TGCN_SPMM_RTP(8, 3, 2, 256); else if (small) TGCN_SPMM_RTP(4, 8, 8, 128); else TGCN_SPMM_RTP(4, 4, 8, 256);
 #undef TGCN_SPMM_RTP
