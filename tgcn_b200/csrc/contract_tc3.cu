@@ -549,7 +549,9 @@ struct BwdW3Params {
     int NB;                        // 32-wide (order, column block) pairs handled per CTA (grid.y splits the rest)
     int MT;                        // output tiles per CTA = ceil(NB / 4)
     int RU, NS, NI, units_per_cta, total_units;
-    int fused_a;                   // the NB blocks of a unit are NB orders of one column block: ONE tensor copy with a box of NB orders
+    int dpg;                       // > 0: blocks in column-block-major order, b = dbi * K + j for the dpg column blocks of this y group:
+                                   // the K orders of a column block arrive by ONE tensor copy (box of K orders); 0: order-major
+                                   // blocks (gbk = j * DB + db), one copy per block
 };
 
 __global__ void __launch_bounds__(kT3ThreadsF, 1)
@@ -569,8 +571,14 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const uint32_t stage_bytes = 2u * a_part + 2u * b_part;           // [A hi | A lo | B hi | B lo]
     const uint32_t accw = 2u * (uint32_t)p.GPw;
     const uint32_t ncols = tmem_cols_pow2((uint32_t)p.MT * accw);
-    const int blk0 = blockIdx.y * p.NB;                               // first (order, column block) pair of this CTA
-    const int nb = min(p.NB, p.K * p.DB - blk0);
+    const int blk0 = blockIdx.y * p.NB;                               // order-major: first (order, column block) pair of this CTA
+    const int db0 = blockIdx.y * p.dpg;                               // column-block-major: first column block of this CTA
+    const int nb = p.dpg > 0 ? min(p.dpg, p.DB - db0) * p.K : min(p.NB, p.K * p.DB - blk0);
+    // first row of block b in the [K * D] x G output
+    auto block_row0 = [&](int b) -> int {
+        if (p.dpg > 0) { const int dbi = b / p.K, j = b - dbi * p.K; return j * p.D + (db0 + dbi) * 32; }
+        return (blk0 + b) * 32;
+    };
     const int u_begin = blockIdx.x * p.units_per_cta;
     const int u_end = min(p.total_units, u_begin + p.units_per_cta);
     const int NS = p.NS, NI = p.NI;
@@ -601,8 +609,9 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(nb + gblocks) * blk);
                 const int m0 = u * p.RU;
-                if (p.fused_a) {
-                    tma_load_3d(st, &tmA, 0, m0, blk0, &full[s]);          // box [32 x RU x NB orders] lands as NB consecutive blocks
+                if (p.dpg > 0) {
+                    for (int dbi = 0; dbi * p.K < nb; ++dbi)               // box [32 x RU x K orders] lands as K consecutive blocks
+                        tma_load_3d(st + (size_t)dbi * p.K * blk, &tmA, (db0 + dbi) * 32, m0, 0, &full[s]);
                 } else {
                     for (int b = 0; b < nb; ++b) {
                         const int gbk = blk0 + b, j = gbk / p.DB, db = gbk - j * p.DB;
@@ -651,7 +660,7 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             for (int t = 0; t < p.MT; ++t) {
                 const int b = t * 4 + lq;                                  // block of this lane quarter
                 const bool ok = b < nb;
-                float* dst = dst_base + ((int64_t)(blk0 + b) * 32 + lane) * p.G;
+                float* dst = dst_base + ((int64_t)block_row0(ok ? b : 0) + lane) * p.G;
                 for (int cb = 0; cb < p.GPw; cb += 16) {
                     float v[16], w[16];
                     tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)t * accw + (uint32_t)cb, v);
@@ -665,7 +674,11 @@ contract_bwd_w_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
         } else {
             const int t0 = tid - kT3EpiWarp0 * 32;
-            for (int e = t0; e < nb * 32 * p.G; e += 128) dst_base[(int64_t)blk0 * 32 * p.G + e] = 0.f;
+            const int per_blk = 32 * p.G;
+            for (int e = t0; e < nb * per_blk; e += 128) {
+                const int b = e / per_blk;
+                dst_base[(int64_t)block_row0(b) * p.G + (e - b * per_blk)] = 0.f;
+            }
         }
     } else {
         // ===================== transform: lo parts of the A blocks and of the dOut blocks =====================
@@ -805,7 +818,7 @@ int contract_bwd_x_tc3(const float* dout, const uint8_t* wimg, float* gstack, in
     return TGCN_OK;
 }
 
-struct BwdW3Plan { bool ok; int GPw, DB, NBtot, NB, NY, MT, RU, NS, NI, P, units_per_cta, total_units; size_t smem; };
+struct BwdW3Plan { bool ok; int GPw, DB, NBtot, NB, NY, MT, RU, NS, NI, P, units_per_cta, total_units, dpg; size_t smem; };
 
 static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
     BwdW3Plan t{};
@@ -816,9 +829,23 @@ static BwdW3Plan make_bwd_w3_plan(int Q, int N, int D, int G, int K) {
     t.NBtot = K * t.DB;
     const int max_tiles = 512 / (2 * t.GPw);                 // TMEM columns: one [128 x 2 GPw] accumulator per output tile
     if (max_tiles < 1) return t;
-    t.NB = t.NBtot < 4 * max_tiles ? t.NBtot : 4 * max_tiles;
-    t.NY = (t.NBtot + t.NB - 1) / t.NB;
-    t.NB = (t.NBtot + t.NY - 1) / t.NY;                      // balance the y groups
+    // One tensor copy per (unit, column block) with a box of K orders when a y group can hold whole column blocks: the producer
+    // thread issued one copy per block before, and the per-unit time hardly depended on the unit's size (RU = 32 / 16 / 8: 2.35 /
+    // 1.82 / 1.67 us per unit, profiles/r02/contract_tc3_notes.txt) -- the copy ISSUE was the pace of the kernel.
+    static const bool fuse_ok = [] { const char* e = getenv("TGCN_T3_FUSEA"); return !(e && e[0] == '0'); }();
+    static const bool fuse_wide = [] { const char* e = getenv("TGCN_T3_FUSEA"); return !(e && e[0] == '1'); }();   // "1": D = 32 layers only
+    if (fuse_ok && K <= 4 * max_tiles && K <= 256 && (fuse_wide || t.DB == 1)) {
+        int dpg = (4 * max_tiles) / K;
+        if (dpg > t.DB) dpg = t.DB;
+        t.NY = (t.DB + dpg - 1) / dpg;
+        t.dpg = (t.DB + t.NY - 1) / t.NY;                    // balance the y groups
+        t.NB = K * t.dpg;
+    } else {
+        t.dpg = 0;
+        t.NB = t.NBtot < 4 * max_tiles ? t.NBtot : 4 * max_tiles;
+        t.NY = (t.NBtot + t.NB - 1) / t.NB;
+        t.NB = (t.NBtot + t.NY - 1) / t.NY;                  // balance the y groups
+    }
     t.MT = (t.NB + 3) / 4;
     const size_t fixed = 1024 + 256;
     int ru_max = 32;                                          // TGCN_T3_RU: experiment knob (rows per unit <= value)
@@ -861,14 +888,10 @@ int contract_bwd_w_tc3(const float* stack, const float* dout, float* partial, in
     BwdW3Params p{};
     p.partial = partial; p.M = (int)M; p.Q = Q; p.N = N; p.D = D; p.G = G; p.GPw = t.GPw; p.K = K; p.DB = t.DB;
     p.NB = t.NB; p.MT = t.MT; p.RU = t.RU; p.NS = t.NS; p.NI = t.NI; p.units_per_cta = t.units_per_cta; p.total_units = t.total_units;
-    // One tensor copy per unit for the A operand when a unit's blocks are the K orders of a single column block (D = 32): the
-    // producer thread issued 10 + 1 copies per unit before, and the per-unit time hardly depended on the unit's size (RU = 32 /
-    // 16 / 8: 2.35 / 1.82 / 1.67 us per unit, profiles/r02/contract_tc3_notes.txt) -- the copy ISSUE was the pace of the kernel.
-    static const bool fuse_ok = [] { const char* e = getenv("TGCN_T3_FUSEA"); return !(e && e[0] == '0'); }();
-    p.fused_a = (fuse_ok && t.DB == 1 && t.NY == 1 && t.NB == K && K <= 256) ? 1 : 0;
+    p.dpg = t.dpg;
     CUtensorMap tmA, tmD;
     TGCN_PROPAGATE(make_tmap3(&tmA, stack, (uint64_t)D, (uint64_t)M, (uint64_t)K, (uint64_t)D * 4, (uint64_t)M * D * 4, 32, (uint32_t)t.RU,
-                              p.fused_a ? (uint32_t)K : 1u, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+                              p.dpg > 0 ? (uint32_t)K : 1u, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     // dOut[Q][N][G] addressed vertex-major: dimension 1 = sample (stride N*G), dimension 2 = vertex (stride G)
     TGCN_PROPAGATE(make_tmap3(&tmD, dout, (uint64_t)G, (uint64_t)Q, (uint64_t)N, (uint64_t)N * G * 4, (uint64_t)G * 4, 32, (uint32_t)Q,
                               (uint32_t)(t.RU / Q), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
