@@ -627,13 +627,18 @@ def measure_roofline(lib, model, Q, H, dev, flush_buf):
                 "bytes_per_launch": int(compulsory), "bytes_formula": "compulsory DRAM bytes: x + pooled y + idx + saved basis + W + bias + CSR",
                 "unfused_bytes_formula": "SURVEY 8d B_fwd = (3K-4)S+(K-1)E+4QNG+4KHFG+4NG = %d" % unfused,
                 "us_per_launch": ms * 1e3, "peak_source": src}
-    stack = torch.randn(K, N, C, device=dev)
+    # the launch the layer really issues: slabs of Q * Dp columns (Dp = D padded to whole 128-byte blocks for the TMA-fed
+    # contraction, mesh layer 1: 30 -> 32); the ALGORITHMIC bytes stay those of the workload's own D
+    from tgcn_b200.nn.gcn import _ENGINE
+    Dp = int(lib.tgcn_layer_slab_width(Q, N, D, G, K, _ENGINE[lay.engine]))
+    Cp = Q * Dp
+    stack = torch.randn(K, N, Cp, device=dev)
 
     def steps():
         st = torch.cuda.current_stream().cuda_stream
         for k in range(1, K):
             lib.tgcn_spmm_step(plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.val.data_ptr(), N,
-                               stack[k - 1].data_ptr(), None, stack[k].data_ptr(), C, 1.0, 0.0, st)
+                               stack[k - 1].data_ptr(), None, stack[k].data_ptr(), Cp, 1.0, 0.0, st)
     per_launch_ms = _time_graph(steps, reps, flush_buf) / (K - 1)
     bytes_per_launch = algorithmic_step_bytes(N, C, plan.nnz, has_prev=False)
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
@@ -641,8 +646,9 @@ def measure_roofline(lib, model, Q, H, dev, flush_buf):
     kname = _rtile_kernel_name(tiles[0][2]["rows_per_tile"]) if tiles else "spmm_step_pipe_kernel"
     return {"bound": "hbm", "kernel": kname + " (layer-1 recursion step; K-1 launches per layer forward)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": _ncu_traffic(kname, "N%d_C%d" % (N, C)),
+            "traffic": _ncu_traffic(kname, "N%d_C%d" % (N, Cp)),
             "bytes_per_launch": int(bytes_per_launch), "bytes_formula": "SURVEY 8d per step: 2S + E (S = 4NC slab, E = 8 nnz + 4(N+1))",
+            "launched_columns": Cp, "algorithmic_columns": C,
             "us_per_launch": per_launch_ms * 1e3, "peak_source": src}
 
 
