@@ -629,8 +629,11 @@ def measure_roofline(lib, model, Q, H, dev, flush_buf):
                 "us_per_launch": ms * 1e3, "peak_source": src}
     # the launch the layer really issues: slabs of Q * Dp columns (Dp = D padded to whole 128-byte blocks for the TMA-fed
     # contraction, mesh layer 1: 30 -> 32); the ALGORITHMIC bytes stay those of the workload's own D
-    from tgcn_b200.nn.gcn import _ENGINE
-    Dp = int(lib.tgcn_layer_slab_width(Q, N, D, G, K, _ENGINE[lay.engine]))
+    try:
+        from tgcn_b200.nn.gcn import _ENGINE
+        Dp = max(D, int(lib.tgcn_layer_slab_width(Q, N, D, G, K, _ENGINE[lay.engine])))
+    except Exception:          # measurement code must not take the bench line down: fall back to the unpadded launch
+        Dp = D
     Cp = Q * Dp
     stack = torch.randn(K, N, Cp, device=dev)
 
