@@ -651,6 +651,8 @@ def measure_roofline(lib, model, Q, H, dev, flush_buf):
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": _ncu_traffic(kname, "N%d_C%d" % (N, Cp)),
             "bytes_per_launch": int(bytes_per_launch), "bytes_formula": "SURVEY 8d per step: 2S + E (S = 4NC slab, E = 8 nnz + 4(N+1))",
+            "traffic_note": "ncu dram bytes of one launch of this kernel at this shape (profiles/r02/ncu_traffic.json); slabs that fit "
+                            "the 126 MB L2 are still there when the next launch reads them, so traffic can be below the algorithmic bytes",
             "launched_columns": Cp, "algorithmic_columns": C,
             "us_per_launch": per_launch_ms * 1e3, "peak_source": src}
 
