@@ -857,11 +857,11 @@ basis_to_reference_kernel(const float* __restrict__ stack, float* __restrict__ X
 
 using namespace tgcn;
 
-// Host-side: distinct source rows per block of RB consecutive rows and block-local column ids.
-// blk_ptr_host[nb+1]; blk_rows_host: capacity = nnz (NULL: size query, returns the total); lcol_host[nnz].
-// At most `cap` rows are staged per block (the most referenced ones); entries whose source row is not staged get
-// the local id 0xFFFF and are gathered from global memory by the kernel.  Returns the total number of staged
-// (block, source row) pairs, or -1 on bad arguments.  *maxd_host receives the largest per-block count (<= cap).
+// Host-side row-tile plan (include/tgcn_b200.h): per tile of R consecutive rows the DISTINCT source rows in ascending order
+// (src_host) and, per source, the R coefficients it has in the rows of the tile (w_host, 0 where a row has no such entry;
+// duplicates within a row are summed).  tile_ptr_host[ceil(N / R) + 1].  src_host == w_host == NULL: size query.  pad > 1
+// rounds every non-empty tile up to a multiple of `pad` entries with zero-coefficient repeats of its last source.  Returns
+// the number of (tile, source) pairs, or -1 on bad arguments.
 extern "C" int64_t tgcn_rowtile_plan_host(const int32_t* rowptr_host, const int32_t* col_host, const float* val_host, int N,
                                           int R, int pad, int32_t* tile_ptr_host, int32_t* src_host, float* w_host) {
     if (N < 0 || (R != 4 && R != 8) || pad < 1 || pad > 16 || !rowptr_host || (rowptr_host[N] > 0 && (!col_host || !val_host))) return -1;
