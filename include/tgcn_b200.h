@@ -74,8 +74,8 @@ long long tgcn_launch_count(void);
  * "SPMM_CSM" = stage the CSR entries of a row block in shared memory (per-entry kernel), "SPMM_RTILE" = use
  * registered row-tile plans (2, the default: persistent plan-prefetching kernel for 4-row tiles, launched with
  * programmatic stream serialization -- TGCN_SPMM_PDL=0 in the environment turns that off; 1 = one-shot kernel;
- * 3 = persistent for 8-row tiles too, 128-thread blocks for 4-row tiles; 4/5/6/8 = one-shot kernel built for that
- * many blocks per SM; 0 = off), "RES_TC" = contraction of
+ * 3 = persistent for 8-row tiles too, 128-thread blocks for 4-row tiles; 4 = one-shot kernel, 8-row tiles built for 4
+ * blocks per SM; 0 = off), "RES_TC" = contraction of
  * the resident forward kernel on tcgen05 with 3xTF32 operands and TMEM accumulators (1) or on the fp32 FFMA pipe (0,
  * the default: measured faster at the resident shapes), "RES_ENT" = keep each thread's CSR entries in registers
  * across the K steps of the resident forward (bit-identical; 0 default).  The per-entry SpMM variants are

@@ -320,16 +320,15 @@ def test_register_tiled_spmm_through_the_layer():
     assert rel(x.grad.cpu().numpy(), dx) < 1e-4
 
 
-# SPMM_RTILE: the builds for 4/5/6/8 blocks per SM; 16 = the SM-contiguous block mapping experiment (ran once on a B200:
-# bit-identical output, 4 % slower; it has not been through this test on a GPU): opt in with TGCN_EXPERIMENTAL=1
-_RT_MODES = [1, 4, 5, 6, 8] + ([16] if os.environ.get("TGCN_EXPERIMENTAL") == "1" else [])
+# SPMM_RTILE values that select the one-shot row-tile kernel: 1 (default occupancy), 4 (8-row tiles built for 4 blocks per SM)
+_RT_MODES = [1, 4]
 
 
 @pytest.mark.parametrize("mode", _RT_MODES)
 @pytest.mark.parametrize("R", [4, 8])
 def test_register_tiled_spmm_long_plan_runs_walk_global_memory(R, mode):
     """Blocks whose tiles hold more (tile, source) pairs than the shared-memory stage (768) walk the plan in global
-    memory; a stretch of short rows IS staged.  Rows of 0, 1, 2, 3, 5 and ~150 entries, every occupancy build."""
+    memory; a stretch of short rows IS staged.  Rows of 0, 1, 2, 3, 5 and ~150 entries, both occupancy builds."""
     from tgcn_b200 import _lib
     from tgcn_b200.csr import build_csr
     import scipy.sparse as sp

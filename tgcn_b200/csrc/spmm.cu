@@ -703,7 +703,7 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
     TGCN_REQUIRE(in != out, "spmm_step: `in` must not alias `out`");
     const bool vec = (C % 4 == 0) && aligned16(in) && aligned16(out) && (prev == nullptr || aligned16(prev));
     // register-tiled row-tile kernels: whenever a row-tile plan is registered for this operand ("SPMM_RTILE": 0 = off,
-    // 1 = one-shot kernel, 2/3 = persistent kernel, 4/5/6/8 = one-shot kernel compiled for that many blocks per SM)
+    // 1 = one-shot kernel, 2/3 = persistent kernel, 4 = one-shot kernel with 4 blocks per SM also for 8-row tiles)
     RowTilePlan rt;
     const int rt_mode = tuning_value(kTuneSpmmRtile);
     if (vec && rt_mode != 0 && C / 4 <= 256 && find_rowtile_plan(col, N, &rt) &&
@@ -744,11 +744,11 @@ static int spmm_step(const int* rowptr, const int* col, const float* val, int N,
             TGCN_LAUNCH_CHECK("spmm_step");
             return TGCN_OK;
         }
+        // one-shot kernel (the 5 / 6 / 8 blocks-per-SM builds of round 1 measured no faster than 4 and were dropped)
         if (rt.R == 8) {
-            if (rt_mode >= 4 && rt_mode != 8) TGCN_SPMM_RT(8, 4); else TGCN_SPMM_RT(8, 3);
+            if (rt_mode == 4) TGCN_SPMM_RT(8, 4); else TGCN_SPMM_RT(8, 3);
         } else {
-            if (rt_mode >= 8) TGCN_SPMM_RT(4, 8); else if (rt_mode == 6) TGCN_SPMM_RT(4, 6);
-            else if (rt_mode == 5) TGCN_SPMM_RT(4, 5); else TGCN_SPMM_RT(4, 4);
+            TGCN_SPMM_RT(4, 4);
         }
 #undef TGCN_SPMM_RT
         TGCN_LAUNCH_CHECK("spmm_step");
